@@ -1,0 +1,414 @@
+// lbvh.cu -- deterministic LBVH build on the GPU; replaces optixAccelBuild + optixAccelCompact
+// (PathTracerMain.cpp:311-398), whose algorithm is closed.
+//
+// Pipeline (DESIGN.md "LBVH spec"; CPU statement of the same arithmetic: oracle/oracle_geom.h):
+//   tri_setup   per triangle: AABB, (v0,e1,e2) record, geometric normal; scene bounds by atomic min/max
+//               on order-preserving integer images of the floats (order-independent => deterministic)
+//   morton      30-bit Morton code of the AABB centre, normalised by the scene bounds
+//   radix sort  4 passes x 8 bits, LSD, STABLE (histogram -> exclusive scan -> ranked scatter with
+//               warp match/ballot ranks), values = primitive ids.  Input is in primitive order, so a stable
+//               sort by Morton code equals sorting the unique 64-bit keys morton<<32|prim: bit-exact.
+//   karras      binary radix tree over the sorted unique keys (Karras 2012) -- a pure function of the keys
+//   refit       bottom-up AABB union with per-node arrival counters (fmin/fmax are order-independent)
+//   pack        64-byte two-child nodes + 48-byte triangle records in leaf order
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "pt_device.cuh"
+#include "pt_scene.h"
+
+namespace ptb {
+
+using namespace ptd;
+
+// ---- order-preserving float <-> uint image ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// bounds[0..2] = min (ordered uint), bounds[3..5] = max
+__global__ void init_bounds_kernel(uint32_t* bounds)
+{
+    if (threadIdx.x < 3) bounds[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) tri_setup_kernel(const float4* __restrict__ verts, const uint32_t* __restrict__ indices,
+                                                        const uint32_t* __restrict__ mat_ids, uint32_t n_tris,
+                                                        float4* __restrict__ tri_in,      // 3 per primitive
+                                                        float4* __restrict__ tri_bb,      // 2 per primitive (lo, hi)
+                                                        float4* __restrict__ tri_shade,   // (N_0, material)
+                                                        uint32_t* __restrict__ bounds)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
+    if (k < n_tris) {
+        const float4 a = verts[indices[3 * k + 0]];
+        const float4 b = verts[indices[3 * k + 1]];
+        const float4 c = verts[indices[3 * k + 2]];
+        const float3 v0 = f3(a.x, a.y, a.z), v1 = f3(b.x, b.y, b.z), v2 = f3(c.x, c.y, c.z);
+        const float3 e1 = v1 - v0, e2 = v2 - v0;
+        lo = f3(fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z));
+        hi = f3(fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z));
+        const uint32_t mat = mat_ids[k];
+        tri_in[3 * k + 0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(k));
+        tri_in[3 * k + 1] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(mat));
+        tri_in[3 * k + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+        tri_bb[2 * k + 0] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        tri_bb[2 * k + 1] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+        // pathTracerPrograms.cu:891  N_0 = normalize(cross(v1 - v0, v2 - v0))
+        const float3 n0 = normalize(cross(e1, e2));
+        tri_shade[k] = make_float4(n0.x, n0.y, n0.z, __uint_as_float(mat));
+    }
+    // block reduction of the bounds (min/max: any order gives the same bits)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, off));
+        lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, off));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, off));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, off));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, off));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&bounds[0], float_to_ordered(lo.x));
+        atomicMin(&bounds[1], float_to_ordered(lo.y));
+        atomicMin(&bounds[2], float_to_ordered(lo.z));
+        atomicMax(&bounds[3], float_to_ordered(hi.x));
+        atomicMax(&bounds[4], float_to_ordered(hi.y));
+        atomicMax(&bounds[5], float_to_ordered(hi.z));
+    }
+}
+
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v)
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) morton_kernel(const float4* __restrict__ tri_bb, uint32_t n_tris,
+                                                     const uint32_t* __restrict__ bounds, uint32_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ vals, float* __restrict__ bounds_f)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const float3 slo = f3(ordered_to_float(bounds[0]), ordered_to_float(bounds[1]), ordered_to_float(bounds[2]));
+    const float3 shi = f3(ordered_to_float(bounds[3]), ordered_to_float(bounds[4]), ordered_to_float(bounds[5]));
+    if (k == 0) {
+        bounds_f[0] = slo.x; bounds_f[1] = slo.y; bounds_f[2] = slo.z;
+        bounds_f[3] = shi.x; bounds_f[4] = shi.y; bounds_f[5] = shi.z;
+    }
+    if (k >= n_tris) return;
+    const float3 e = shi - slo;
+    const float3 inv = f3(e.x > 0.0f ? 1.0f / e.x : 0.0f, e.y > 0.0f ? 1.0f / e.y : 0.0f, e.z > 0.0f ? 1.0f / e.z : 0.0f);
+    const float4 lo = tri_bb[2 * k + 0];
+    const float4 hi = tri_bb[2 * k + 1];
+    const float cx = (lo.x + hi.x) * 0.5f, cy = (lo.y + hi.y) * 0.5f, cz = (lo.z + hi.z) * 0.5f;
+    const float nx = (cx - slo.x) * inv.x, ny = (cy - slo.y) * inv.y, nz = (cz - slo.z) * inv.z;
+    const uint32_t qx = (uint32_t)fminf(fmaxf(nx * 1024.0f, 0.0f), 1023.0f);
+    const uint32_t qy = (uint32_t)fminf(fmaxf(ny * 1024.0f, 0.0f), 1023.0f);
+    const uint32_t qz = (uint32_t)fminf(fmaxf(nz * 1024.0f, 0.0f), 1023.0f);
+    keys[k] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz);
+    vals[k] = k;
+}
+
+// ---- stable LSD radix sort, 8-bit digits ---------------------------------------------------------------------
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;                               // per thread
+constexpr int kSortTile = kSortThreads * kSortItems;        // 2048 keys per block
+constexpr int kSortWarps = kSortThreads / 32;
+
+// block_hist[digit * n_blocks + block]
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift,
+                                                                 uint32_t* __restrict__ block_hist, uint32_t n_blocks)
+{
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t i = base + j * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    block_hist[threadIdx.x * n_blocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+// exclusive scan of `count` uint32 in place, single block of 1024 threads
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ data, uint32_t count)
+{
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < count; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < count ? data[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t s = warp_sums[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, s, off);
+                if (lane >= off) s += y;
+            }
+            warp_sums[lane] = s;   // inclusive
+        }
+        __syncthreads();
+        const uint32_t warp_off = warp > 0 ? warp_sums[warp - 1] : 0u;
+        const uint32_t incl = x + warp_off + carry;
+        if (i < count) data[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+
+// Ranked, stable scatter.  Warp w of a block owns the contiguous chunk [w*256, (w+1)*256) of the block's
+// tile and walks it in rounds of 32 consecutive keys, so (block, warp, round, lane) is the input order.
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                    const uint32_t* __restrict__ vals_in,
+                                                                    uint32_t* __restrict__ keys_out,
+                                                                    uint32_t* __restrict__ vals_out, uint32_t n, int shift,
+                                                                    const uint32_t* __restrict__ block_base, uint32_t n_blocks)
+{
+    __shared__ uint32_t warp_count[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = threadIdx.x; d < kSortWarps * 256; d += kSortThreads) (&warp_count[0][0])[d] = 0;
+    __syncthreads();
+    const uint32_t chunk = blockIdx.x * kSortTile + warp * (32 * kSortItems);
+    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t i = chunk + j * 32 + lane;
+        const bool valid = i < n;
+        key[j] = valid ? keys_in[i] : 0xffffffffu;
+        val[j] = valid ? vals_in[i] : 0u;
+        const uint32_t digit = (key[j] >> shift) & 255u;
+        // peers: valid lanes with the same digit (invalid lanes form their own group via bit 8)
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 256u);
+        const uint32_t before = __popc(peers & lt_mask);
+        uint32_t base = 0;
+        if (valid) base = warp_count[warp][digit];
+        __syncwarp();
+        if (valid && before == 0) warp_count[warp][digit] = base + __popc(peers);
+        __syncwarp();
+        rank[j] = base + before;
+    }
+    __syncthreads();
+    // exclusive prefix over warps for each digit (thread d handles digit d), then add the global base
+    {
+        const int d = threadIdx.x;
+        uint32_t run = block_base[d * n_blocks + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = warp_count[w][d];
+            warp_count[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kSortItems; ++j) {
+        const uint32_t i = chunk + j * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (key[j] >> shift) & 255u;
+            const uint32_t pos = warp_count[warp][digit] + rank[j];
+            keys_out[pos] = key[j];
+            vals_out[pos] = val[j];
+        }
+    }
+}
+
+// ---- Karras 2012 radix tree -------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta64(const uint32_t* __restrict__ mort, const uint32_t* __restrict__ prim, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = ((unsigned long long)mort[i] << 32) | prim[i];
+    const unsigned long long b = ((unsigned long long)mort[j] << 32) | prim[j];
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void __launch_bounds__(256) karras_kernel(const uint32_t* __restrict__ mort, const uint32_t* __restrict__ prim, int n,
+                                                     int* __restrict__ left, int* __restrict__ right,
+                                                     int* __restrict__ node_parent, int* __restrict__ leaf_parent)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta64(mort, prim, n, i, i + 1) - delta64(mort, prim, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta64(mort, prim, n, i, i - d);
+    int lmax = 2;
+    while (delta64(mort, prim, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta64(mort, prim, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta64(mort, prim, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta64(mort, prim, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int lref = (lo == gamma) ? ~gamma : gamma;
+    const int rref = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    left[i] = lref;
+    right[i] = rref;
+    if (lref >= 0) node_parent[lref] = i; else leaf_parent[~lref] = i;
+    if (rref >= 0) node_parent[rref] = i; else leaf_parent[~rref] = i;
+    if (i == 0) node_parent[0] = -1;
+}
+
+// ---- bottom-up refit ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) refit_kernel(int n, const int* __restrict__ left, const int* __restrict__ right,
+                                                    const int* __restrict__ node_parent, const int* __restrict__ leaf_parent,
+                                                    const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ tri_bb,
+                                                    float4* node_lo, float4* node_hi, uint32_t* __restrict__ visit)
+{
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (leaf >= n) return;
+    int cur = leaf_parent[leaf];
+    while (cur >= 0) {
+        // the second arrival at a node sees both children complete
+        __threadfence();
+        if (atomicAdd(&visit[cur], 1u) == 0u) return;
+        __threadfence();
+        float4 lo[2], hi[2];
+        const int c[2] = {left[cur], right[cur]};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (c[s] < 0) {
+                const uint32_t p = sorted_prim[~c[s]];
+                lo[s] = tri_bb[2 * p + 0];
+                hi[s] = tri_bb[2 * p + 1];
+            } else {
+                lo[s] = __ldcg(&node_lo[c[s]]);
+                hi[s] = __ldcg(&node_hi[c[s]]);
+            }
+        }
+        __stcg(&node_lo[cur], make_float4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.0f));
+        __stcg(&node_hi[cur], make_float4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.0f));
+        cur = node_parent[cur];
+    }
+}
+
+// ---- pack -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_nodes_kernel(int n_internal, const int* __restrict__ left, const int* __restrict__ right,
+                                                         const uint32_t* __restrict__ sorted_prim, const float4* __restrict__ tri_bb,
+                                                         const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                                                         float4* __restrict__ nodes)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    float4 lo[2], hi[2];
+    const int c[2] = {left[i], right[i]};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (c[s] < 0) {
+            const uint32_t p = sorted_prim[~c[s]];
+            lo[s] = tri_bb[2 * p + 0];
+            hi[s] = tri_bb[2 * p + 1];
+        } else {
+            lo[s] = node_lo[c[s]];
+            hi[s] = node_hi[c[s]];
+        }
+    }
+    nodes[4 * i + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(c[0]));
+    nodes[4 * i + 1] = make_float4(hi[0].x, hi[0].y, hi[0].z, __int_as_float(c[1]));
+    nodes[4 * i + 2] = make_float4(lo[1].x, lo[1].y, lo[1].z, 0.0f);
+    nodes[4 * i + 3] = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.0f);
+}
+
+__global__ void __launch_bounds__(256) pack_tris_kernel(uint32_t n, const uint32_t* __restrict__ sorted_prim,
+                                                        const float4* __restrict__ tri_in, float4* __restrict__ tris)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = sorted_prim[i];
+    tris[3 * i + 0] = tri_in[3 * p + 0];
+    tris[3 * i + 1] = tri_in[3 * p + 1];
+    tris[3 * i + 2] = tri_in[3 * p + 2];
+}
+
+// single triangle: one node whose two children are the same leaf
+__global__ void single_node_kernel(const float4* __restrict__ tri_bb, float4* __restrict__ nodes, int* node_parent)
+{
+    const float4 lo = tri_bb[0], hi = tri_bb[1];
+    nodes[0] = make_float4(lo.x, lo.y, lo.z, __int_as_float(~0));
+    nodes[1] = make_float4(hi.x, hi.y, hi.z, __int_as_float(~0));
+    nodes[2] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+    nodes[3] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    node_parent[0] = -1;
+}
+
+#define PTB_CUDA_TRY(expr)                  \
+    do {                                    \
+        cudaError_t e__ = (expr);           \
+        if (e__ != cudaSuccess) return e__; \
+    } while (0)
+
+static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+
+// Builds every device array of `s` from the uploaded inputs.  All work is enqueued on `stream`.
+cudaError_t lbvh_build(Scene& s, cudaStream_t stream)
+{
+    const uint32_t n = s.n_tris;
+    if (n == 0) return cudaSuccess;
+    const unsigned g = div_up(n, 256);
+    init_bounds_kernel<<<1, 32, 0, stream>>>(s.d_bounds_ordered);
+    tri_setup_kernel<<<g, 256, 0, stream>>>(s.d_verts, s.d_indices, s.d_mat_ids, n, s.d_tri_in, s.d_tri_bb, s.d_tri_shade,
+                                            s.d_bounds_ordered);
+    morton_kernel<<<g, 256, 0, stream>>>(s.d_tri_bb, n, s.d_bounds_ordered, s.d_keys[0], s.d_vals[0], s.d_bounds);
+    PTB_CUDA_TRY(cudaMemcpyAsync(s.d_morton, s.d_keys[0], sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream));
+    const uint32_t n_blocks = div_up(n, kSortTile);
+    int src = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        sort_hist_kernel<<<n_blocks, kSortThreads, 0, stream>>>(s.d_keys[src], n, shift, s.d_block_hist, n_blocks);
+        scan_kernel<<<1, 1024, 0, stream>>>(s.d_block_hist, 256u * n_blocks);
+        sort_scatter_kernel<<<n_blocks, kSortThreads, 0, stream>>>(s.d_keys[src], s.d_vals[src], s.d_keys[src ^ 1],
+                                                                  s.d_vals[src ^ 1], n, shift, s.d_block_hist, n_blocks);
+        src ^= 1;
+    }
+    // after 4 passes the sorted data is back in buffer 0
+    s.sorted_buf = src;
+    const uint32_t* mort = s.d_keys[src];
+    const uint32_t* prim = s.d_vals[src];
+    if (n == 1) {
+        single_node_kernel<<<1, 1, 0, stream>>>(s.d_tri_bb, s.d_nodes, s.d_node_parent);
+    } else {
+        karras_kernel<<<div_up(n - 1, 256), 256, 0, stream>>>(mort, prim, (int)n, s.d_left, s.d_right, s.d_node_parent,
+                                                             s.d_leaf_parent);
+        PTB_CUDA_TRY(cudaMemsetAsync(s.d_visit, 0, sizeof(uint32_t) * (n - 1), stream));
+        refit_kernel<<<g, 256, 0, stream>>>((int)n, s.d_left, s.d_right, s.d_node_parent, s.d_leaf_parent, prim, s.d_tri_bb,
+                                            s.d_node_lo, s.d_node_hi, s.d_visit);
+        pack_nodes_kernel<<<div_up(n - 1, 256), 256, 0, stream>>>((int)n - 1, s.d_left, s.d_right, prim, s.d_tri_bb, s.d_node_lo,
+                                                                 s.d_node_hi, s.d_nodes);
+    }
+    pack_tris_kernel<<<g, 256, 0, stream>>>(n, prim, s.d_tri_in, s.d_tris);
+    return cudaGetLastError();
+}
+
+}  // namespace ptb

@@ -1,0 +1,252 @@
+// pt_device.cuh -- device-side building blocks shared by the LBVH build and the render kernels:
+// float3 helpers with the reference's rounding order, the reference's RNG, and the intersection spec.
+//
+// The library is compiled with -fmad=false: the compiler never fuses a*b+c, so plain C++ float
+// expressions below round exactly like the reference source does under IEEE rules (and like the CPU
+// oracle compiled with -ffp-contract=off).  Where a fused multiply-add is part of OUR spec (ray/box,
+// ray/triangle -- arithmetic the reference leaves to the OptiX driver) it is written as __fmaf_rn.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pt_detmath.h"
+
+namespace ptd {
+
+// ---- float3 helpers: sutil/vec_math.h semantics (operation order matters) -------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 f3(float s) { return make_float3(s, s, s); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }   // vec_math.h:479
+__device__ __forceinline__ float3 div_by_scalar(float3 a, float s)      // vec_math.h:483-487: multiply by reciprocal
+{
+    float inv = 1.0f / s;
+    return a * inv;
+}
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }            // :527
+__device__ __forceinline__ float3 cross(float3 a, float3 b)                                                        // :533
+{
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float length(float3 v) { return sqrtf(dot(v, v)); }                                     // :539
+__device__ __forceinline__ float3 normalize(float3 v)                                                              // :545
+{
+    float invLen = 1.0f / sqrtf(dot(v, v));
+    return v * invLen;
+}
+__device__ __forceinline__ float3 reflect(float3 i, float3 n) { return i - (2.0f * n) * dot(n, i); }               // :558
+__device__ __forceinline__ float clampf(float f, float a, float b) { return fmaxf(a, fminf(f, b)); }               // :114
+
+// ---- RNG: cuda/random.h ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tea4(uint32_t val0, uint32_t val1)      // random.h:32-46, N = 4
+{
+    uint32_t v0 = val0, v1 = val1, s0 = 0;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v0;
+}
+__device__ __forceinline__ float rnd(uint32_t& prev)                        // random.h:49-67
+{
+    prev = 1664525u * prev + 1013904223u;
+    // (float)(prev & 0xffffff) / 2^24: both exact, so a multiply by 2^-24 is the same value
+    return (float)(prev & 0x00ffffffu) * 5.9604644775390625e-8f;
+}
+
+// ---- acceleration-structure records (DESIGN.md "LBVH spec") ---------------------------------------------------
+// Node, 64 B = 4 x float4:  q0 = (lo0.xyz, child0)  q1 = (hi0.xyz, child1)  q2 = (lo1.xyz, 0)  q3 = (hi1.xyz, 0)
+//   child >= 0: internal node index; child < 0: leaf, ~child = slot in the leaf-ordered triangle array.
+// Triangle, 48 B = 3 x float4: t0 = (v0.xyz, primIdx)  t1 = (e1.xyz, materialId)  t2 = (e2.xyz, 0),  e1 = v1-v0, e2 = v2-v0.
+struct BvhView {
+    const float4* nodes;   // 4 per node
+    const float4* tris;    // 3 per leaf
+    uint32_t n_tris;
+};
+
+// SMEM = true: the records live in shared memory (plain LDS); false: global memory through the read-only path.
+template <bool SMEM>
+__device__ __forceinline__ float4 ld4(const float4* p)
+{
+    if (SMEM) return *p;
+    return __ldg(p);
+}
+
+struct Ray {
+    float3 o, d;
+    float3 inv, ood;   // 1/d (|d| clamped away from 0) and o*inv
+};
+
+__device__ __forceinline__ float safe_inv(float d)
+{
+    float dd = fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d);
+    return 1.0f / dd;
+}
+
+__device__ __forceinline__ Ray make_ray(float3 o, float3 d)
+{
+    Ray r;
+    r.o = o;
+    r.d = d;
+    r.inv = f3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    r.ood = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
+    return r;
+}
+
+// Slab test against one child box; far bound padded by 2 ulp.  Returns hit, writes entry distance.
+__device__ __forceinline__ bool ray_box(const Ray& r, float3 lo, float3 hi, float tmin, float tfar, float& tnear)
+{
+    float t0x = __fmaf_rn(lo.x, r.inv.x, -r.ood.x), t1x = __fmaf_rn(hi.x, r.inv.x, -r.ood.x);
+    float t0y = __fmaf_rn(lo.y, r.inv.y, -r.ood.y), t1y = __fmaf_rn(hi.y, r.inv.y, -r.ood.y);
+    float t0z = __fmaf_rn(lo.z, r.inv.z, -r.ood.z), t1z = __fmaf_rn(hi.z, r.inv.z, -r.ood.z);
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), tmin));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tfar));
+    tnear = tn;
+    return tn <= tf * 1.0000004f;
+}
+
+__device__ __forceinline__ float fms(float a, float b, float c, float d) { return __fmaf_rn(a, b, -(c * d)); }
+__device__ __forceinline__ float dot_fma(float3 a, float3 b) { return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, a.z * b.z)); }
+
+// Moeller-Trumbore on a (v0, e1, e2) record, both sides, tmin < t < tmax.
+__device__ __forceinline__ bool ray_tri(const Ray& r, float3 v0, float3 e1, float3 e2, float tmin, float tmax, float& t_out)
+{
+    float3 p = f3(fms(r.d.y, e2.z, r.d.z, e2.y), fms(r.d.z, e2.x, r.d.x, e2.z), fms(r.d.x, e2.y, r.d.y, e2.x));
+    float det = dot_fma(e1, p);
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    float3 tv = f3(r.o.x - v0.x, r.o.y - v0.y, r.o.z - v0.z);
+    float u = dot_fma(tv, p) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    float3 q = f3(fms(tv.y, e1.z, tv.z, e1.y), fms(tv.z, e1.x, tv.x, e1.z), fms(tv.x, e1.y, tv.y, e1.x));
+    float v = dot_fma(r.d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    float t = dot_fma(e2, q) * inv;
+    if (!(t > tmin && t < tmax)) return false;
+    t_out = t;
+    return true;
+}
+
+struct TraceCount {
+    uint32_t n_node, n_tri;
+};
+
+constexpr int kStackSize = 64;   // >= depth of a radix tree over 62-bit unique keys
+
+// Closest hit under the total order (t, primIdx).  Logical visiting order (mirrored by the oracle, which
+// matters only for the work counters): nearer hit child first, child 1 only when strictly nearer.
+template <bool COUNT, bool SMEM>
+__device__ __forceinline__ bool trace_closest(const BvhView& bvh, float3 o, float3 d, float tmin, float tmax,
+                                              float& t_hit, uint32_t& prim_hit, uint32_t& leaf_hit, TraceCount& tc)
+{
+    float best_t = tmax;
+    uint32_t best_prim = 0xffffffffu;
+    uint32_t best_leaf = 0xffffffffu;
+    if (bvh.n_tris == 0) return false;
+    const Ray r = make_ray(o, d);
+    int stack[kStackSize];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            const float4 q0 = ld4<SMEM>(bvh.nodes + 4 * cur + 0);
+            const float4 q1 = ld4<SMEM>(bvh.nodes + 4 * cur + 1);
+            const float4 q2 = ld4<SMEM>(bvh.nodes + 4 * cur + 2);
+            const float4 q3 = ld4<SMEM>(bvh.nodes + 4 * cur + 3);
+            if (COUNT) tc.n_node++;
+            float tn0, tn1;
+            const bool h0 = ray_box(r, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), tmin, best_t, tn0);
+            const bool h1 = ray_box(r, f3(q2.x, q2.y, q2.z), f3(q3.x, q3.y, q3.z), tmin, best_t, tn1);
+            const int c0 = __float_as_int(q0.w), c1 = __float_as_int(q1.w);
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;
+                stack[sp++] = swap ? c0 : c1;
+                cur = swap ? c1 : c0;
+                continue;
+            } else if (h0) {
+                cur = c0;
+                continue;
+            } else if (h1) {
+                cur = c1;
+                continue;
+            }
+        } else {
+            const int leaf = ~cur;
+            const float4 t0 = ld4<SMEM>(bvh.tris + 3 * leaf + 0);
+            const float4 t1 = ld4<SMEM>(bvh.tris + 3 * leaf + 1);
+            const float4 t2 = ld4<SMEM>(bvh.tris + 3 * leaf + 2);
+            if (COUNT) tc.n_tri++;
+            float t;
+            if (ray_tri(r, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), tmin, tmax, t)) {
+                const uint32_t prim = __float_as_uint(t0.w);
+                if (t < best_t || (t == best_t && prim < best_prim)) {
+                    best_t = t;
+                    best_prim = prim;
+                    best_leaf = (uint32_t)leaf;
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    t_hit = best_t;
+    prim_hit = best_prim;
+    leaf_hit = best_leaf;
+    return best_prim != 0xffffffffu;
+}
+
+// Any hit in (tmin, tmax): boolean, order-free.
+template <bool COUNT, bool SMEM>
+__device__ __forceinline__ bool trace_any(const BvhView& bvh, float3 o, float3 d, float tmin, float tmax, TraceCount& tc)
+{
+    if (bvh.n_tris == 0) return false;
+    const Ray r = make_ray(o, d);
+    int stack[kStackSize];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        if (cur >= 0) {
+            const float4 q0 = ld4<SMEM>(bvh.nodes + 4 * cur + 0);
+            const float4 q1 = ld4<SMEM>(bvh.nodes + 4 * cur + 1);
+            const float4 q2 = ld4<SMEM>(bvh.nodes + 4 * cur + 2);
+            const float4 q3 = ld4<SMEM>(bvh.nodes + 4 * cur + 3);
+            if (COUNT) tc.n_node++;
+            float tn0, tn1;
+            const bool h0 = ray_box(r, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), tmin, tmax, tn0);
+            const bool h1 = ray_box(r, f3(q2.x, q2.y, q2.z), f3(q3.x, q3.y, q3.z), tmin, tmax, tn1);
+            const int c0 = __float_as_int(q0.w), c1 = __float_as_int(q1.w);
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;
+                stack[sp++] = swap ? c0 : c1;
+                cur = swap ? c1 : c0;
+                continue;
+            } else if (h0) {
+                cur = c0;
+                continue;
+            } else if (h1) {
+                cur = c1;
+                continue;
+            }
+        } else {
+            const int leaf = ~cur;
+            const float4 t0 = ld4<SMEM>(bvh.tris + 3 * leaf + 0);
+            const float4 t1 = ld4<SMEM>(bvh.tris + 3 * leaf + 1);
+            const float4 t2 = ld4<SMEM>(bvh.tris + 3 * leaf + 2);
+            if (COUNT) tc.n_tri++;
+            float t;
+            if (ray_tri(r, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), tmin, tmax, t)) return true;
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return false;
+}
+
+}  // namespace ptd

@@ -1,0 +1,93 @@
+// pt_scene.h -- host-side scene object behind the opaque pt_scene handle (include/ptb200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ptb200.h"
+
+namespace ptd {
+struct DevMaterial;
+struct LaunchConst;
+}
+
+namespace ptb {
+
+constexpr uint64_t kSceneMagic = 0x5054423230305343ull;   // "PTB200SC"
+
+struct Scene {
+    uint64_t magic = kSceneMagic;
+    int device = 0;
+    uint32_t n_verts = 0, n_tris = 0, n_mats = 0, n_nodes = 0;
+    float background[3] = {0.f, 0.f, 0.f};
+    float build_ms = 0.f;
+    int pipeline = 0;              // 0 auto, 1 persistent thread-per-path, 2 CTA-local wavefront
+    bool count_enabled = false;
+
+    // inputs (device copies of the TinyObjWrapper arrays)
+    float4* d_verts = nullptr;
+    uint32_t* d_indices = nullptr;
+    uint32_t* d_mat_ids = nullptr;
+    ptd::DevMaterial* d_mats = nullptr;
+
+    // LBVH build products
+    float4* d_tri_in = nullptr;       // 3 per primitive (primitive order)
+    float4* d_tri_bb = nullptr;       // 2 per primitive
+    float4* d_tri_shade = nullptr;    // (N_0, material) per primitive
+    uint32_t* d_bounds_ordered = nullptr;   // 6
+    float* d_bounds = nullptr;        // 6
+    uint32_t* d_morton = nullptr;     // primitive order
+    uint32_t* d_keys[2] = {nullptr, nullptr};
+    uint32_t* d_vals[2] = {nullptr, nullptr};
+    int sorted_buf = 0;
+    uint32_t* d_block_hist = nullptr;
+    int* d_left = nullptr;
+    int* d_right = nullptr;
+    int* d_node_parent = nullptr;
+    int* d_leaf_parent = nullptr;
+    uint32_t* d_visit = nullptr;
+    float4* d_node_lo = nullptr;
+    float4* d_node_hi = nullptr;
+    float4* d_nodes = nullptr;        // 4 per node
+    float4* d_tris = nullptr;         // 3 per leaf (leaf order)
+
+    // launch-time scratch
+    uint32_t* d_work_counter = nullptr;
+    unsigned long long* d_counters = nullptr;   // pt_counters layout (10 x u64)
+    float4* d_stage_accum = nullptr;            // pt_launch_host staging
+    uchar4* d_stage_frame = nullptr;
+    size_t stage_pixels = 0;
+    void* d_wf_state = nullptr;                 // pipeline 2 scratch (wavefront.cu)
+    size_t wf_state_bytes = 0;
+
+    // last launch
+    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0;
+};
+
+// lbvh.cu
+cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
+
+// render.cu
+cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint32_t n_ranks, cudaStream_t stream,
+                          const ptd::LaunchConst* probe_overrides);
+cudaError_t trace_rays_device(Scene& s, const float* d_org, const float* d_dir, const float* d_tmin, const float* d_tmax,
+                              uint64_t n, int32_t* d_prim, float* d_t, uint8_t* d_any, unsigned long long* d_counters2,
+                              cudaStream_t stream);
+cudaError_t partition_pack(const void* accum_full, const void* frame_full, void* accum_compact, void* frame_compact,
+                           uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks, cudaStream_t stream);
+cudaError_t partition_unpack(const void* accum_compact_all, const void* frame_compact_all, void* accum_full,
+                             void* frame_full, uint32_t width, uint32_t height, uint32_t n_ranks, cudaStream_t stream);
+uint32_t partition_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks);
+uint32_t partition_max_owned_tiles(uint32_t width, uint32_t height, uint32_t n_ranks);
+
+// microbench.cu
+cudaError_t bench_fp32_peak(double* tflops);
+cudaError_t bench_l2_bandwidth(double* gbps);
+cudaError_t bench_hbm_bandwidth(double* gbps);
+
+// error plumbing (capi.cu)
+void set_error(const std::string& msg);
+
+}  // namespace ptb

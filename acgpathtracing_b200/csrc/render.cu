@@ -1,0 +1,381 @@
+// render.cu -- the render kernels: what optixLaunch(width, height, 1) runs in the reference
+// (__raygen__rg / __closesthit__diffuse__ch / __miss__ms, pathTracerPrograms.cu:707-1031), re-designed for
+// sm_100a without OptiX.
+//
+// Pipeline 1, "persistent path state machine" (this file's render_persistent_kernel):
+//   * one resident warp per SM sub-partition slot, grid = SMs x occupancy; warps pull 8x4-pixel tiles from a
+//     global counter (dynamic load balance), one lane = one pixel;
+//   * a lane keeps ONE path in flight and regenerates the pixel's next sample in place when the path ends,
+//     so the per-pixel float sums run in the reference's order (samples in sequence, segments in path order)
+//     and warps stay full until a pixel has used all its samples;
+//   * the whole scene (64-B BVH nodes, 48-B triangles, normals, materials) is staged into shared memory when
+//     it fits (Cornell box: 4 KB), else read through the read-only path from L1/L2.
+// Pipeline 2 (CTA-local wavefront with compacted queues) lives in wavefront.cu.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pt_scene.h"
+#include "pt_shade.cuh"
+
+namespace ptb {
+
+using namespace ptd;
+
+constexpr int kBlock = 256;
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr size_t kSmemSceneLimit = 40 * 1024;   // stage the scene in shared memory up to this size
+
+struct ThreadCounters {
+    uint32_t n_samples, n_radiance, n_shadow, n_node, n_tri, n_hit0, n_hit1, n_hit2, n_miss;
+};
+
+__device__ __forceinline__ void flush_counter(unsigned long long* dst, uint32_t v)
+{
+    unsigned long long x = v;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(kFull, x, off);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(dst, x);
+}
+
+__device__ __forceinline__ float safe_divide(float a, float b) { return b == 0.0f ? 0.0f : a / b; }   // :265-284
+
+// Scene bytes when staged: nodes | tris | tri_shade | materials (all float4)
+__host__ __device__ inline size_t staged_scene_float4s(uint32_t n_nodes, uint32_t n_tris, uint32_t n_mats)
+{
+    return 4 * (size_t)n_nodes + 3 * (size_t)n_tris + (size_t)n_tris + 3 * (size_t)n_mats;
+}
+
+template <bool COUNT, bool PROBE, bool SMEM>
+__global__ void __launch_bounds__(kBlock, 2) render_persistent_kernel(const __grid_constant__ LaunchConst lc)
+{
+    extern __shared__ float4 smem4[];
+    BvhView bvh = lc.bvh;
+    const float4* tri_shade = lc.tri_shade;
+    const float4* mats = reinterpret_cast<const float4*>(lc.mats);
+    if (SMEM) {
+        const uint32_t n_nodes4 = 4 * lc.n_nodes, n_tris4 = 3 * lc.bvh.n_tris, n_sh = lc.bvh.n_tris, n_m4 = 3 * lc.n_mats;
+        float4* s_nodes = smem4;
+        float4* s_tris = s_nodes + n_nodes4;
+        float4* s_shade = s_tris + n_tris4;
+        float4* s_mats = s_shade + n_sh;
+        for (uint32_t i = threadIdx.x; i < n_nodes4; i += kBlock) s_nodes[i] = __ldg(lc.bvh.nodes + i);
+        for (uint32_t i = threadIdx.x; i < n_tris4; i += kBlock) s_tris[i] = __ldg(lc.bvh.tris + i);
+        for (uint32_t i = threadIdx.x; i < n_sh; i += kBlock) s_shade[i] = __ldg(lc.tri_shade + i);
+        for (uint32_t i = threadIdx.x; i < n_m4; i += kBlock) s_mats[i] = __ldg(mats + i);
+        __syncthreads();
+        bvh.nodes = s_nodes;
+        bvh.tris = s_tris;
+        tri_shade = s_shade;
+        mats = s_mats;
+    }
+
+    const float l_area = length(cross(lc.l_v1, lc.l_v2));   // :1021
+    const int lane = threadIdx.x & 31;
+    ThreadCounters ctr = {};
+    TraceCount tc = {0, 0};
+
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(lc.work_counter, 1u);
+        k = __shfl_sync(kFull, k, 0);
+        if (k >= lc.n_owned_tiles) break;
+        const uint32_t tile = lc.rank + k * lc.n_ranks;
+        const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
+        const uint32_t ix = tx * 8u + (uint32_t)(lane & 7), iy = ty * 4u + (uint32_t)(lane >> 3);
+        if (ix < lc.width && iy < lc.height) {
+            const uint32_t image_index = iy * lc.width + ix;
+            uint32_t pixel_seed = tea4(image_index, lc.frame);                                 // :721
+            float3 result = f3(0.0f);
+            uint32_t left = lc.spp;
+            Path p;
+            generate_camera_ray(lc, ix, iy, pixel_seed, p);
+            if (COUNT) ctr.n_samples++;
+            bool first = true;
+            if (PROBE) {
+                if (lc.dbg_seed_after_jitter) lc.dbg_seed_after_jitter[image_index] = pixel_seed;
+                if (lc.dbg_primary_dir) {
+                    lc.dbg_primary_dir[3 * image_index + 0] = p.d.x;
+                    lc.dbg_primary_dir[3 * image_index + 1] = p.d.y;
+                    lc.dbg_primary_dir[3 * image_index + 2] = p.d.z;
+                }
+            }
+            for (;;) {
+                // traceRadiance :577-635, tmin 0.01, tmax 1e16 (:754-755)
+                float t_hit;
+                uint32_t prim, leaf;
+                if (COUNT) ctr.n_radiance++;
+                const bool hit = trace_closest<COUNT, SMEM>(bvh, p.o, p.d, 0.01f, 1e16f, t_hit, prim, leaf, tc);
+                if (PROBE && first) {
+                    if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = hit ? (int32_t)prim : -1;
+                    if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = hit ? t_hit : 0.0f;
+                    first = false;
+                }
+                float3 emission, radiance;
+                bool done;
+                if (hit) {
+                    ShadowQuery sq;
+                    int hit_type;
+                    shade_hit<SMEM>(lc, tri_shade, mats, l_area, prim, t_hit, p, emission, radiance, done, sq, hit_type);
+                    if (COUNT) {
+                        ctr.n_hit0 += hit_type == 0;
+                        ctr.n_hit1 += hit_type == 1;
+                        ctr.n_hit2 += hit_type == 2;
+                    }
+                    if (sq.want) {
+                        // traceOcclusion :651-684: "anything in (0.01, Ldist - 0.01)" 
+                        if (COUNT) ctr.n_shadow++;
+                        if (!trace_any<COUNT, SMEM>(bvh, sq.org, sq.dir, 0.01f, sq.tmax, tc)) radiance = radiance + sq.add;
+                    }
+                } else {
+                    // __miss__ms :833-847
+                    radiance = lc.background;
+                    emission = f3(0.0f);
+                    done = true;
+                    if (COUNT) ctr.n_miss++;
+                }
+                result = result + emission;                                                     // :760
+                result = result + radiance * p.att;                                             // :761
+                const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                           // :763
+                const bool rr = rnd(p.seed) > pr;                                               // :765
+                if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                          // :767
+                    if (--left == 0u) break;
+                    generate_camera_ray(lc, ix, iy, pixel_seed, p);                             // next sample, in place
+                    if (COUNT) ctr.n_samples++;
+                } else {
+                    p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
+                    ++p.depth;
+                }
+            }
+            write_pixel(lc, image_index, result);
+            if (PROBE) {
+                if (lc.dbg_final_path_seed) lc.dbg_final_path_seed[image_index] = p.seed;
+                if (lc.dbg_final_pixel_seed) lc.dbg_final_pixel_seed[image_index] = pixel_seed;
+            }
+        }
+        __syncwarp();
+    }
+
+    if (COUNT && lc.counters) {
+        flush_counter(lc.counters + 0, ctr.n_samples);
+        flush_counter(lc.counters + 1, ctr.n_radiance);
+        flush_counter(lc.counters + 2, ctr.n_shadow);
+        flush_counter(lc.counters + 3, tc.n_node);
+        flush_counter(lc.counters + 4, tc.n_tri);
+        flush_counter(lc.counters + 5, ctr.n_hit0);
+        flush_counter(lc.counters + 6, ctr.n_hit1);
+        flush_counter(lc.counters + 7, ctr.n_hit2);
+        flush_counter(lc.counters + 8, ctr.n_miss);
+    }
+}
+
+// ---- batch ray queries (parity probe) --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trace_rays_kernel(BvhView bvh, const float* __restrict__ org, const float* __restrict__ dir,
+                                                         const float* __restrict__ tmin, const float* __restrict__ tmax,
+                                                         uint64_t n, int32_t* prim_out, float* t_out, uint8_t* any_out,
+                                                         unsigned long long* counters2)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TraceCount tc = {0, 0};
+    if (i < n) {
+        const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
+        const float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+        if (prim_out || t_out) {
+            float t;
+            uint32_t prim, leaf;
+            const bool hit = trace_closest<true, false>(bvh, o, d, tmin[i], tmax[i], t, prim, leaf, tc);
+            if (prim_out) prim_out[i] = hit ? (int32_t)prim : -1;
+            if (t_out) t_out[i] = hit ? t : 0.0f;
+        }
+        if (any_out) any_out[i] = trace_any<true, false>(bvh, o, d, tmin[i], tmax[i], tc) ? 1 : 0;
+    }
+    if (counters2) {
+        flush_counter(counters2 + 0, tc.n_node);
+        flush_counter(counters2 + 1, tc.n_tri);
+    }
+}
+
+cudaError_t trace_rays_device(Scene& s, const float* d_org, const float* d_dir, const float* d_tmin, const float* d_tmax,
+                              uint64_t n, int32_t* d_prim, float* d_t, uint8_t* d_any, unsigned long long* d_counters2,
+                              cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    BvhView bvh{s.d_nodes, s.d_tris, s.n_tris};
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    trace_rays_kernel<<<grid, 256, 0, stream>>>(bvh, d_org, d_dir, d_tmin, d_tmax, n, d_prim, d_t, d_any, d_counters2);
+    return cudaGetLastError();
+}
+
+// ---- pixel partition: tile k of rank r is image tile r + k * n_ranks (tiles of 8x4 pixels, row-major) ----------
+uint32_t partition_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks)
+{
+    const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
+    return rank < tiles ? (tiles - rank + n_ranks - 1) / n_ranks : 0;
+}
+uint32_t partition_max_owned_tiles(uint32_t width, uint32_t height, uint32_t n_ranks)
+{
+    const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
+    return (tiles + n_ranks - 1) / n_ranks;
+}
+
+__global__ void __launch_bounds__(256) partition_pack_kernel(const float4* __restrict__ accum_full, const uchar4* __restrict__ frame_full,
+                                                             float4* __restrict__ accum_compact, uchar4* __restrict__ frame_compact,
+                                                             uint32_t width, uint32_t height, uint32_t tiles_x, uint32_t rank,
+                                                             uint32_t n_ranks, uint32_t capacity_tiles, uint32_t owned)
+{
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;   // k * 32 + lane
+    if (slot >= capacity_tiles * 32u) return;
+    const uint32_t k = slot >> 5, lane = slot & 31u;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    uchar4 c = make_uchar4(0, 0, 0, 0);
+    if (k < owned) {
+        const uint32_t tile = rank + k * n_ranks;
+        const uint32_t ix = (tile % tiles_x) * 8u + (lane & 7u), iy = (tile / tiles_x) * 4u + (lane >> 3);
+        if (ix < width && iy < height) {
+            a = accum_full[iy * width + ix];
+            if (frame_full) c = frame_full[iy * width + ix];
+        }
+    }
+    accum_compact[slot] = a;
+    if (frame_compact) frame_compact[slot] = c;
+}
+
+__global__ void __launch_bounds__(256) partition_unpack_kernel(const float4* __restrict__ accum_compact_all,
+                                                               const uchar4* __restrict__ frame_compact_all,
+                                                               float4* __restrict__ accum_full, uchar4* __restrict__ frame_full,
+                                                               uint32_t width, uint32_t height, uint32_t tiles_x, uint32_t n_tiles,
+                                                               uint32_t n_ranks, uint32_t capacity_tiles)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;    // tile * 32 + lane
+    if (idx >= n_tiles * 32u) return;
+    const uint32_t tile = idx >> 5, lane = idx & 31u;
+    const uint32_t ix = (tile % tiles_x) * 8u + (lane & 7u), iy = (tile / tiles_x) * 4u + (lane >> 3);
+    if (ix >= width || iy >= height) return;
+    const uint32_t r = tile % n_ranks, k = tile / n_ranks;
+    const size_t slot = ((size_t)r * capacity_tiles + k) * 32u + lane;
+    accum_full[iy * width + ix] = accum_compact_all[slot];
+    if (frame_full && frame_compact_all) frame_full[iy * width + ix] = frame_compact_all[slot];
+}
+
+cudaError_t partition_pack(const void* accum_full, const void* frame_full, void* accum_compact, void* frame_compact,
+                           uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks, cudaStream_t stream)
+{
+    const uint32_t tiles_x = (width + 7) / 8;
+    const uint32_t cap = partition_max_owned_tiles(width, height, n_ranks);
+    const uint32_t owned = partition_owned_tiles(width, height, rank, n_ranks);
+    const unsigned grid = (cap * 32u + 255u) / 256u;
+    partition_pack_kernel<<<grid, 256, 0, stream>>>((const float4*)accum_full, (const uchar4*)frame_full, (float4*)accum_compact,
+                                                    (uchar4*)frame_compact, width, height, tiles_x, rank, n_ranks, cap, owned);
+    return cudaGetLastError();
+}
+
+cudaError_t partition_unpack(const void* accum_compact_all, const void* frame_compact_all, void* accum_full,
+                             void* frame_full, uint32_t width, uint32_t height, uint32_t n_ranks, cudaStream_t stream)
+{
+    const uint32_t tiles_x = (width + 7) / 8;
+    const uint32_t n_tiles = tiles_x * ((height + 3) / 4);
+    const uint32_t cap = partition_max_owned_tiles(width, height, n_ranks);
+    const unsigned grid = (n_tiles * 32u + 255u) / 256u;
+    partition_unpack_kernel<<<grid, 256, 0, stream>>>((const float4*)accum_compact_all, (const uchar4*)frame_compact_all,
+                                                      (float4*)accum_full, (uchar4*)frame_full, width, height, tiles_x, n_tiles,
+                                                      n_ranks, cap);
+    return cudaGetLastError();
+}
+
+// ---- launch ---------------------------------------------------------------------------------------------------------
+static inline float3 to3(const pt_float3& v) { return make_float3(v.x, v.y, v.z); }
+
+template <bool COUNT, bool PROBE, bool SMEM>
+static cudaError_t launch_persistent(Scene& s, const LaunchConst& lc, size_t smem_bytes, cudaStream_t stream)
+{
+    auto kernel = render_persistent_kernel<COUNT, PROBE, SMEM>;
+    cudaError_t e;
+    if (smem_bytes > 0) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem_bytes);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // persistent grid: every resident warp pulls tiles until the counter runs out
+    const uint32_t warps_needed = lc.n_owned_tiles;
+    uint32_t grid = (uint32_t)(sms * per_sm);
+    const uint32_t grid_needed = (warps_needed + (kBlock / 32) - 1) / (kBlock / 32);
+    if (grid > grid_needed) grid = grid_needed;
+    if (grid == 0) grid = 1;
+    e = cudaMemsetAsync(s.d_work_counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kBlock, smem_bytes, stream>>>(lc);
+    s.last_grid = grid;
+    s.last_block = kBlock;
+    s.last_smem = (uint32_t)smem_bytes;
+    s.last_kernels = 1;
+    return cudaGetLastError();
+}
+
+cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint32_t n_ranks, cudaStream_t stream,
+                          const LaunchConst* probe_overrides)
+{
+    LaunchConst lc = {};
+    lc.frame = params.currentFrameIdx;
+    lc.width = params.width;
+    lc.height = params.height;
+    lc.spp = params.samplesPerPixel;
+    lc.max_depth = params.maxDepth;
+    lc.eye = to3(params.cameraEye);
+    lc.U = to3(params.cameraU);
+    lc.V = to3(params.cameraV);
+    lc.W = to3(params.cameraW);
+    lc.l_corner = to3(params.areaLight.corner);
+    lc.l_v1 = to3(params.areaLight.v1);
+    lc.l_v2 = to3(params.areaLight.v2);
+    lc.l_normal = to3(params.areaLight.normal);
+    lc.l_emission = to3(params.areaLight.emission);
+    lc.use_nee = params.useDirectLighting ? 1 : 0;
+    lc.use_is = params.useImportanceSampling ? 1 : 0;
+    lc.background = make_float3(s.background[0], s.background[1], s.background[2]);
+    lc.accum = (float4*)params.accumulationBuffer;
+    lc.frame_buffer = (uchar4*)params.frameBuffer;
+    lc.bvh = BvhView{s.d_nodes, s.d_tris, s.n_tris};
+    lc.n_nodes = s.n_nodes;
+    lc.n_mats = s.n_mats;
+    lc.tri_shade = s.d_tri_shade;
+    lc.mats = s.d_mats;
+    lc.tiles_x = (params.width + 7) / 8;
+    lc.tiles_y = (params.height + 3) / 4;
+    lc.rank = rank;
+    lc.n_ranks = n_ranks;
+    lc.n_owned_tiles = partition_owned_tiles(params.width, params.height, rank, n_ranks);
+    lc.counters = s.count_enabled ? s.d_counters : nullptr;
+    lc.work_counter = s.d_work_counter;
+    bool probe = false;
+    if (probe_overrides) {
+        lc.dbg_seed_after_jitter = probe_overrides->dbg_seed_after_jitter;
+        lc.dbg_primary_dir = probe_overrides->dbg_primary_dir;
+        lc.dbg_primary_prim = probe_overrides->dbg_primary_prim;
+        lc.dbg_primary_t = probe_overrides->dbg_primary_t;
+        lc.dbg_final_path_seed = probe_overrides->dbg_final_path_seed;
+        lc.dbg_final_pixel_seed = probe_overrides->dbg_final_pixel_seed;
+        probe = true;
+    }
+    if (lc.n_owned_tiles == 0) return cudaSuccess;
+
+    const size_t staged = staged_scene_float4s(s.n_nodes, s.n_tris, s.n_mats) * sizeof(float4);
+    const bool smem = s.n_tris > 0 && staged <= kSmemSceneLimit;
+    const bool count = s.count_enabled;
+    if (probe) {
+        return smem ? launch_persistent<false, true, true>(s, lc, staged, stream)
+                    : launch_persistent<false, true, false>(s, lc, 0, stream);
+    }
+    if (count) {
+        return smem ? launch_persistent<true, false, true>(s, lc, staged, stream)
+                    : launch_persistent<true, false, false>(s, lc, 0, stream);
+    }
+    return smem ? launch_persistent<false, false, true>(s, lc, staged, stream)
+                : launch_persistent<false, false, false>(s, lc, 0, stream);
+}
+
+}  // namespace ptb

@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mpixel-samples/s of the path-tracing hot path on BASELINE.json's config C2
+(Cornell box 1920x1080, 16 bounces, importance sampling + direct lighting, 128 spp per launch).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1|c2|c3|c4|c5]
+
+A "step" is one launch (= one optixLaunch(w, h, 1) of the reference, PathTracerMain.cpp:197): samplesPerPixel
+samples for every pixel folded into the running average; step i uses currentFrameIdx = i, so K = 8 steps are the
+1024 spp of config C2.  Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline,
+cpu_baseline, e2e, clocks, gpu_launches, grays_per_s).
+
+For N > 1 (torchrun, one rank per GPU) the scene and LBVH are replicated, 8x4-pixel tiles are interleaved over
+ranks, and every step ends with one NCCL all-gather of the owned pixels, so that each rank holds the complete
+image after each step.  Total work is fixed as N grows ("strong" scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene, width, height, spp per launch, maxDepth, NEE, importance sampling, description)
+    "c1": ("cornell", 512, 512, 1, 3, False, True, "Cornell-32 512x512, 1 spp, 3 bounces, IS, no NEE (configs[0])"),
+    "c2": ("cornell", 1920, 1080, 128, 16, True, True, "Cornell-32 1920x1080, 16 bounces, IS+NEE, 128 spp/launch (configs[1]; 8 launches = 1024 spp)"),
+    "c3": ("material", 1920, 1080, 128, 28, True, True, "Cornell + dielectric + conductor spheres 1080p, 28 bounces, IS+NEE, 128 spp/launch (configs[2])"),
+    "c4": ("tess1000", 1920, 1080, 128, 8, True, True, "2.0 M-triangle displaced height field in the Cornell box, 1080p, 8 bounces, 128 spp/launch (configs[3])"),
+    "c5": ("cornell", 3840, 2160, 128, 28, True, True, "Cornell-32 3840x2160, 28 bounces, IS+NEE, 128 spp/launch (configs[4])"),
+}
+
+# Algorithmic work per event (SURVEY.md 8d / DESIGN.md "Roofline accounting"); FMA = 2 flop.
+FLOP_NODE, FLOP_TRI = 24, 45
+FLOP_SAMPLE, FLOP_SEGMENT, FLOP_NEE = 40, 20, 60
+FLOP_HIT = (110, 190, 120)
+BYTES_NODE, BYTES_TRI = 64, 48
+
+
+def algorithmic_work(c, nee):
+    flops = (FLOP_NODE * c["n_node"] + FLOP_TRI * c["n_tri"] + FLOP_SAMPLE * c["n_samples"] +
+             FLOP_SEGMENT * c["n_radiance"] + sum(f * n for f, n in zip(FLOP_HIT, c["n_hit"])))
+    if nee:
+        flops += FLOP_NEE * (c["n_hit"][0] + c["n_hit"][1])
+    return flops, BYTES_NODE * c["n_node"] + BYTES_TRI * c["n_tri"]
+
+
+def make_scene_arrays(name):
+    from acgpathtracing_b200 import scenes as S
+    if name == "cornell":
+        return S.cornell32()
+    if name == "material":
+        return S.material_scene(3)
+    if name.startswith("tess"):
+        return S.tessellated_scene(int(name[4:]))
+    raise ValueError(name)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                power.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# ================================================================================================================
+# reference arm: the reference's own programs on the host cores
+# ================================================================================================================
+def cpu_reference_run(workload, steps, warmup, prefer_ref=True, target_step_s=2.0):
+    """Times the reference's CPU implementation of the path on this box's host cores with all hardware threads:
+    oracle/_ref/libptref.so (the reference's own pathTracerPrograms.cu compiled for the host) when it exists, else
+    the oracle port.  Each step is a bounded sample of the workload: the full frame at a reduced spp."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    scene_name, w, h, spp, md, nee, imp, desc = WORKLOADS[workload]
+    arr = make_scene_arrays(scene_name)
+    port = O.load_port()
+    ref = O.load_ref() if prefer_ref else None
+    cores = port.ptor_hardware_threads()
+    use_bvh = arr.n_tri > 64            # brute force over <= 64 triangles is the faster CPU choice (measured)
+    osc = None if ref is not None else O.OracleScene(port, arr)
+
+    def one(frame, s_spp, region=None):
+        p = O.make_params(port, w, h, s_spp, md, frame=frame, nee=nee, importance=imp)
+        t0 = time.perf_counter()
+        if ref is not None:
+            O.ref_render(ref, arr, p, use_bvh=use_bvh, nthreads=cores, region=region)
+        else:
+            osc.render(p, math_mode=0, use_bvh=use_bvh, nthreads=cores, region=region, want_fb=True)
+        return time.perf_counter() - t0
+
+    rows = max(8, h // 8)
+    t = one(0, 1, region=(0, w, (h - rows) // 2, (h + rows) // 2))      # calibration strip from the image centre
+    rate = w * rows / max(t, 1e-6)
+    s_spp = int(max(1, min(spp, round(target_step_s * rate / (w * h)))))
+    for i in range(warmup):
+        one(i, s_spp)
+    times = [one(i, s_spp) for i in range(steps)]
+    total = sum(times)
+    value = w * h * s_spp * steps / total / 1e6
+    kind = "reference" if ref is not None else "port"
+    sample = (f"{desc}: full {w}x{h} frame at {s_spp} spp per step ({steps} steps, frames 0..{steps - 1}), "
+              f"{'CPU LBVH' if use_bvh else 'brute-force'} intersection, {cores} threads, glibc libm")
+    return dict(value=value, unit="Mpixel-samples/s", cores=cores, kind=kind, sample=sample,
+                ms_per_step=1e3 * total / steps, spp=s_spp)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene_name, w, h, spp, md, nee, imp, desc = WORKLOADS[args.workload]
+    r = cpu_reference_run(args.workload, args.steps, args.warmup)
+    out = {
+        "impl": "reference", "metric": "Mpixel-samples/s", "value": r["value"], "unit": "Mpixel-samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "width": w, "height": h, "max_depth": md, "spp_per_step": r["spp"],
+                   "direct_lighting": nee, "importance_sampling": imp},
+        "cpu_baseline": {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ================================================================================================================
+# B200 arm
+# ================================================================================================================
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from acgpathtracing_b200 import api
+    from acgpathtracing_b200.types import PathTraceParams
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("for --gpus N > 1 launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    scene_name, w, h, spp, md, nee, imp, desc = WORKLOADS[args.workload]
+    if args.spp:
+        spp = args.spp
+    arr = make_scene_arrays(scene_name)
+    scene = api.Scene(arr)
+    if args.pipeline:
+        scene.set_pipeline(args.pipeline)
+    info = scene.info()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    acc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
+    fb = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
+    cap = api.partition_capacity(w, h, world)
+    if world > 1:
+        my_acc = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
+        my_fb = torch.zeros((cap, 4), dtype=torch.uint8, device=dev)
+        all_acc = torch.zeros((world, cap, 4), dtype=torch.float32, device=dev)
+        all_fb = torch.zeros((world, cap, 4), dtype=torch.uint8, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def params(frame):
+        p = api.make_params(w, h, spp, md, frame=frame, nee=nee, importance=imp, scene=scene)
+        p.accumulationBuffer, p.frameBuffer = acc.data_ptr(), fb.data_ptr()
+        return p
+
+    def step(frame):
+        """One launch of the hot path with device-resident buffers; returns the number of our kernels launched."""
+        p = params(frame)
+        if world == 1:
+            api.launch(p, stream)
+            return 1
+        api.launch_partition(p, rank, world, stream)
+        api.partition_pack(acc.data_ptr(), fb.data_ptr(), my_acc.data_ptr(), my_fb.data_ptr(), w, h, rank, world, stream)
+        dist.all_gather_into_tensor(all_acc, my_acc)
+        dist.all_gather_into_tensor(all_fb, my_fb)
+        api.partition_unpack(all_acc.data_ptr(), all_fb.data_ptr(), acc.data_ptr(), fb.data_ptr(), w, h, world, stream)
+        return 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ------------------------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---- timed region: K steps, CUDA events around each step, L2 flushed between steps ------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)                     # evict L2 (untimed)
+        ev[i][0].record()
+        launches += step(i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    clocks = sampler.stop() if sampler else None
+    checksum = float(acc[..., :3].double().mean().item())
+
+    pixel_samples = float(w) * h * spp * args.steps
+    value = pixel_samples / (total_ms * 1e-3) / 1e6
+
+    # ---- work counters for the timed frames (instrumented kernel, untimed) -> Grays/s and algorithmic flops ----
+    scene.enable_counters(True)
+    scene.counters(reset=True)
+    for i in range(args.steps):
+        step(i)
+    barrier()
+    c = scene.counters(reset=True)
+    scene.enable_counters(False)
+    ct = torch.tensor([c["n_samples"], c["n_radiance"], c["n_shadow"], c["n_node"], c["n_tri"], *c["n_hit"], c["n_miss"]],
+                      dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ct)
+    ct = [int(x) for x in ct.tolist()]
+    counters = dict(n_samples=ct[0], n_radiance=ct[1], n_shadow=ct[2], n_node=ct[3], n_tri=ct[4], n_hit=ct[5:8], n_miss=ct[8])
+    flops, tbytes = algorithmic_work(counters, nee)
+    rays = counters["n_radiance"] + counters["n_shadow"]
+
+    # ---- end to end through the host-buffer entry point (pt_launch_host): pinned host buffers, H2D + D2H in the
+    # timed region every step -------------------------------------------------------------------------------------
+    e2e = None
+    if world == 1:
+        h_acc = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
+        h_fb = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+        up = down = 0
+        import ctypes as C
+
+        def host_step(frame):
+            p = api.make_params(w, h, spp, md, frame=frame, nee=nee, importance=imp, scene=scene)
+            p.accumulationBuffer, p.frameBuffer = h_acc.data_ptr(), h_fb.data_ptr()
+            a, b = C.c_uint64(), C.c_uint64()
+            api._check(api.lib.pt_launch_host(C.byref(p), C.byref(a), C.byref(b)))
+            return a.value, b.value
+
+        for i in range(min(args.warmup, 2)):
+            host_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            a, b = host_step(i)       # synchronous: returns after the D2H copies completed
+            up += a
+            down += b
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": pixel_samples / t_e2e / 1e6, "unit": "Mpixel-samples/s",
+               "h2d_bytes_per_step": up // args.steps, "d2h_bytes_per_step": down // args.steps,
+               "ms_per_step": 1e3 * t_e2e / args.steps,
+               "checksum_matches_device_path": abs(float(h_acc[..., :3].double().mean().item()) - checksum) == 0.0}
+    else:
+        # every rank: H2D of the previous full image, partition launch, exchange, D2H of the full image
+        h_acc = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
+        h_fb = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+
+        def host_step(frame):
+            if frame > 0:
+                acc.copy_(h_acc, non_blocking=True)
+            step(frame)
+            h_acc.copy_(acc, non_blocking=True)
+            h_fb.copy_(fb, non_blocking=True)
+            torch.cuda.synchronize()
+
+        host_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            host_step(i)
+        barrier()
+        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        t_e2e = float(t_e2e.item())
+        e2e = {"value": pixel_samples / t_e2e / 1e6, "unit": "Mpixel-samples/s",
+               "h2d_bytes_per_step": (args.steps - 1) * w * h * 16 // args.steps, "d2h_bytes_per_step": w * h * 20,
+               "ms_per_step": 1e3 * t_e2e / args.steps, "note": "bytes are per rank"}
+
+    # ---- roofline denominators measured on this device -----------------------------------------------------------
+    roofline = None
+    cpu = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        dinfo = api.device_info()
+        fp32_meas = api.bench_fp32_peak()
+        l2_meas = api.bench_l2_bandwidth()
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        fp32_nominal = dinfo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
+        kernel_ms = total_ms / args.steps        # at N = 1 the step IS the kernel; at N > 1 it includes the exchange
+        ach_tflops = flops / world / args.steps / (kernel_ms * 1e-3) / 1e12
+        ach_gbs = tbytes / world / args.steps / (kernel_ms * 1e-3) / 1e9
+        roofline = {
+            "kernel": "render_persistent_kernel" if (args.pipeline or 1) == 1 else "wavefront_kernel",
+            "bound": "fp32", "achieved": ach_tflops, "peak": fp32_meas, "unit": "TFLOP/s", "frac": ach_tflops / fp32_meas,
+            "peak_source": "measured live by pt_bench_fp32_peak (dependent-free FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
+            "peak_nominal": fp32_nominal, "traffic": None,
+            "l2": {"achieved": ach_gbs, "peak": l2_meas, "unit": "GB/s", "frac": ach_gbs / l2_meas,
+                   "note": "node/triangle record bytes; served from shared memory when the scene is staged there"},
+            "hbm": {"achieved": (w * h * (36 if True else 0)) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
+                    "unit": "GB/s", "note": "image traffic only: 16 B read + 16 B write + 4 B framebuffer per pixel per launch"},
+            "algorithmic_flops_per_launch": flops / args.steps, "algorithmic_bytes_per_launch": tbytes / args.steps,
+            "per_gpu": world > 1,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(args.workload, steps=1, warmup=0, prefer_ref=False, target_step_s=12.0)
+            cpu = {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+
+    if rank == 0:
+        out = {
+            "metric": "Mpixel-samples/s", "value": value, "unit": "Mpixel-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "scene": scene_name, "triangles": info["n_tris"], "width": w, "height": h,
+                       "spp_per_step": spp, "max_depth": md, "direct_lighting": nee, "importance_sampling": imp,
+                       "frames": f"0..{args.steps - 1}", "parallelism": f"pixel-tiles x{world}",
+                       "l2": "flushed between timed steps (256 MiB fill)", "pipeline": scene.last_launch_info(),
+                       "lbvh_build_ms": info["build_ms"]},
+            "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
+            "rays_per_sample": rays / max(counters["n_samples"], 1),
+            "counters": counters, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "image_mean_radiance": checksum,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per launch")
+    ap.add_argument("--pipeline", type=int, default=0, help="0 auto, 1 persistent state machine, 2 CTA-local wavefront")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

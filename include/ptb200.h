@@ -1,0 +1,154 @@
+/* ptb200.h -- C ABI of the B200-native path tracer (libptb200.so).
+ *
+ * Drop-in boundary for the hot path of fallinbryan/ACGPathTracing: everything between "arrays from
+ * TinyObjWrapper" and "pixels in two buffers".  The reference has no FFI layer; the calls below replace
+ * what PathTracer_Optix/PathTracerMain.cpp does through the OptiX host API (file:line cited per entry).
+ * Plain C types only: pointers, sizes, opaque handles.  Every function returns 0 on success or a
+ * PT_ERR_* code; pt_last_error() gives the message (thread-local).  Nothing throws across the boundary
+ * (the reference throws sutil::Exception, sutil/Exception.h:136, caught once in main :742).
+ *
+ * There is no CPU fallback: calls that need the GPU fail with PT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_OK 0
+#define PT_ERR_INVALID 1   /* bad argument (null pointer, zero size, index out of range, bad BSDF type) */
+#define PT_ERR_CUDA 2      /* CUDA runtime error / no device */
+#define PT_ERR_IO 3        /* OBJ/MTL file could not be read or parsed */
+
+/* ---- launch contract: byte-identical to the reference ------------------------------------------------ */
+typedef struct { float x, y, z; } pt_float3;
+
+/* pathTracer.h:77-83 (60 bytes) */
+typedef struct {
+    pt_float3 corner, v1, v2, normal, emission;
+} pt_area_light;
+
+/* pathTracer.h:85-108 (168 bytes, align 8).  `handle` carries pt_scene_handle() instead of an
+ * OptixTraversableHandle.  accumulationBuffer (float4*) and frameBuffer (uchar4*) are DEVICE pointers owned
+ * by the caller for pt_launch* (ref: cudaMalloc PathTracerMain.cpp:145 / mapped PBO :186) and HOST pointers
+ * for pt_launch_host.  frameBuffer may be NULL (headless extension). */
+typedef struct {
+    uint32_t currentFrameIdx;
+    void* accumulationBuffer;
+    void* frameBuffer;
+    uint32_t width, height, samplesPerPixel, maxDepth;
+    pt_float3 cameraEye, cameraU, cameraV, cameraW;
+    pt_area_light areaLight;
+    uint64_t handle;
+    uint8_t useDirectLighting;      /* bool */
+    uint8_t useImportanceSampling;  /* bool */
+} pt_params;
+
+/* TinyObjWrapper.h:27-40 (40 bytes) */
+enum { PT_BSDF_DIFFUSE = 0, PT_BSDF_METALLIC = 1, PT_BSDF_REFRACTION = 2 };
+typedef struct {
+    pt_float3 diffuse, emission;
+    float roughness, metallic, ior;
+    int32_t bsdfType;
+} pt_material;
+
+/* Work counters: per launch, cumulative until reset. */
+typedef struct {
+    uint64_t n_samples, n_radiance, n_shadow, n_node, n_tri, n_hit[3], n_miss;
+} pt_counters;
+
+typedef struct pt_scene pt_scene;
+
+const char* pt_last_error(void);
+
+/* ---- scene: replaces buildTheAccelarationStructure (PathTracerMain.cpp:260-398: upload + optixAccelBuild
+ * + compaction) and createShaderBindingTable (:544-608: one hit record per material).  Copies the four
+ * TinyObjWrapper arrays (TinyObjWrapper.h:87-93) to the current CUDA device and builds the LBVH there.
+ * The caller keeps ownership of the host arrays. ------------------------------------------------------- */
+int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* indices, uint32_t n_tris,
+                    const uint32_t* mat_ids, const pt_material* materials, uint32_t n_materials, pt_scene** out);
+void pt_scene_destroy(pt_scene* scene);                                   /* CleanAllTheThings :629-646 */
+int pt_scene_set_background(pt_scene* scene, float r, float g, float b);  /* MissData.backgroundColor :568 */
+uint64_t pt_scene_handle(const pt_scene* scene);                          /* value for pt_params.handle */
+int pt_scene_info(const pt_scene* scene, uint32_t* n_tris, uint32_t* n_nodes, float* build_ms);
+
+/* ---- launch: replaces cudaMemcpyAsync(d_params) + optixLaunch(pipeline, stream, d_params, ..., w, h, 1)
+ * (PathTracerMain.cpp:191-206).  One call = one subframe of samplesPerPixel samples per pixel folded into
+ * the running average with weight 1/(currentFrameIdx+1) (pathTracerPrograms.cu:803-811); the caller
+ * increments currentFrameIdx (:714).  Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default). ---- */
+int pt_launch(const pt_params* params, void* cuda_stream);
+
+/* Pixel-partitioned launch for multi-GPU rendering: renders only the 8x4-pixel tiles owned by `rank` of
+ * `n_ranks` (tile L is owned by rank L % n_ranks, rows rotated) into the full-size buffers.
+ * The RNG stream of a pixel depends only on (pixel index, currentFrameIdx) (pathTracerPrograms.cu:721), so
+ * the union over ranks is bit-identical to pt_launch. */
+int pt_launch_partition(const pt_params* params, uint32_t rank, uint32_t n_ranks, void* cuda_stream);
+
+/* Owned-pixel exchange helpers (one NCCL all-gather per image sits between them).
+ * pack: full-size accumulation/frame buffers -> this rank's compact tile-major buffers
+ *       (pt_partition_capacity() pixels: float4 and uchar4 each).
+ * unpack: n_ranks compact buffers laid out back to back -> full-size buffers. */
+uint64_t pt_partition_capacity(uint32_t width, uint32_t height, uint32_t n_ranks);   /* pixels per rank */
+int pt_partition_pack(const void* accum_full, const void* frame_full, void* accum_compact, void* frame_compact,
+                      uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks, void* cuda_stream);
+int pt_partition_unpack(const void* accum_compact_all, const void* frame_compact_all, void* accum_full,
+                        void* frame_full, uint32_t width, uint32_t height, uint32_t n_ranks, void* cuda_stream);
+
+/* Same launch with HOST buffers: uploads the previous accumulation when currentFrameIdx > 0, renders,
+ * downloads accumulation (and frame buffer if non-NULL); synchronous.  This is the call the end-to-end
+ * benchmark times.  Reports the bytes moved. */
+int pt_launch_host(const pt_params* params_host_buffers, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* ---- counters and tuning ----------------------------------------------------------------------------- */
+int pt_scene_enable_counters(pt_scene* scene, int enable);   /* counted launches use an instrumented kernel */
+int pt_scene_get_counters(pt_scene* scene, pt_counters* out, int reset);
+/* kernel variant: 0 = auto, 1 = persistent thread-per-path, 2 = CTA-local wavefront */
+int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
+int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes,
+                              uint32_t* kernels_launched);
+
+/* ---- parity probes (tests only; not on the hot path) --------------------------------------------------- */
+/* LBVH export; any pointer may be NULL.  morton[n_tris] in primitive order; sorted_keys[n_tris] =
+ * morton<<32|prim ascending; sorted_prim[n_tris]; parent[n_nodes]; nodes: n_nodes x 64 B; tris: n_tris x 48 B
+ * (leaf order); bounds: lo xyz, hi xyz. */
+int pt_bvh_export(const pt_scene* scene, uint32_t* morton, uint64_t* sorted_keys, uint32_t* sorted_prim,
+                  int32_t* parent, void* nodes64, void* tris48, float* bounds6);
+/* Batch ray queries through the device traversal kernels (host arrays in/out). */
+int pt_trace_rays(const pt_scene* scene, const float* org3, const float* dir3, const float* tmin, const float* tmax,
+                  uint64_t n, int32_t* prim_out, float* t_out, uint8_t* any_out, uint64_t* counters2);
+/* Per-pixel state of the FIRST sample of a launch (host arrays, w*h each; any may be NULL): pixel seed after
+ * the two jitter draws, primary ray direction (3 floats), primary hit primitive (-1 = miss) and distance. */
+int pt_debug_primary(const pt_params* params, uint32_t* seed_after_jitter, float* primary_dir3,
+                     int32_t* primary_prim, float* primary_t);
+/* Final RNG states of a launch (host arrays, w*h each): path seed when the last sample ended, pixel seed after
+ * all jitter draws.  Re-runs the launch into scratch buffers. */
+int pt_debug_final_seeds(const pt_params* params, uint32_t* final_path_seed, uint32_t* final_pixel_seed);
+
+/* ---- host helpers mirroring the reference's host code ------------------------------------------------ */
+/* sutil::Camera::UVWFrame (sutil/Camera.cpp:33-45) */
+void pt_camera_uvw_frame(const float eye[3], const float lookat[3], const float up[3], float fov_y_deg,
+                         float aspect, float U[3], float V[3], float W[3]);
+/* TinyObjWrapper-equivalent OBJ/MTL ingest (TinyObjWrapper.cpp:38-244).  Two-call protocol: counts first
+ * (array pointers NULL), then fill. */
+typedef struct pt_obj pt_obj;
+int pt_obj_load(const char* path, pt_obj** out);
+void pt_obj_free(pt_obj* obj);
+int pt_obj_counts(const pt_obj* obj, uint32_t* n_vert_floats, uint32_t* n_indices, uint32_t* n_mat_ids,
+                  uint32_t* n_materials);
+int pt_obj_copy(const pt_obj* obj, float* verts_xyzw, uint32_t* indices, uint32_t* mat_ids, pt_material* materials);
+int pt_scene_create_from_obj(const pt_obj* obj, pt_scene** out);
+
+/* ---- device microbenchmarks for the roofline denominators (bench.py) ----------------------------------- */
+int pt_device_info(int* sm_count, int* l2_bytes, int* clock_khz, char* name64);
+int pt_bench_fp32_peak(double* tflops);          /* dependent-free FFMA loop on every SM */
+int pt_bench_l2_bandwidth(double* gbps);         /* streaming read of an L2-resident buffer */
+int pt_bench_hbm_bandwidth(double* gbps);        /* streaming copy of a buffer much larger than L2 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path through the C-ABI (include/ptb200.h) against the CPU oracle.
+
+Bars (SURVEY 8c / north star):
+  * bit-exact: RNG streams (pixel seed after jitter, final path / pixel seeds), Morton keys, sort permutation,
+    LBVH topology + node boxes, primary-hit (primitive id, t bits), any-hit bits, work counters;
+  * radiance: the GPU kernels use the same portable transcendentals as the oracle's "det" mode
+    (csrc/pt_detmath.h) and are compiled without fused multiply-add contraction, so accumulation buffers are
+    required to be BIT-IDENTICAL too (RADIANCE_RTOL = 0); the north star's looser bound (1e-4 relative at 1 spp)
+    is asserted against the oracle's glibc mode, where sinf/cosf/acosf differ in the last place.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_api as O
+from acgpathtracing_b200 import scenes as S
+from acgpathtracing_b200.types import PathTraceParams
+
+pytestmark = pytest.mark.gpu
+
+RADIANCE_RTOL = 0.0          # vs the oracle's det-math mode: bit-exact
+LIBM_RTOL = 1e-4             # vs the oracle's glibc mode (reference source semantics), per channel
+LIBM_OUTLIER_BUDGET = 2e-3   # fraction of pixels allowed outside LIBM_RTOL (a flipped discrete decision)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from acgpathtracing_b200 import api as A
+    return A
+
+
+def _scene(name):
+    return {"cornell": S.cornell32, "material": lambda: S.material_scene(2), "tess40": lambda: S.tessellated_scene(40),
+            "tess300": lambda: S.tessellated_scene(300)}[name]()
+
+
+@pytest.fixture(scope="module")
+def scenes_cache():
+    return {}
+
+
+def _get(scenes_cache, api, port, name):
+    if name not in scenes_cache:
+        arr = _scene(name)
+        scenes_cache[name] = (arr, api.Scene(arr), O.OracleScene(port, arr))
+    return scenes_cache[name]
+
+
+# ---- LBVH: Morton keys, radix sort, Karras tree, refit ----------------------------------------------------------
+@pytest.mark.parametrize("name", ["cornell", "material", "tess40", "tess300"])
+def test_lbvh_bit_exact(api, port, scenes_cache, name):
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    g, o = gs.bvh_export(), osc.bvh()
+    assert np.array_equal(g["bounds"].view(np.uint32), o["bounds"].view(np.uint32))
+    assert np.array_equal(g["morton"], o["morton"])
+    assert np.array_equal(g["sorted_keys"], o["sorted_keys"])
+    assert np.array_equal(g["sorted_prim"], o["sorted_prim"])
+    assert np.array_equal(g["parent"], o["parent"])
+    gn, on = g["nodes"].copy(), o["nodes"].copy()
+    gn[:, [11, 15]] = 0   # padding words
+    on[:, [11, 15]] = 0
+    assert np.array_equal(gn, on)
+    gt, ot = g["tris"].copy(), o["tris"].copy()
+    gt[:, 11] = 0
+    ot[:, 11] = 0
+    assert np.array_equal(gt, ot)
+
+
+def _rays(scene, n, seed):
+    rng = np.random.default_rng(seed)
+    lo = scene.verts[:, :3].min(0) - 50
+    hi = scene.verts[:, :3].max(0) + 50
+    org = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    d[: n // 20] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, n // 20)] * rng.choice([-1, 1], (n // 20, 1))
+    tri = scene.indices[rng.integers(0, scene.n_tri, n // 4)]
+    bary = rng.dirichlet((1, 1, 1), n // 4)
+    p = (scene.verts[tri[:, 0], :3] * bary[:, :1] + scene.verts[tri[:, 1], :3] * bary[:, 1:2] +
+         scene.verts[tri[:, 2], :3] * bary[:, 2:3])
+    org[n // 2: n // 2 + n // 4] = p.astype(np.float32)
+    return org, d
+
+
+@pytest.mark.parametrize("name", ["cornell", "material", "tess40"])
+def test_traversal_bit_exact(api, port, scenes_cache, name):
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    n = 200_000
+    org, d = _rays(arr, n, 11)
+    gp, gt, ga, gc = gs.trace(org, d, 0.01, 1e16, want_any=True)
+    op, ot, oa, oc = osc.trace(org, d, 0.01, 1e16, use_bvh=True, want_any=True)
+    assert np.array_equal(gp, op)
+    assert np.array_equal(gt.view(np.uint32), ot.view(np.uint32))
+    assert np.array_equal(ga, oa)
+    assert gc.tolist() == oc.tolist()                      # node fetches and triangle tests, ray by ray order-free sums
+    # brute force over all triangles agrees as well (BVH culling is conservative)
+    bp, bt, ba, _ = osc.trace(org[:50_000], d[:50_000], 0.01, 1e16, use_bvh=False, want_any=True)
+    assert np.array_equal(gp[:50_000], bp) and np.array_equal(gt[:50_000].view(np.uint32), bt.view(np.uint32))
+    assert np.array_equal(ga[:50_000], ba)
+    tmax = np.random.default_rng(5).uniform(1, 600, n).astype(np.float32)
+    _, _, ga, _ = gs.trace(org, d, 0.01, tmax, want_any=True)
+    _, _, oa, _ = osc.trace(org, d, 0.01, tmax, use_bvh=True, want_any=True)
+    assert np.array_equal(ga, oa)
+
+
+# ---- RNG streams + primary hits -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,w,h", [("cornell", 512, 512), ("material", 320, 180), ("cornell", 253, 131)])
+def test_rng_streams_and_primary_hits(api, port, scenes_cache, name, w, h):
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    p = api.make_params(w, h, 3, 5, frame=2, nee=True, importance=True, scene=gs)
+    g = gs.debug_primary(p)
+    gf = gs.debug_final_seeds(p)
+    o = osc.render(p, math_mode=1, use_bvh=True, probes=True)
+    assert np.array_equal(g["seed_after_jitter"], o["seed_after_jitter"])
+    assert np.array_equal(g["primary_dir"].view(np.uint32), o["primary_dir"].view(np.uint32))
+    assert np.array_equal(g["prim"], o["prim"])
+    assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
+    assert np.array_equal(gf["final_path_seed"], o["final_path_seed"])
+    assert np.array_equal(gf["final_pixel_seed"], o["final_pixel_seed"])
+    assert (g["prim"] >= 0).mean() > 0.2
+
+
+def test_rng_known_answers(api, port, scenes_cache):
+    """tea<4> / LCG known answers from the reference's own cuda/random.h through the kernel."""
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    p = api.make_params(512, 512, 1, 3, frame=0, scene=gs)
+    g = gs.debug_primary(p)
+    s = 1576399551                                # tea<4>(0, 0)
+    for _ in range(2):
+        s = (1664525 * s + 1013904223) & 0xFFFFFFFF
+    assert int(g["seed_after_jitter"][0, 0]) == s == 4105309513
+    p3 = api.make_params(512, 512, 1, 3, frame=3, scene=gs)
+    g3 = gs.debug_primary(p3)
+    s = 2391278879                                # tea<4>(262143, 3)
+    for _ in range(2):
+        s = (1664525 * s + 1013904223) & 0xFFFFFFFF
+    assert int(g3["seed_after_jitter"][511, 511]) == s
+
+
+# ---- radiance ---------------------------------------------------------------------------------------------------------
+RENDER_CASES = [
+    # scene, w, h, spp, maxDepth, NEE, IS, launches
+    ("cornell", 512, 512, 1, 3, False, True, 1),      # BASELINE config C1
+    ("cornell", 480, 270, 8, 16, True, True, 3),      # C2 shape (16 bounces, IS + NEE), reduced size
+    ("material", 320, 180, 8, 28, True, True, 2),     # C3 shape
+    ("material", 200, 120, 4, 6, False, False, 1),    # uniform hemisphere sampling
+    ("tess40", 240, 136, 4, 8, True, True, 1),        # C4 shape, reduced
+    ("cornell", 97, 61, 5, 1, True, True, 2),         # ragged tiles, minimum depth
+]
+
+
+@pytest.mark.parametrize("case", RENDER_CASES, ids=lambda c: "-".join(str(x) for x in c))
+def test_render_matches_oracle(api, port, scenes_cache, case):
+    name, w, h, spp, md, nee, imp, frames = case
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    gs.enable_counters(True)
+    gs.counters(reset=True)
+    acc_g = acc_o = None
+    tot = None
+    try:
+        for f in range(frames):
+            p = api.make_params(w, h, spp, md, frame=f, nee=nee, importance=imp, scene=gs)
+            g = gs.launch_host(p, accum=acc_g)
+            o = osc.render(p, accum=acc_o, math_mode=1, use_bvh=True)
+            acc_g, acc_o = g["accum"], o["accum"]
+            assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), f"frame {f}"
+            assert np.array_equal(g["fb"], o["fb"]), f"frame {f}"
+            tot = o["counters"] if tot is None else {k: (tot[k] + v if not isinstance(v, list) else
+                                                         [a + b for a, b in zip(tot[k], v)]) for k, v in o["counters"].items()}
+        assert gs.counters(reset=True) == tot
+    finally:
+        gs.enable_counters(False)
+
+
+def test_uncounted_kernel_equals_counted(api, port, scenes_cache):
+    arr, gs, osc = _get(scenes_cache, api, port, "material")
+    p = api.make_params(192, 108, 6, 12, frame=1, nee=True, scene=gs)
+    prev = np.random.default_rng(0).random((108, 192, 4), dtype=np.float32)
+    a = gs.launch_host(p, accum=prev.copy())
+    gs.enable_counters(True)
+    b = gs.launch_host(p, accum=prev.copy())
+    gs.enable_counters(False)
+    gs.counters(reset=True)
+    assert np.array_equal(a["accum"].view(np.uint32), b["accum"].view(np.uint32))
+    assert np.array_equal(a["fb"], b["fb"])
+
+
+def test_radiance_vs_reference_libm_semantics(api, port, scenes_cache):
+    """North-star tolerance: 1e-4 relative at 1 spp with identical seeds against the reference-source semantics
+    (glibc sinf/cosf/acosf/powf).  Pixels whose path took a different discrete decision (Russian roulette, Fresnel
+    branch, NEE visibility) because of a last-place difference are counted against a budget."""
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    p = api.make_params(512, 512, 1, 3, frame=0, nee=False, importance=True, scene=gs)
+    g = gs.launch_host(p)
+    o = osc.render(p, math_mode=0, use_bvh=True)
+    ga, oa = g["accum"][..., :3], o["accum"][..., :3]
+    bad = np.abs(ga - oa) > LIBM_RTOL * np.maximum(np.abs(oa), 1e-3)
+    assert bad.any(axis=-1).mean() <= LIBM_OUTLIER_BUDGET
+    ok = ~bad.any(axis=-1)
+    assert np.abs(g["fb"].astype(int) - o["fb"].astype(int))[ok].max() <= 1      # framebuffer bytes: +-1 LSB
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------------------------
+def test_empty_scene_and_background(api, port):
+    empty = S.SceneArrays(np.ones((3, 4), np.float32), np.zeros((0, 3), np.uint32), np.zeros(0, np.uint32),
+                          [dict(name="m", Kd=(1, 1, 1), Ke=(0, 0, 0))])
+    gs = api.Scene(empty, background=(0.25, 0.5, 0.75))
+    p = api.make_params(2, 2, 2, 3, scene=gs)
+    g = gs.launch_host(p)
+    assert np.array_equal(g["accum"], np.broadcast_to(np.array([0.25, 0.5, 0.75, 1.0], np.float32), (2, 2, 4)))
+    assert np.array_equal(g["fb"], np.broadcast_to(np.array([137, 188, 225, 255], np.uint8), (2, 2, 4)))
+
+
+def test_single_triangle_scene(api, port):
+    one = S.SceneArrays(np.array([[100, 100, 300, 1], [500, 100, 300, 1], [300, 500, 300, 1]], np.float32),
+                        np.array([[0, 1, 2]], np.uint32), np.zeros(1, np.uint32),
+                        [dict(name="m", Kd=(0.5, 0.6, 0.7), Ke=(0, 0, 0))])
+    gs = api.Scene(one, background=(0.1, 0.2, 0.3))
+    osc = O.OracleScene(port, one, background=(0.1, 0.2, 0.3))
+    p = api.make_params(64, 64, 4, 4, nee=True, scene=gs)
+    g = gs.launch_host(p)
+    o = osc.render(p, math_mode=1, use_bvh=True)
+    assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32))
+    prim, t, anyh, _ = gs.trace(np.array([[300, 200, -1]], np.float32), np.array([[0, 0, 1]], np.float32), 0.01, 1e16, True)
+    assert prim.tolist() == [0] and t[0] == 301.0 and anyh.tolist() == [1]
+
+
+def test_max_depth_28_and_many_frames(api, port, scenes_cache):
+    arr, gs, osc = _get(scenes_cache, api, port, "material")
+    acc_g = acc_o = None
+    for f in range(5):
+        p = api.make_params(96, 54, 2, 28, frame=f, nee=True, scene=gs)
+        acc_g = gs.launch_host(p, accum=acc_g)["accum"]
+        acc_o = osc.render(p, accum=acc_o, math_mode=1, use_bvh=True)["accum"]
+    assert np.array_equal(acc_g.view(np.uint32), acc_o.view(np.uint32))
+
+
+def test_error_codes(api, port, scenes_cache):
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    p = api.make_params(16, 16, 1, 1, scene=gs)
+    p.handle = 12345
+    p.accumulationBuffer = 1
+    with pytest.raises(api.PtError) as e:
+        api.launch(p)
+    assert e.value.code == api.PT_ERR_INVALID
+    bad = S.cornell32()
+    bad.mat_ids = bad.mat_ids.copy()
+    bad.mat_ids[3] = 0xFFFFFFFF          # tinyobj's "no usemtl" id
+    with pytest.raises(api.PtError) as e:
+        api.Scene(bad)
+    assert e.value.code == api.PT_ERR_INVALID
+    bad = S.cornell32()
+    bad.indices = bad.indices.copy()
+    bad.indices[0, 0] = 10_000
+    with pytest.raises(api.PtError):
+        api.Scene(bad)
+    p = api.make_params(16, 16, 0, 1, scene=gs)
+    with pytest.raises(api.PtError):
+        gs.launch_host(p)
+
+
+# ---- device-buffer launches, partition, determinism at BASELINE size ----------------------------------------------
+def _dev_buffers(w, h):
+    import torch
+    acc = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    fb = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    return acc, fb
+
+
+def _launch_dev(api, gs, p, acc, fb, rank=None, n=None):
+    import torch
+    q = PathTraceParams.from_buffer_copy(p)
+    q.handle = gs.handle
+    q.accumulationBuffer = acc.data_ptr()
+    q.frameBuffer = fb.data_ptr()
+    stream = torch.cuda.current_stream().cuda_stream
+    if rank is None:
+        api.launch(q, stream)
+    else:
+        api.launch_partition(q, rank, n, stream)
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+def test_partition_union_is_bit_identical(api, port, scenes_cache, n_ranks):
+    import torch
+    from acgpathtracing_b200 import partition as P
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    w, h = 250, 122
+    p = api.make_params(w, h, 4, 16, frame=0, nee=True, scene=gs)
+    full_acc, full_fb = _dev_buffers(w, h)
+    _launch_dev(api, gs, p, full_acc, full_fb)
+    cap = api.partition_capacity(w, h, n_ranks)
+    assert cap == P.capacity(w, h, n_ranks)
+    comp_acc = torch.zeros((n_ranks, cap, 4), dtype=torch.float32, device="cuda")
+    comp_fb = torch.zeros((n_ranks, cap, 4), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    owner = torch.from_numpy(P.owner_map(w, h, n_ranks)).cuda()
+    for r in range(n_ranks):
+        acc, fb = _dev_buffers(w, h)
+        acc.fill_(-7.0)
+        _launch_dev(api, gs, p, acc, fb, r, n_ranks)
+        torch.cuda.synchronize()
+        mine = owner == r
+        assert torch.equal(acc[mine].view(torch.int32), full_acc[mine].view(torch.int32))     # owned pixels rendered
+        assert bool((acc[~mine] == -7.0).all())                                               # others untouched
+        api.partition_pack(acc.data_ptr(), fb.data_ptr(), comp_acc[r].data_ptr(), comp_fb[r].data_ptr(), w, h, r, n_ranks, stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(comp_acc[r].cpu().numpy(), P.pack_numpy(acc.cpu().numpy(), w, h, r, n_ranks))
+    out_acc, out_fb = _dev_buffers(w, h)
+    api.partition_unpack(comp_acc.data_ptr(), comp_fb.data_ptr(), out_acc.data_ptr(), out_fb.data_ptr(), w, h, n_ranks, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(out_acc.view(torch.int32), full_acc.view(torch.int32))
+    assert torch.equal(out_fb, full_fb)
+    assert np.array_equal(P.unpack_numpy(comp_acc.cpu().numpy(), w, h, n_ranks), full_acc.cpu().numpy())
+
+
+def test_full_size_c2_properties(api, port, scenes_cache):
+    """BASELINE config C2 shape at full resolution (1920x1080, 16 bounces, IS + NEE), one 128-spp launch:
+    determinism (two launches bit-identical), a crop of the image bit-identical to the oracle (pixels are
+    independent), every pixel written, and the running-average fold of a second launch."""
+    import torch
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    w, h, spp = 1920, 1080, 128
+    p = api.make_params(w, h, spp, 16, frame=0, nee=True, scene=gs)
+    a1, f1 = _dev_buffers(w, h)
+    a2, f2 = _dev_buffers(w, h)
+    a1.fill_(float("nan"))
+    _launch_dev(api, gs, p, a1, f1)
+    _launch_dev(api, gs, p, a2, f2)
+    torch.cuda.synchronize()
+    assert torch.equal(a1.view(torch.int32), a2.view(torch.int32)) and torch.equal(f1, f2)
+    assert bool(torch.isfinite(a1).all()) and bool((a1[..., 3] == 1.0).all()) and bool((f1[..., 3] == 255).all())
+    x0, x1, y0, y1 = 900, 932, 500, 516
+    o = osc.render(p, math_mode=1, use_bvh=True, region=(x0, x1, y0, y1))
+    ga = a1[y0:y1, x0:x1].cpu().numpy()
+    assert np.array_equal(ga.view(np.uint32), o["accum"][y0:y1, x0:x1].view(np.uint32))
+    assert np.array_equal(f1[y0:y1, x0:x1].cpu().numpy(), o["fb"][y0:y1, x0:x1])
+    # second launch folds into the running average with weight 1/2 (pathTracerPrograms.cu:803-810)
+    p1 = api.make_params(w, h, spp, 16, frame=1, nee=True, scene=gs)
+    _launch_dev(api, gs, p1, a1, f1)
+    torch.cuda.synchronize()
+    o1 = osc.render(p1, accum=o["accum"], math_mode=1, use_bvh=True, region=(x0, x1, y0, y1))
+    assert np.array_equal(a1[y0:y1, x0:x1].cpu().numpy().view(np.uint32), o1["accum"][y0:y1, x0:x1].view(np.uint32))
+    mean = a1[..., :3].mean().item()
+    assert 0.05 < mean < 2.0
