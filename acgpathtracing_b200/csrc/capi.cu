@@ -197,6 +197,7 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
         A(cudaEventRecord(e1, stream));
         A(cudaStreamSynchronize(stream));
         if (e == cudaSuccess) cudaEventElapsedTime(&s->build_ms, e0, e1);
+        if (e == cudaSuccess && n) A(cudaMemcpy(&s->bvh_depth, s->d_work_counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -320,7 +321,10 @@ int pt_launch_host(const pt_params* hp, uint64_t* h2d_bytes, uint64_t* d2h_bytes
         PT_CUDA(cudaMemcpyAsync(hp->frameBuffer, s->d_stage_frame, pixels * sizeof(uchar4), cudaMemcpyDeviceToHost, stream));
         down += pixels * sizeof(uchar4);
     }
+    unsigned long long watchdog = 0;
+    PT_CUDA(cudaMemcpyAsync(&watchdog, s->d_counters + 15, sizeof(watchdog), cudaMemcpyDeviceToHost, stream));
     PT_CUDA(cudaStreamSynchronize(stream));
+    if (watchdog) return fail(PT_ERR_CUDA, "render kernel watchdog fired (scheduler made no progress)");
     if (h2d_bytes) *h2d_bytes = up;
     if (d2h_bytes) *d2h_bytes = down;
     return PT_OK;
@@ -351,6 +355,7 @@ int pt_scene_get_counters(pt_scene* scene, pt_counters* out, int reset)
     out->n_hit[1] = h[6];
     out->n_hit[2] = h[7];
     out->n_miss = h[8];
+    if (h[15]) return fail(PT_ERR_CUDA, "render kernel watchdog fired (scheduler made no progress)");
     if (reset) PT_CUDA(cudaMemset(s->d_counters, 0, sizeof(h)));
     return PT_OK;
 }

@@ -363,6 +363,24 @@ __global__ void single_node_kernel(const float4* __restrict__ tri_bb, float4* __
     node_parent[0] = -1;
 }
 
+// Tree depth in internal nodes (root alone = 1): the traversal stack never holds more than this many entries.
+__global__ void __launch_bounds__(256) depth_kernel(int n, const int* __restrict__ node_parent,
+                                                    const int* __restrict__ leaf_parent, uint32_t* __restrict__ depth_out)
+{
+    const int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t d = 0;
+    if (leaf < n) {
+        int cur = leaf_parent[leaf];
+        while (cur >= 0) {
+            ++d;
+            cur = node_parent[cur];
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, off));
+    if ((threadIdx.x & 31) == 0 && d) atomicMax(depth_out, d);
+}
+
 #define PTB_CUDA_TRY(expr)                  \
     do {                                    \
         cudaError_t e__ = (expr);           \
@@ -396,8 +414,10 @@ cudaError_t lbvh_build(Scene& s, cudaStream_t stream)
     s.sorted_buf = src;
     const uint32_t* mort = s.d_keys[src];
     const uint32_t* prim = s.d_vals[src];
+    PTB_CUDA_TRY(cudaMemsetAsync(s.d_work_counter + 1, 0, sizeof(uint32_t), stream));
     if (n == 1) {
         single_node_kernel<<<1, 1, 0, stream>>>(s.d_tri_bb, s.d_nodes, s.d_node_parent);
+        PTB_CUDA_TRY(cudaMemsetAsync(s.d_work_counter + 1, 1, 1, stream));   // depth 1
     } else {
         karras_kernel<<<div_up(n - 1, 256), 256, 0, stream>>>(mort, prim, (int)n, s.d_left, s.d_right, s.d_node_parent,
                                                              s.d_leaf_parent);
@@ -406,6 +426,7 @@ cudaError_t lbvh_build(Scene& s, cudaStream_t stream)
                                             s.d_node_lo, s.d_node_hi, s.d_visit);
         pack_nodes_kernel<<<div_up(n - 1, 256), 256, 0, stream>>>((int)n - 1, s.d_left, s.d_right, prim, s.d_tri_bb, s.d_node_lo,
                                                                  s.d_node_hi, s.d_nodes);
+        depth_kernel<<<g, 256, 0, stream>>>((int)n, s.d_node_parent, s.d_leaf_parent, s.d_work_counter + 1);
     }
     pack_tris_kernel<<<g, 256, 0, stream>>>(n, prim, s.d_tri_in, s.d_tris);
     return cudaGetLastError();

@@ -71,13 +71,48 @@ struct BvhView {
     uint32_t n_tris;
 };
 
-// SMEM = true: the records live in shared memory (plain LDS); false: global memory through the read-only path.
-template <bool SMEM>
-__device__ __forceinline__ float4 ld4(const float4* p)
-{
-    if (SMEM) return *p;
-    return __ldg(p);
-}
+// Where the scene records are read from.  Every kernel takes one of these "fetch" policies:
+//   FetchGlobal      global memory through the read-only path (L1/L2), one copy
+//   FetchShared      one copy staged in shared memory (plain LDS)
+//   FetchSharedBanked `1 << shift` interleaved copies in shared memory: element e of copy k lives at float4 index
+//                    (e << shift) + k and lane l reads copy l & (copies - 1).  With 8 copies the 8 lanes of every
+//                    quarter-warp hit 8 different 16-byte bank groups whatever elements they ask for, so a
+//                    divergent LDS.128 costs exactly its 4 data wavefronts.
+struct FetchGlobal {
+    const float4 *nodes, *tris, *shade, *mats;
+    __device__ __forceinline__ float4 node(int i, int q) const { return __ldg(nodes + 4 * i + q); }
+    __device__ __forceinline__ float4 tri(int i, int q) const { return __ldg(tris + 3 * i + q); }
+    __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return __ldg(shade + prim); }
+    __device__ __forceinline__ float4 mat(int m, int q) const { return __ldg(mats + 3 * m + q); }
+};
+struct FetchShared {
+    const float4 *nodes, *tris, *shade, *mats;
+    __device__ __forceinline__ float4 node(int i, int q) const { return nodes[4 * i + q]; }
+    __device__ __forceinline__ float4 tri(int i, int q) const { return tris[3 * i + q]; }
+    __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim]; }
+    __device__ __forceinline__ float4 mat(int m, int q) const { return mats[3 * m + q]; }
+};
+struct FetchSharedBanked {
+    const float4 *nodes, *tris, *shade, *mats;   // each already offset by this lane's copy index
+    int shift;
+    __device__ __forceinline__ float4 node(int i, int q) const { return nodes[(4 * i + q) << shift]; }
+    __device__ __forceinline__ float4 tri(int i, int q) const { return tris[(3 * i + q) << shift]; }
+    __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim << shift]; }
+    __device__ __forceinline__ float4 mat(int m, int q) const { return mats[(3 * m + q) << shift]; }
+};
+
+// Where a traversal keeps its stack of deferred children.
+struct StackLocal {      // per-thread array (local memory)
+    int* a;
+    __device__ __forceinline__ void put(int i, int v) const { a[i] = v; }
+    __device__ __forceinline__ int get(int i) const { return a[i]; }
+};
+struct StackStrided {    // level-major words, `stride` paths apart (shared memory; bank = path id mod 32)
+    int* base;
+    int stride;
+    __device__ __forceinline__ void put(int i, int v) const { base[i * stride] = v; }
+    __device__ __forceinline__ int get(int i) const { return base[i * stride]; }
+};
 
 struct Ray {
     float3 o, d;
@@ -139,114 +174,134 @@ struct TraceCount {
 };
 
 constexpr int kStackSize = 64;   // >= depth of a radix tree over 62-bit unique keys
+constexpr int kTravDone = (int)0x80000000;        // `cur` value of a finished traversal (never a node or ~leaf)
+constexpr uint32_t kNoPrim = 0xffffffffu;
 
-// Closest hit under the total order (t, primIdx).  Logical visiting order (mirrored by the oracle, which
-// matters only for the work counters): nearer hit child first, child 1 only when strictly nearer.
-template <bool COUNT, bool SMEM>
-__device__ __forceinline__ bool trace_closest(const BvhView& bvh, float3 o, float3 d, float tmin, float tmax,
-                                              float& t_hit, uint32_t& prim_hit, uint32_t& leaf_hit, TraceCount& tc)
+// One traversal in flight.  `cur` >= 0: internal node to test next; `cur` < 0: leaf ~cur to test next;
+// kTravDone: finished.  Closest hit: `tfar` shrinks to the best t and `prim` is the best primitive under the
+// total order (t, primIdx).  Any hit: `tfar` stays the ray's tmax and `prim` becomes 0 on the first hit.
+struct Trav {
+    Ray r;
+    float tfar;
+    uint32_t prim;
+    int cur, sp;
+};
+
+__device__ __forceinline__ void trav_begin(Trav& t, float3 o, float3 d, float tmax, bool have_tris)
 {
-    float best_t = tmax;
-    uint32_t best_prim = 0xffffffffu;
-    uint32_t best_leaf = 0xffffffffu;
-    if (bvh.n_tris == 0) return false;
-    const Ray r = make_ray(o, d);
-    int stack[kStackSize];
-    int sp = 0;
-    int cur = 0;
-    for (;;) {
-        if (cur >= 0) {
-            const float4 q0 = ld4<SMEM>(bvh.nodes + 4 * cur + 0);
-            const float4 q1 = ld4<SMEM>(bvh.nodes + 4 * cur + 1);
-            const float4 q2 = ld4<SMEM>(bvh.nodes + 4 * cur + 2);
-            const float4 q3 = ld4<SMEM>(bvh.nodes + 4 * cur + 3);
-            if (COUNT) tc.n_node++;
-            float tn0, tn1;
-            const bool h0 = ray_box(r, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), tmin, best_t, tn0);
-            const bool h1 = ray_box(r, f3(q2.x, q2.y, q2.z), f3(q3.x, q3.y, q3.z), tmin, best_t, tn1);
-            const int c0 = __float_as_int(q0.w), c1 = __float_as_int(q1.w);
-            if (h0 && h1) {
-                const bool swap = tn1 < tn0;
-                stack[sp++] = swap ? c0 : c1;
-                cur = swap ? c1 : c0;
-                continue;
-            } else if (h0) {
-                cur = c0;
-                continue;
-            } else if (h1) {
-                cur = c1;
-                continue;
-            }
-        } else {
-            const int leaf = ~cur;
-            const float4 t0 = ld4<SMEM>(bvh.tris + 3 * leaf + 0);
-            const float4 t1 = ld4<SMEM>(bvh.tris + 3 * leaf + 1);
-            const float4 t2 = ld4<SMEM>(bvh.tris + 3 * leaf + 2);
-            if (COUNT) tc.n_tri++;
-            float t;
-            if (ray_tri(r, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), tmin, tmax, t)) {
-                const uint32_t prim = __float_as_uint(t0.w);
-                if (t < best_t || (t == best_t && prim < best_prim)) {
-                    best_t = t;
-                    best_prim = prim;
-                    best_leaf = (uint32_t)leaf;
-                }
-            }
-        }
-        if (sp == 0) break;
-        cur = stack[--sp];
+    t.r = make_ray(o, d);
+    t.tfar = tmax;
+    t.prim = kNoPrim;
+    t.sp = 0;
+    t.cur = have_tris ? 0 : kTravDone;
+}
+
+template <class STK>
+__device__ __forceinline__ void trav_pop(Trav& t, const STK& stack)
+{
+    if (t.sp > 0) {
+        t.cur = stack.get(--t.sp);
+    } else {
+        t.cur = kTravDone;
     }
-    t_hit = best_t;
-    prim_hit = best_prim;
-    leaf_hit = best_leaf;
-    return best_prim != 0xffffffffu;
+}
+
+// Internal-node step.  Logical visiting order (mirrored by the oracle, which matters only for the work counters):
+// nearer hit child first, child 1 only when strictly nearer.  Uses r.inv / r.ood only.
+template <class FETCH, class STK>
+__device__ __forceinline__ void trav_node_step(Trav& t, const STK& stack, const FETCH& f, float tmin)
+{
+    const float4 q0 = f.node(t.cur, 0);
+    const float4 q1 = f.node(t.cur, 1);
+    const float4 q2 = f.node(t.cur, 2);
+    const float4 q3 = f.node(t.cur, 3);
+    float tn0, tn1;
+    const bool h0 = ray_box(t.r, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), tmin, t.tfar, tn0);
+    const bool h1 = ray_box(t.r, f3(q2.x, q2.y, q2.z), f3(q3.x, q3.y, q3.z), tmin, t.tfar, tn1);
+    const int c0 = __float_as_int(q0.w), c1 = __float_as_int(q1.w);
+    if (h0 && h1) {
+        const bool swap = tn1 < tn0;
+        stack.put(t.sp++, swap ? c0 : c1);
+        t.cur = swap ? c1 : c0;
+    } else if (h0) {
+        t.cur = c0;
+    } else if (h1) {
+        t.cur = c1;
+    } else {
+        trav_pop(t, stack);
+    }
+}
+
+// Leaf step.  any = false: closest hit in (tmin, tmax_closest) under (t, primIdx); any = true: the first hit in
+// (tmin, t.tfar) ends the traversal.  Uses r.o / r.d only.
+template <class FETCH, class STK>
+__device__ __forceinline__ void trav_leaf_step(Trav& t, const STK& stack, const FETCH& f, bool any, float tmin,
+                                               float tmax_closest)
+{
+    const int leaf = ~t.cur;
+    const float4 t0 = f.tri(leaf, 0);
+    const float4 t1 = f.tri(leaf, 1);
+    const float4 t2 = f.tri(leaf, 2);
+    float th;
+    const bool hit = ray_tri(t.r, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), tmin,
+                             any ? t.tfar : tmax_closest, th);
+    if (hit) {
+        if (any) {
+            t.prim = 0u;
+            t.cur = kTravDone;
+            return;
+        }
+        const uint32_t prim = __float_as_uint(t0.w);
+        if (th < t.tfar || (th == t.tfar && prim < t.prim)) {
+            t.tfar = th;
+            t.prim = prim;
+        }
+    }
+    trav_pop(t, stack);
+}
+
+// Whole-ray wrappers (batch ray queries; the render kernels schedule the steps themselves).
+template <bool COUNT, class FETCH>
+__device__ __forceinline__ bool trace_closest(const FETCH& f, bool have_tris, float3 o, float3 d, float tmin, float tmax,
+                                              float& t_hit, uint32_t& prim_hit, TraceCount& tc)
+{
+    Trav t;
+    int stack_mem[kStackSize];
+    const StackLocal stack{stack_mem};
+    trav_begin(t, o, d, tmax, have_tris);
+    while (t.cur != kTravDone) {
+        if (t.cur >= 0) {
+            if (COUNT) tc.n_node++;
+            trav_node_step(t, stack, f, tmin);
+        } else {
+            if (COUNT) tc.n_tri++;
+            trav_leaf_step(t, stack, f, false, tmin, tmax);
+        }
+    }
+    t_hit = t.tfar;
+    prim_hit = t.prim;
+    return t.prim != kNoPrim;
 }
 
 // Any hit in (tmin, tmax): boolean, order-free.
-template <bool COUNT, bool SMEM>
-__device__ __forceinline__ bool trace_any(const BvhView& bvh, float3 o, float3 d, float tmin, float tmax, TraceCount& tc)
+template <bool COUNT, class FETCH>
+__device__ __forceinline__ bool trace_any(const FETCH& f, bool have_tris, float3 o, float3 d, float tmin, float tmax,
+                                          TraceCount& tc)
 {
-    if (bvh.n_tris == 0) return false;
-    const Ray r = make_ray(o, d);
-    int stack[kStackSize];
-    int sp = 0;
-    int cur = 0;
-    for (;;) {
-        if (cur >= 0) {
-            const float4 q0 = ld4<SMEM>(bvh.nodes + 4 * cur + 0);
-            const float4 q1 = ld4<SMEM>(bvh.nodes + 4 * cur + 1);
-            const float4 q2 = ld4<SMEM>(bvh.nodes + 4 * cur + 2);
-            const float4 q3 = ld4<SMEM>(bvh.nodes + 4 * cur + 3);
+    Trav t;
+    int stack_mem[kStackSize];
+    const StackLocal stack{stack_mem};
+    trav_begin(t, o, d, tmax, have_tris);
+    while (t.cur != kTravDone) {
+        if (t.cur >= 0) {
             if (COUNT) tc.n_node++;
-            float tn0, tn1;
-            const bool h0 = ray_box(r, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), tmin, tmax, tn0);
-            const bool h1 = ray_box(r, f3(q2.x, q2.y, q2.z), f3(q3.x, q3.y, q3.z), tmin, tmax, tn1);
-            const int c0 = __float_as_int(q0.w), c1 = __float_as_int(q1.w);
-            if (h0 && h1) {
-                const bool swap = tn1 < tn0;
-                stack[sp++] = swap ? c0 : c1;
-                cur = swap ? c1 : c0;
-                continue;
-            } else if (h0) {
-                cur = c0;
-                continue;
-            } else if (h1) {
-                cur = c1;
-                continue;
-            }
+            trav_node_step(t, stack, f, tmin);
         } else {
-            const int leaf = ~cur;
-            const float4 t0 = ld4<SMEM>(bvh.tris + 3 * leaf + 0);
-            const float4 t1 = ld4<SMEM>(bvh.tris + 3 * leaf + 1);
-            const float4 t2 = ld4<SMEM>(bvh.tris + 3 * leaf + 2);
             if (COUNT) tc.n_tri++;
-            float t;
-            if (ray_tri(r, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), tmin, tmax, t)) return true;
+            trav_leaf_step(t, stack, f, true, tmin, tmax);
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
     }
-    return false;
+    return t.prim != kNoPrim;
 }
 
 }  // namespace ptd

@@ -21,10 +21,13 @@ struct Scene {
     uint64_t magic = kSceneMagic;
     int device = 0;
     uint32_t n_verts = 0, n_tris = 0, n_mats = 0, n_nodes = 0;
+    uint32_t bvh_depth = 0;        // internal nodes on the longest root-to-leaf chain
     float background[3] = {0.f, 0.f, 0.f};
     float build_ms = 0.f;
-    int pipeline = 0;              // 0 auto, 1 persistent thread-per-path, 2 CTA-local wavefront
+    int pipeline = 0;              // 0 auto (wavefront when it can hold the scene), 1 persistent lane-per-path, 2 CTA-local wavefront
+    int wf_tune[7] = {1, 1, 1, 1, 8, 3, 28};   // wavefront: vote weights NODE/LEAF/SHADE/END, NODE steps per batch, keep threshold / 8, full-warp columns
     bool count_enabled = false;
+    int sched[5] = {1, 1, 1, 1, 20};   // render-kernel stage weights (NODE, LEAF, SHADE, END) and NODE fast-path lane count
 
     // inputs (device copies of the TinyObjWrapper arrays)
     float4* d_verts = nullptr;
@@ -54,13 +57,12 @@ struct Scene {
     float4* d_tris = nullptr;         // 3 per leaf (leaf order)
 
     // launch-time scratch
-    uint32_t* d_work_counter = nullptr;
+    uint32_t* d_work_counter = nullptr;         // [0] pixel fetch counter  [1] LBVH depth (build)
     unsigned long long* d_counters = nullptr;   // pt_counters layout (10 x u64)
     float4* d_stage_accum = nullptr;            // pt_launch_host staging
     uchar4* d_stage_frame = nullptr;
     size_t stage_pixels = 0;
-    void* d_wf_state = nullptr;                 // pipeline 2 scratch (wavefront.cu)
-    size_t wf_state_bytes = 0;
+    void* d_wf_state = nullptr;                 // unused
 
     // last launch
     uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0;
@@ -81,6 +83,10 @@ cudaError_t partition_unpack(const void* accum_compact_all, const void* frame_co
                              void* frame_full, uint32_t width, uint32_t height, uint32_t n_ranks, cudaStream_t stream);
 uint32_t partition_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks);
 uint32_t partition_max_owned_tiles(uint32_t width, uint32_t height, uint32_t n_ranks);
+
+// wavefront.cu
+bool wavefront_supported(const Scene& s);
+cudaError_t wavefront_launch(Scene& s, const ptd::LaunchConst& lc, bool probe, cudaStream_t stream);
 
 // microbench.cu
 cudaError_t bench_fp32_peak(double* tflops);

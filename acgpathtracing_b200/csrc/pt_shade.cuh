@@ -37,7 +37,11 @@ struct LaunchConst {   // everything a launch needs, passed by value as a kernel
     uint32_t tiles_x, tiles_y, rank, n_ranks, n_owned_tiles;
     // optional outputs
     unsigned long long* counters;   // pt_counters layout, or null
-    uint32_t* work_counter;         // dynamic tile fetch
+    uint32_t* work_counter;         // dynamic pixel fetch
+    unsigned long long* error_flag; // set when a kernel watchdog fired (never expected)
+    // stage scheduling of the render kernel: weights of the NODE / LEAF / SHADE / END votes and the lane count at
+    // or above which the NODE stage runs without a full vote
+    int sched[5];
     // probes (null on the hot path)
     uint32_t* dbg_seed_after_jitter;
     float* dbg_primary_dir;
@@ -197,18 +201,18 @@ struct ShadowQuery {    // NEE probe ray produced by shading (pathTracerPrograms
 // __closesthit__diffuse__ch :866-1031 up to (not including) the occlusion trace.
 // In: path (ray that hit, attenuation, seed, depth), hit (prim, t).  Out: path advanced to the next
 // ray/attenuation/seed; emission, radiance, done; the shadow query.  `hit_type` receives the BSDF type.
-// `tri_shade` / `mats` point to shared memory when SMEM, else to global memory; `l_area` is
-// length(cross(light.v1, light.v2)) (:1021), constant per launch.
-template <bool SMEM>
-__device__ __forceinline__ void shade_hit(const LaunchConst& lc, const float4* tri_shade, const float4* mats, float l_area,
+// `f` says where the per-triangle shading records and the material table live (pt_device.cuh); `l_area` is
+// length(cross(light.v1, light.v2)) (:1021), constant per launch.  `mat_id` receives the material index.
+template <class FETCH>
+__device__ __forceinline__ void shade_hit(const LaunchConst& lc, const FETCH& f, float l_area,
                                           uint32_t prim, float t_hit, Path& p, float3& emission, float3& radiance,
-                                          bool& done, ShadowQuery& sq, int& hit_type)
+                                          bool& done, ShadowQuery& sq, int& hit_type, int& mat_id)
 {
-    const float4 ts = ld4<SMEM>(tri_shade + prim);
+    const float4 ts = f.tri_shade(prim);
     DevMaterial m;
     {
-        const float4* mp = mats + 3 * __float_as_int(ts.w);
-        const float4 m0 = ld4<SMEM>(mp + 0), m1 = ld4<SMEM>(mp + 1), m2 = ld4<SMEM>(mp + 2);
+        mat_id = __float_as_int(ts.w);
+        const float4 m0 = f.mat(mat_id, 0), m1 = f.mat(mat_id, 1), m2 = f.mat(mat_id, 2);
         m.diffuse = f3(m0.x, m0.y, m0.z);
         m.ior = m0.w;
         m.emission = f3(m1.x, m1.y, m1.z);

@@ -1,18 +1,24 @@
-// render.cu -- the render kernels: what optixLaunch(width, height, 1) runs in the reference
+// render.cu -- the render kernel: what optixLaunch(width, height, 1) runs in the reference
 // (__raygen__rg / __closesthit__diffuse__ch / __miss__ms, pathTracerPrograms.cu:707-1031), re-designed for
 // sm_100a without OptiX.
 //
-// Pipeline 1, "persistent path state machine" (this file's render_persistent_kernel):
-//   * one resident warp per SM sub-partition slot, grid = SMs x occupancy; warps pull 8x4-pixel tiles from a
-//     global counter (dynamic load balance), one lane = one pixel;
-//   * a lane keeps ONE path in flight and regenerates the pixel's next sample in place when the path ends,
-//     so the per-pixel float sums run in the reference's order (samples in sequence, segments in path order)
-//     and warps stay full until a pixel has used all its samples;
-//   * the whole scene (64-B BVH nodes, 48-B triangles, normals, materials) is staged into shared memory when
-//     it fits (Cornell box: 4 KB), else read through the read-only path from L1/L2.
-// Pipeline 2 (CTA-local wavefront with compacted queues) lives in wavefront.cu.
+// render_persistent_kernel: a persistent grid (SMs x occupancy CTAs) of warps; one LANE = one pixel = one path
+// in flight, kept entirely in registers.
+//   * Per-pixel order is the reference's: samples in sequence, segments in path order, so the float sums and the
+//     RNG chaining are bit-identical; when a path ends the lane regenerates the pixel's next sample in
+//     place, and when the pixel has used all its samples the lane writes it and takes the next pixel index from a
+//     global counter (8x4-pixel tiles, tile-major), so lanes never wait for the slowest pixel of a tile.
+//   * A lane is always in one of four stages: NODE (internal-node slab tests), LEAF (triangle test), SHADE
+//     (closest-hit shading + BSDF sample + NEE set-up) or END (miss / shadow result, accumulate, Russian roulette,
+//     next ray or next sample or next pixel).  Radiance rays and shadow rays share the same traversal code.
+//     Each round the warp votes (ballot + popc) and runs the stage with the most waiting lanes, so every stage
+//     body is executed once per round for many lanes instead of once per lane-specific control path.
+//   * The whole scene (64-B BVH nodes, 48-B triangles, normals, materials) is staged into shared memory when it
+//     fits (Cornell box: 4 KB), else read through the read-only path from L1/L2.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "pt_scene.h"
 #include "pt_shade.cuh"
@@ -22,6 +28,7 @@ namespace ptb {
 using namespace ptd;
 
 constexpr int kBlock = 256;
+constexpr int kMinBlocksPerSm = 2;
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr size_t kSmemSceneLimit = 40 * 1024;   // stage the scene in shared memory up to this size
 
@@ -45,52 +52,87 @@ __host__ __device__ inline size_t staged_scene_float4s(uint32_t n_nodes, uint32_
     return 4 * (size_t)n_nodes + 3 * (size_t)n_tris + (size_t)n_tris + 3 * (size_t)n_mats;
 }
 
+template <bool SMEM> struct FetchSelect { typedef FetchGlobal type; };
+template <> struct FetchSelect<true> { typedef FetchShared type; };
+
+enum : int { PH_RAD = 0, PH_SHADOW = 1, PH_END = 2, PH_IDLE = 3 };
+
+// Work item j of this rank -> pixel: owned tile j / 32 (image tile rank + k * n_ranks), pixel j % 32 of the 8x4 tile.
+// Items that fall outside a ragged image edge are skipped by taking the next index.
+__device__ __forceinline__ bool take_pixel(const LaunchConst& lc, uint32_t n_work, uint32_t j, uint32_t& ix, uint32_t& iy)
+{
+    for (;;) {
+        if (j >= n_work) return false;
+        const uint32_t tile = lc.rank + (j >> 5) * lc.n_ranks;
+        const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
+        ix = tx * 8u + (j & 7u);
+        iy = ty * 4u + ((j >> 3) & 3u);
+        if (ix < lc.width && iy < lc.height) return true;
+        j = atomicAdd(lc.work_counter, 1u);
+    }
+}
+
 template <bool COUNT, bool PROBE, bool SMEM>
-__global__ void __launch_bounds__(kBlock, 2) render_persistent_kernel(const __grid_constant__ LaunchConst lc)
+__global__ void __launch_bounds__(kBlock, kMinBlocksPerSm) render_persistent_kernel(const __grid_constant__ LaunchConst lc)
 {
     extern __shared__ float4 smem4[];
-    BvhView bvh = lc.bvh;
-    const float4* tri_shade = lc.tri_shade;
-    const float4* mats = reinterpret_cast<const float4*>(lc.mats);
+    typename FetchSelect<SMEM>::type f;
+    f.nodes = lc.bvh.nodes;
+    f.tris = lc.bvh.tris;
+    f.shade = lc.tri_shade;
+    f.mats = reinterpret_cast<const float4*>(lc.mats);
     if (SMEM) {
         const uint32_t n_nodes4 = 4 * lc.n_nodes, n_tris4 = 3 * lc.bvh.n_tris, n_sh = lc.bvh.n_tris, n_m4 = 3 * lc.n_mats;
         float4* s_nodes = smem4;
         float4* s_tris = s_nodes + n_nodes4;
         float4* s_shade = s_tris + n_tris4;
         float4* s_mats = s_shade + n_sh;
-        for (uint32_t i = threadIdx.x; i < n_nodes4; i += kBlock) s_nodes[i] = __ldg(lc.bvh.nodes + i);
-        for (uint32_t i = threadIdx.x; i < n_tris4; i += kBlock) s_tris[i] = __ldg(lc.bvh.tris + i);
-        for (uint32_t i = threadIdx.x; i < n_sh; i += kBlock) s_shade[i] = __ldg(lc.tri_shade + i);
-        for (uint32_t i = threadIdx.x; i < n_m4; i += kBlock) s_mats[i] = __ldg(mats + i);
+        for (uint32_t i = threadIdx.x; i < n_nodes4; i += kBlock) s_nodes[i] = __ldg(f.nodes + i);
+        for (uint32_t i = threadIdx.x; i < n_tris4; i += kBlock) s_tris[i] = __ldg(f.tris + i);
+        for (uint32_t i = threadIdx.x; i < n_sh; i += kBlock) s_shade[i] = __ldg(f.shade + i);
+        for (uint32_t i = threadIdx.x; i < n_m4; i += kBlock) s_mats[i] = __ldg(f.mats + i);
         __syncthreads();
-        bvh.nodes = s_nodes;
-        bvh.tris = s_tris;
-        tri_shade = s_shade;
-        mats = s_mats;
+        f.nodes = s_nodes;
+        f.tris = s_tris;
+        f.shade = s_shade;
+        f.mats = s_mats;
     }
 
     const float l_area = length(cross(lc.l_v1, lc.l_v2));   // :1021
     const int lane = threadIdx.x & 31;
+    const bool have_tris = lc.bvh.n_tris != 0;
+    const uint32_t n_work = lc.n_owned_tiles * 32u;
     ThreadCounters ctr = {};
-    TraceCount tc = {0, 0};
 
-    for (;;) {
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(lc.work_counter, 1u);
-        k = __shfl_sync(kFull, k, 0);
-        if (k >= lc.n_owned_tiles) break;
-        const uint32_t tile = lc.rank + k * lc.n_ranks;
-        const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
-        const uint32_t ix = tx * 8u + (uint32_t)(lane & 7), iy = ty * 4u + (uint32_t)(lane >> 3);
-        if (ix < lc.width && iy < lc.height) {
+    // ---- lane state ------------------------------------------------------------------------------------------
+    uint32_t ix = 0, iy = 0, pixel_seed = 0, left = 0;   // pixel, its seed (advanced by jitter draws only), samples left
+    float3 result = f3(0.0f);                            // sum over this launch's samples (:724-780)
+    Path p;                                              // next ray / attenuation / path seed / depth
+    p.o = p.d = p.att = f3(0.0f);
+    p.seed = 0;
+    p.depth = 0;
+    Trav t;                                              // traversal in flight (radiance or shadow ray)
+    t.r.o = t.r.d = t.r.inv = t.r.ood = f3(0.0f);
+    t.tfar = 0.0f;
+    t.prim = kNoPrim;
+    t.sp = 0;
+    t.cur = kTravDone;
+    int stack_mem[kStackSize];
+    const StackLocal stack{stack_mem};
+    float3 rad = f3(0.0f), add = f3(0.0f);               // radiance of the segment; NEE term added if unoccluded
+    bool done = false;
+    int phase = PH_IDLE;
+
+    {   // first pixel: 32 consecutive work items per warp (one 8x4 tile)
+        uint32_t j = 0;
+        if (lane == 0) j = atomicAdd(lc.work_counter, 32u);
+        j = __shfl_sync(kFull, j, 0) + (uint32_t)lane;
+        if (take_pixel(lc, n_work, j, ix, iy)) {
             const uint32_t image_index = iy * lc.width + ix;
-            uint32_t pixel_seed = tea4(image_index, lc.frame);                                 // :721
-            float3 result = f3(0.0f);
-            uint32_t left = lc.spp;
-            Path p;
+            pixel_seed = tea4(image_index, lc.frame);                                          // :721
+            left = lc.spp;
             generate_camera_ray(lc, ix, iy, pixel_seed, p);
-            if (COUNT) ctr.n_samples++;
-            bool first = true;
+            if (COUNT) ctr.n_samples++, ctr.n_radiance++;
             if (PROBE) {
                 if (lc.dbg_seed_after_jitter) lc.dbg_seed_after_jitter[image_index] = pixel_seed;
                 if (lc.dbg_primary_dir) {
@@ -99,68 +141,149 @@ __global__ void __launch_bounds__(kBlock, 2) render_persistent_kernel(const __gr
                     lc.dbg_primary_dir[3 * image_index + 2] = p.d.z;
                 }
             }
-            for (;;) {
-                // traceRadiance :577-635, tmin 0.01, tmax 1e16 (:754-755)
-                float t_hit;
-                uint32_t prim, leaf;
-                if (COUNT) ctr.n_radiance++;
-                const bool hit = trace_closest<COUNT, SMEM>(bvh, p.o, p.d, 0.01f, 1e16f, t_hit, prim, leaf, tc);
-                if (PROBE && first) {
-                    if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = hit ? (int32_t)prim : -1;
-                    if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = hit ? t_hit : 0.0f;
-                    first = false;
+            trav_begin(t, p.o, p.d, 1e16f, have_tris);                                         // tmax :755
+            phase = PH_RAD;
+        }
+    }
+
+    const int w_node = lc.sched[0], w_leaf = lc.sched[1], w_shade = lc.sched[2], w_end = lc.sched[3];
+    const int node_min = lc.sched[4];
+
+    for (;;) {
+        // ---- vote -------------------------------------------------------------------------------------------
+        const int n_node = __popc(__ballot_sync(kFull, t.cur >= 0));
+        int stage = 0;
+        if (n_node < node_min) {
+            const bool fin = t.cur == kTravDone;
+            const bool sh = fin && phase == PH_RAD && t.prim != kNoPrim;
+            const bool en = fin && !sh && phase != PH_IDLE;
+            const int n_leaf = __popc(__ballot_sync(kFull, !fin && t.cur < 0));
+            const int n_sh = __popc(__ballot_sync(kFull, sh));
+            const int n_en = __popc(__ballot_sync(kFull, en));
+            if ((n_node | n_leaf | n_sh | n_en) == 0) break;
+            const int s0 = n_node * w_node, s1 = n_leaf * w_leaf, s2 = n_sh * w_shade, s3 = n_en * w_end;
+            if (s0 >= s1 && s0 >= s2 && s0 >= s3 && n_node) {
+                stage = 0;
+            } else if (s1 >= s2 && s1 >= s3 && n_leaf) {
+                stage = 1;
+            } else if (s2 >= s3 && n_sh) {
+                stage = 2;
+            } else if (n_en) {
+                stage = 3;
+            } else {
+                stage = n_node ? 0 : (n_leaf ? 1 : 2);
+            }
+        }
+
+        if (stage == 0) {
+            // ---- NODE: two child-box slab tests, descend / push / pop ----------------------------------------
+            if (t.cur >= 0) {
+                if (COUNT) ctr.n_node++;
+                trav_node_step(t, stack, f, 0.01f);                              // tmin :754
+            }
+        } else if (stage == 1) {
+            // ---- LEAF: one triangle test; a shadow ray ends on its first hit (traceOcclusion :651-684) -------
+            if (t.cur < 0 && t.cur != kTravDone) {
+                if (COUNT) ctr.n_tri++;
+                trav_leaf_step(t, stack, f, phase == PH_SHADOW, 0.01f, 1e16f);
+            }
+        } else if (stage == 2) {
+            // ---- SHADE: __closesthit__diffuse__ch :866-1031 for lanes whose radiance ray found a hit --------
+            if (t.cur == kTravDone && phase == PH_RAD && t.prim != kNoPrim) {
+                if (PROBE && left == lc.spp && p.depth == 0) {
+                    const uint32_t image_index = iy * lc.width + ix;
+                    if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = (int32_t)t.prim;
+                    if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = t.tfar;
                 }
-                float3 emission, radiance;
-                bool done;
-                if (hit) {
-                    ShadowQuery sq;
-                    int hit_type;
-                    shade_hit<SMEM>(lc, tri_shade, mats, l_area, prim, t_hit, p, emission, radiance, done, sq, hit_type);
-                    if (COUNT) {
-                        ctr.n_hit0 += hit_type == 0;
-                        ctr.n_hit1 += hit_type == 1;
-                        ctr.n_hit2 += hit_type == 2;
-                    }
-                    if (sq.want) {
-                        // traceOcclusion :651-684: "anything in (0.01, Ldist - 0.01)" 
-                        if (COUNT) ctr.n_shadow++;
-                        if (!trace_any<COUNT, SMEM>(bvh, sq.org, sq.dir, 0.01f, sq.tmax, tc)) radiance = radiance + sq.add;
-                    }
+                ShadowQuery sq;
+                int hit_type, mat_id;
+                float3 emission;
+                shade_hit(lc, f, l_area, t.prim, t.tfar, p, emission, rad, done, sq, hit_type, mat_id);
+                result = result + emission;                                                    // :760
+                if (COUNT) {
+                    ctr.n_hit0 += hit_type == 0;
+                    ctr.n_hit1 += hit_type == 1;
+                    ctr.n_hit2 += hit_type == 2;
+                }
+                if (sq.want) {
+                    // traceOcclusion :651-684: "anything in (0.01, Ldist - 0.01)" 
+                    if (COUNT) ctr.n_shadow++;
+                    add = sq.add;
+                    trav_begin(t, sq.org, sq.dir, sq.tmax, true);
+                    phase = PH_SHADOW;
                 } else {
-                    // __miss__ms :833-847
-                    radiance = lc.background;
-                    emission = f3(0.0f);
-                    done = true;
-                    if (COUNT) ctr.n_miss++;
+                    phase = PH_END;
                 }
-                result = result + emission;                                                     // :760
-                result = result + radiance * p.att;                                             // :761
-                const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                           // :763
-                const bool rr = rnd(p.seed) > pr;                                               // :765
-                if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                          // :767
-                    if (--left == 0u) break;
-                    generate_camera_ray(lc, ix, iy, pixel_seed, p);                             // next sample, in place
-                    if (COUNT) ctr.n_samples++;
+            }
+        } else {
+            // ---- END: finish the segment (__miss__ms :833-847, shadow result, :760-778), start the next ray -----
+            if (t.cur == kTravDone && phase != PH_IDLE && !(phase == PH_RAD && t.prim != kNoPrim)) {
+                if (phase == PH_RAD) {                  // miss
+                    if (PROBE && left == lc.spp && p.depth == 0) {
+                        const uint32_t image_index = iy * lc.width + ix;
+                        if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
+                        if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = 0.0f;
+                    }
+                    rad = lc.background;
+                    done = true;
+                    result = result + f3(0.0f);                                                // emissionColor = 0, :760
+                    if (COUNT) ctr.n_miss++;
+                } else if (phase == PH_SHADOW) {
+                    if (t.prim == kNoPrim) rad = rad + add;                                    // unoccluded, :1019-1024
+                }
+                result = result + rad * p.att;                                                 // :761
+                const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                          // :763
+                const bool rr = rnd(p.seed) > pr;                                              // :765
+                bool alive = true;
+                if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                         // :767
+                    if (--left == 0u) {
+                        const uint32_t image_index = iy * lc.width + ix;
+                        write_pixel(lc, image_index, result);
+                        if (PROBE) {
+                            if (lc.dbg_final_path_seed) lc.dbg_final_path_seed[image_index] = p.seed;
+                            if (lc.dbg_final_pixel_seed) lc.dbg_final_pixel_seed[image_index] = pixel_seed;
+                        }
+                        alive = take_pixel(lc, n_work, atomicAdd(lc.work_counter, 1u), ix, iy);
+                        if (alive) {
+                            pixel_seed = tea4(iy * lc.width + ix, lc.frame);                   // :721
+                            result = f3(0.0f);
+                            left = lc.spp;
+                        }
+                    }
+                    if (alive) {
+                        generate_camera_ray(lc, ix, iy, pixel_seed, p);                        // next sample, in place
+                        if (COUNT) ctr.n_samples++;
+                        if (PROBE && left == lc.spp) {
+                            const uint32_t image_index = iy * lc.width + ix;
+                            if (lc.dbg_seed_after_jitter) lc.dbg_seed_after_jitter[image_index] = pixel_seed;
+                            if (lc.dbg_primary_dir) {
+                                lc.dbg_primary_dir[3 * image_index + 0] = p.d.x;
+                                lc.dbg_primary_dir[3 * image_index + 1] = p.d.y;
+                                lc.dbg_primary_dir[3 * image_index + 2] = p.d.z;
+                            }
+                        }
+                    }
                 } else {
                     p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
                     ++p.depth;
                 }
-            }
-            write_pixel(lc, image_index, result);
-            if (PROBE) {
-                if (lc.dbg_final_path_seed) lc.dbg_final_path_seed[image_index] = p.seed;
-                if (lc.dbg_final_pixel_seed) lc.dbg_final_pixel_seed[image_index] = pixel_seed;
+                if (alive) {
+                    if (COUNT) ctr.n_radiance++;
+                    trav_begin(t, p.o, p.d, 1e16f, have_tris);                                 // traceRadiance :577-635
+                    phase = PH_RAD;
+                } else {
+                    phase = PH_IDLE;
+                }
             }
         }
-        __syncwarp();
     }
 
     if (COUNT && lc.counters) {
         flush_counter(lc.counters + 0, ctr.n_samples);
         flush_counter(lc.counters + 1, ctr.n_radiance);
         flush_counter(lc.counters + 2, ctr.n_shadow);
-        flush_counter(lc.counters + 3, tc.n_node);
-        flush_counter(lc.counters + 4, tc.n_tri);
+        flush_counter(lc.counters + 3, ctr.n_node);
+        flush_counter(lc.counters + 4, ctr.n_tri);
         flush_counter(lc.counters + 5, ctr.n_hit0);
         flush_counter(lc.counters + 6, ctr.n_hit1);
         flush_counter(lc.counters + 7, ctr.n_hit2);
@@ -176,17 +299,22 @@ __global__ void __launch_bounds__(256) trace_rays_kernel(BvhView bvh, const floa
 {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TraceCount tc = {0, 0};
+    FetchGlobal f;
+    f.nodes = bvh.nodes;
+    f.tris = bvh.tris;
+    f.shade = nullptr;
+    f.mats = nullptr;
     if (i < n) {
         const float3 o = f3(org[3 * i], org[3 * i + 1], org[3 * i + 2]);
         const float3 d = f3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
         if (prim_out || t_out) {
             float t;
-            uint32_t prim, leaf;
-            const bool hit = trace_closest<true, false>(bvh, o, d, tmin[i], tmax[i], t, prim, leaf, tc);
+            uint32_t prim;
+            const bool hit = trace_closest<true>(f, bvh.n_tris != 0, o, d, tmin[i], tmax[i], t, prim, tc);
             if (prim_out) prim_out[i] = hit ? (int32_t)prim : -1;
             if (t_out) t_out[i] = hit ? t : 0.0f;
         }
-        if (any_out) any_out[i] = trace_any<true, false>(bvh, o, d, tmin[i], tmax[i], tc) ? 1 : 0;
+        if (any_out) any_out[i] = trace_any<true>(f, bvh.n_tris != 0, o, d, tmin[i], tmax[i], tc) ? 1 : 0;
     }
     if (counters2) {
         flush_counter(counters2 + 0, tc.n_node);
@@ -351,6 +479,13 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.n_owned_tiles = partition_owned_tiles(params.width, params.height, rank, n_ranks);
     lc.counters = s.count_enabled ? s.d_counters : nullptr;
     lc.work_counter = s.d_work_counter;
+    lc.error_flag = s.d_counters + 15;
+    for (int i = 0; i < 5; ++i) lc.sched[i] = s.sched[i];
+    if (const char* env = getenv("PTB_SCHED")) {   // tuning experiments: "w_node,w_leaf,w_shade,w_end,node_min"
+        int v[5];
+        if (sscanf(env, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]) == 5)
+            for (int i = 0; i < 5; ++i) lc.sched[i] = v[i];
+    }
     bool probe = false;
     if (probe_overrides) {
         lc.dbg_seed_after_jitter = probe_overrides->dbg_seed_after_jitter;
@@ -362,6 +497,10 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
         probe = true;
     }
     if (lc.n_owned_tiles == 0) return cudaSuccess;
+
+    // pipeline 2 (wavefront.cu) whenever it can hold the scene, unless pipeline 1 was asked for
+    if (s.pipeline != 1 && wavefront_supported(s)) return wavefront_launch(s, lc, probe, stream);
+    if (s.pipeline == 2) return cudaErrorInvalidConfiguration;
 
     const size_t staged = staged_scene_float4s(s.n_nodes, s.n_tris, s.n_mats) * sizeof(float4);
     const bool smem = s.n_tris > 0 && staged <= kSmemSceneLimit;

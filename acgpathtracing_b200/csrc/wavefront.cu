@@ -1,0 +1,567 @@
+// wavefront.cu -- pipeline 2, the CTA-local wavefront render kernel (the default for every scene it can hold).
+//
+// Same arithmetic per path as render_persistent_kernel (render.cu) and as the reference programs
+// (pathTracerPrograms.cu:707-1031) -- only the scheduling differs, so results are bit-identical.
+//
+// Why: a path alternates between four kinds of work of very different cost -- NODE (two slab tests), LEAF (one
+// triangle test), SHADE (closest-hit shading, BSDF sample, NEE set-up) and END (miss / shadow result, accumulate,
+// Russian roulette, next ray / next sample / next pixel).  With one path per lane held in registers the 32 lanes
+// of a warp are spread over the four kinds and each kind runs with a handful of lanes (ncu: 25 % useful SIMT
+// efficiency, profiles/r1_v2_*).  Here paths live in SHARED MEMORY and lanes are just workers:
+//   * one persistent CTA per SM owns NP = 32 * P paths (P <= 32); path id = 32 * j + c belongs to "column" c and
+//     is only ever processed by lane c of some warp;
+//   * the queues are four 32-bit words per column (one per stage): bit j of mask[stage][c] says that path
+//     32 * j + c waits for that stage.  Push = atomicOr, pop = atomicAnd on the lane's own word: no ring buffers,
+//     no slots to spin on, nothing to overflow, and every queue word sits in its own bank;
+//   * a warp repeatedly votes for the stage with the most non-empty columns (ballot + popc), every lane pops one
+//     path of its column, the warp runs that stage's code ONCE for (typically) 30+ lanes, and every lane pushes its
+//     path to the stage it needs next.  NODE batches run up to K slab-test steps and stop early when too many lanes
+//     have left the NODE state;
+//   * bank conflicts are designed out: all per-path state is float4 arrays indexed by path id (ids of a batch are
+//     distinct mod 32, hence distinct mod 8 inside every quarter-warp => conflict-free LDS.128/STS.128), traversal
+//     stacks are level-major word arrays (bank = column), and a scene small enough is staged as 8 interleaved
+//     copies so that a divergent node/triangle fetch costs exactly its data wavefronts (pt_device.cuh).
+// Per-pixel order is untouched: one path per pixel at a time, samples in sequence, segments in path order.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "pt_scene.h"
+#include "pt_shade.cuh"
+
+namespace ptb {
+
+using namespace ptd;
+
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr int kWfBlock = 512;          // threads per CTA (16 warps); one CTA per SM
+constexpr int kCtlF4 = 33;             // float4s in front of the state arrays: mask[4][32] + 4 control words
+constexpr int kStateF4 = 9;            // float4 state arrays per path
+constexpr size_t kMaxSmem = 227 * 1024;
+
+enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3 };
+enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3 };
+
+struct WfConst {
+    uint32_t np;             // paths per CTA
+    uint32_t stack_depth;    // words per path
+    uint32_t copies_shift;   // staged scene copies = 1 << copies_shift
+    int node_steps;          // K: slab-test steps per NODE batch
+    int node_keep8;          // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
+    int w[4];                // vote weights NODE, LEAF, SHADE, END (applied to the backlog of stages that can fill a warp)
+    int full_cols;           // columns that count as "can fill a warp"
+};
+
+struct ThreadCounters {
+    uint32_t n_samples, n_radiance, n_shadow, n_node, n_tri, n_hit0, n_hit1, n_hit2, n_miss;
+};
+
+__device__ __forceinline__ void flush_counter(unsigned long long* dst, uint32_t v)
+{
+    unsigned long long x = v;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(kFull, x, off);
+    if ((threadIdx.x & 31) == 0 && x) atomicAdd(dst, x);
+}
+
+__device__ __forceinline__ float safe_divide(float a, float b) { return b == 0.0f ? 0.0f : a / b; }   // :265-284
+
+__device__ __forceinline__ uint32_t vol_ld(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// Work item j of this rank -> pixel (same map as render.cu): owned tile j / 32, pixel j % 32 of the 8x4 tile.
+__device__ __forceinline__ bool take_pixel(const LaunchConst& lc, uint32_t n_work, uint32_t j, uint32_t& ix, uint32_t& iy)
+{
+    for (;;) {
+        if (j >= n_work) return false;
+        const uint32_t tile = lc.rank + (j >> 5) * lc.n_ranks;
+        const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
+        ix = tx * 8u + (j & 7u);
+        iy = ty * 4u + ((j >> 3) & 3u);
+        if (ix < lc.width && iy < lc.height) return true;
+        j = atomicAdd(lc.work_counter, 1u);
+    }
+}
+
+// Pop one waiting path of this lane's column: returns j (path id = 32 * j + lane) or -1.
+__device__ __forceinline__ int wf_pop(uint32_t* word, uint32_t snapshot, int rot)
+{
+    uint32_t m = snapshot;
+    while (m) {
+        const uint32_t mr = __funnelshift_r(m, m, rot);   // rotate right: fairness between the column's paths
+        const int j = (__ffs(mr) - 1 + rot) & 31;
+        const uint32_t bit = 1u << j;
+        const uint32_t old = atomicAnd(word, ~bit);
+        if (old & bit) {
+            __threadfence_block();                          // acquire: the path's state was written before the bit was set
+            return j;
+        }
+        m = old & ~bit;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ void wf_push(uint32_t* mask, int stage, int lane, int j)
+{
+    __threadfence_block();                                  // release: state stores before the bit becomes visible
+    atomicOr(mask + stage * 32 + lane, 1u << j);
+}
+
+template <bool SMEM> struct WfFetch { typedef FetchGlobal type; };
+template <> struct WfFetch<true> { typedef FetchSharedBanked type; };
+
+__device__ __forceinline__ void set_shift(FetchGlobal&, int) {}
+__device__ __forceinline__ void set_shift(FetchSharedBanked& f, int s) { f.shift = s; }
+
+__device__ __forceinline__ float4 pack(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+__device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
+
+template <bool COUNT, bool PROBE, bool SMEM>
+__global__ void __launch_bounds__(kWfBlock, 1)
+render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_constant__ WfConst wc)
+{
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t NP = wc.np;
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);            // [4][32]
+    uint32_t* ctl = mask + 128;                                     // [0] idle paths  [1] error flag
+    float4* R0 = smem4 + kCtlF4;        // (ray origin, -)
+    float4* R1 = R0 + NP;               // (ray direction, -)
+    float4* R2 = R1 + NP;               // (1 / direction, -)
+    float4* TS = R2 + NP;               // traversal: (tfar, prim, cur, sp | mode << 8)
+    float4* P0 = TS + NP;               // (attenuation, path seed)
+    float4* P1 = P0 + NP;               // (depth | done << 8 | material << 16, samples left, pixel seed, ix | iy << 16)
+    float4* RS = P1 + NP;               // (result, add.z)
+    float4* S0 = RS + NP;               // (next ray origin, add.x)     add = NEE term, applied when the shadow ray is free
+    float4* S1 = S0 + NP;               // (next ray direction, add.y)
+    int* stack_mem = reinterpret_cast<int*>(S1 + NP);               // [stack_depth][NP]
+    float4* scene = reinterpret_cast<float4*>(stack_mem + (size_t)wc.stack_depth * NP);
+
+    typename WfFetch<SMEM>::type f;
+    f.nodes = lc.bvh.nodes;
+    f.tris = lc.bvh.tris;
+    f.shade = lc.tri_shade;
+    f.mats = reinterpret_cast<const float4*>(lc.mats);
+    if (SMEM) {
+        const uint32_t shift = wc.copies_shift, copies = 1u << shift;
+        const uint32_t n_nodes4 = 4 * lc.n_nodes, n_tris4 = 3 * lc.bvh.n_tris, n_sh = lc.bvh.n_tris, n_m4 = 3 * lc.n_mats;
+        float4* s_nodes = scene;
+        float4* s_tris = s_nodes + ((size_t)n_nodes4 << shift);
+        float4* s_shade = s_tris + ((size_t)n_tris4 << shift);
+        float4* s_mats = s_shade + ((size_t)n_sh << shift);
+        for (uint32_t i = threadIdx.x; i < (n_nodes4 << shift); i += kWfBlock) s_nodes[i] = __ldg(f.nodes + (i >> shift));
+        for (uint32_t i = threadIdx.x; i < (n_tris4 << shift); i += kWfBlock) s_tris[i] = __ldg(f.tris + (i >> shift));
+        for (uint32_t i = threadIdx.x; i < (n_sh << shift); i += kWfBlock) s_shade[i] = __ldg(f.shade + (i >> shift));
+        for (uint32_t i = threadIdx.x; i < (n_m4 << shift); i += kWfBlock) s_mats[i] = __ldg(f.mats + (i >> shift));
+        const uint32_t k = (uint32_t)lane & (copies - 1u);
+        f.nodes = s_nodes + k;
+        f.tris = s_tris + k;
+        f.shade = s_shade + k;
+        f.mats = s_mats + k;
+        set_shift(f, (int)shift);
+    }
+
+    // every path starts "fresh": waiting in END for its first pixel
+    for (uint32_t i = threadIdx.x; i < 132; i += kWfBlock) mask[i] = 0u;
+    for (uint32_t pid = threadIdx.x; pid < NP; pid += kWfBlock)
+        TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_FRESH << 8));
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t P = NP >> 5;
+        mask[ST_END * 32 + lane] = P >= 32u ? 0xffffffffu : ((1u << P) - 1u);
+    }
+    __syncthreads();
+
+    const float l_area = length(cross(lc.l_v1, lc.l_v2));   // :1021
+    const bool have_tris = lc.bvh.n_tris != 0;
+    const uint32_t n_work = lc.n_owned_tiles * 32u;
+    ThreadCounters ctr = {};
+    uint32_t it = 0, idle_polls = 0;
+
+    for (;;) {
+        // ---- vote ---------------------------------------------------------------------------------------------------
+        // cols = columns with a waiting path (the lanes a batch of that stage would fill), tot = waiting paths.
+        // Among the stages that can fill (almost) a whole warp take the one with the largest weighted backlog, so
+        // that no stage starves behind NODE; if none can, take the stage with the most columns.
+        const uint32_t m0 = vol_ld(mask + 0 * 32 + lane), m1 = vol_ld(mask + 1 * 32 + lane);
+        const uint32_t m2 = vol_ld(mask + 2 * 32 + lane), m3 = vol_ld(mask + 3 * 32 + lane);
+        const int c0 = __popc(__ballot_sync(kFull, m0 != 0u)), c1 = __popc(__ballot_sync(kFull, m1 != 0u));
+        const int c2 = __popc(__ballot_sync(kFull, m2 != 0u)), c3 = __popc(__ballot_sync(kFull, m3 != 0u));
+        if ((c0 | c1 | c2 | c3) == 0) {
+            if (vol_ld(ctl) >= NP) break;                // every path has run out of pixels
+            if (++idle_polls > (1u << 26)) {             // watchdog: never spin forever
+                ctl[1] = 1u;
+                break;
+            }
+            __nanosleep(64);
+            continue;
+        }
+        idle_polls = 0;
+        int s0, s1, s2, s3;
+        if (max(max(c0, c1), max(c2, c3)) >= wc.full_cols) {
+            const int t0 = __reduce_add_sync(kFull, __popc(m0)), t1 = __reduce_add_sync(kFull, __popc(m1));
+            const int t2 = __reduce_add_sync(kFull, __popc(m2)), t3 = __reduce_add_sync(kFull, __popc(m3));
+            s0 = c0 >= wc.full_cols ? t0 * wc.w[0] : 0;
+            s1 = c1 >= wc.full_cols ? t1 * wc.w[1] : 0;
+            s2 = c2 >= wc.full_cols ? t2 * wc.w[2] : 0;
+            s3 = c3 >= wc.full_cols ? t3 * wc.w[3] : 0;
+        } else {
+            s0 = c0, s1 = c1, s2 = c2, s3 = c3;
+        }
+        int stage = ST_NODE, best = s0;
+        if (s1 > best) stage = ST_LEAF, best = s1;
+        if (s2 > best) stage = ST_SHADE, best = s2;
+        if (s3 > best) stage = ST_END, best = s3;
+        const int rot = (warp * 7 + (int)(it++)) & 31;
+
+        if (stage == ST_NODE) {
+            // ---- NODE: up to K slab-test steps for every lane that holds a path at an internal node ----------------
+            const int j = wf_pop(mask + ST_NODE * 32 + lane, m0, rot);
+            const bool active = j >= 0;
+            const int pid = (active ? j : 0) * 32 + lane;
+            Trav t;
+            int mode = 0;
+            t.cur = kTravDone;
+            t.sp = 0;
+            t.tfar = 0.0f;
+            t.prim = kNoPrim;
+            t.r.inv = t.r.ood = f3(0.0f);
+            if (active) {
+                const float4 r0 = R0[pid], r2 = R2[pid], ts = TS[pid];
+                t.r.inv = xyz(r2);
+                t.r.ood = f3(r0.x * r2.x, r0.y * r2.y, r0.z * r2.z);          // make_ray: o * inv
+                t.tfar = ts.x;
+                t.prim = __float_as_uint(ts.y);
+                t.cur = __float_as_int(ts.z);
+                const int spm = __float_as_int(ts.w);
+                t.sp = spm & 0xff;
+                mode = spm >> 8;
+            }
+            const StackStrided stack{stack_mem + pid, (int)NP};
+            const int n0 = __popc(__ballot_sync(kFull, active));
+            for (int step = 0; step < wc.node_steps; ++step) {
+                const bool at = t.cur >= 0;
+                const int n = __popc(__ballot_sync(kFull, at));
+                if (n == 0 || n * 8 < n0 * wc.node_keep8) break;
+                if (at) {
+                    if (COUNT) ctr.n_node++;
+                    trav_node_step(t, stack, f, 0.01f);                          // tmin :754
+                }
+            }
+            if (active) {
+                TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(t.cur), __int_as_float(t.sp | (mode << 8)));
+                const int next = t.cur >= 0 ? ST_NODE
+                                            : (t.cur != kTravDone ? ST_LEAF
+                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? ST_SHADE : ST_END));
+                wf_push(mask, next, lane, j);
+            }
+        } else if (stage == ST_LEAF) {
+            // ---- LEAF: one triangle test; a shadow ray ends on its first hit (traceOcclusion :651-684) ------------
+            const int j = wf_pop(mask + ST_LEAF * 32 + lane, m1, rot);
+            if (j >= 0) {
+                const int pid = j * 32 + lane;
+                const float4 r0 = R0[pid], r1 = R1[pid], ts = TS[pid];
+                Trav t;
+                t.r.o = xyz(r0);
+                t.r.d = xyz(r1);
+                t.tfar = ts.x;
+                t.prim = __float_as_uint(ts.y);
+                t.cur = __float_as_int(ts.z);
+                const int spm = __float_as_int(ts.w);
+                t.sp = spm & 0xff;
+                const int mode = spm >> 8;
+                const StackStrided stack{stack_mem + pid, (int)NP};
+                if (COUNT) ctr.n_tri++;
+                trav_leaf_step(t, stack, f, mode == MODE_SHADOW, 0.01f, 1e16f);
+                TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(t.cur), __int_as_float(t.sp | (mode << 8)));
+                const int next = t.cur >= 0 ? ST_NODE
+                                            : (t.cur != kTravDone ? ST_LEAF
+                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? ST_SHADE : ST_END));
+                wf_push(mask, next, lane, j);
+            }
+        } else if (stage == ST_SHADE) {
+            // ---- SHADE: __closesthit__diffuse__ch :866-1031 up to the occlusion trace -------------------------------
+            const int j = wf_pop(mask + ST_SHADE * 32 + lane, m2, rot);
+            if (j >= 0) {
+                const int pid = j * 32 + lane;
+                const float4 r0 = R0[pid], r1 = R1[pid], ts = TS[pid], p0 = P0[pid], p1 = P1[pid], rs = RS[pid];
+                Path p;
+                p.o = xyz(r0);
+                p.d = xyz(r1);
+                p.att = xyz(p0);
+                p.seed = __float_as_uint(p0.w);
+                p.depth = __float_as_int(p1.x) & 0xff;
+                const float t_hit = ts.x;
+                const uint32_t prim = __float_as_uint(ts.y);
+                if (PROBE && __float_as_uint(p1.y) == lc.spp && p.depth == 0) {
+                    const uint32_t pix = __float_as_uint(p1.w);
+                    const uint32_t image_index = (pix >> 16) * lc.width + (pix & 0xffffu);
+                    if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = (int32_t)prim;
+                    if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = t_hit;
+                }
+                ShadowQuery sq;
+                int hit_type, mat_id;
+                float3 emission, rad;
+                bool done;
+                shade_hit(lc, f, l_area, prim, t_hit, p, emission, rad, done, sq, hit_type, mat_id);
+                const float3 result = xyz(rs) + emission;                                       // :760
+                if (COUNT) {
+                    ctr.n_hit0 += hit_type == 0;
+                    ctr.n_hit1 += hit_type == 1;
+                    ctr.n_hit2 += hit_type == 2;
+                }
+                // rad is the material's emission when it is emissive (done), else 0: END re-reads it from the table
+                P0[pid] = pack(p.att, __uint_as_float(p.seed));
+                P1[pid] = make_float4(__int_as_float(p.depth | ((done ? 1 : 0) << 8) | (mat_id << 16)), p1.y, p1.z, p1.w);
+                const float3 add = sq.want ? sq.add : f3(0.0f);
+                S0[pid] = pack(p.o, add.x);
+                S1[pid] = pack(p.d, add.y);
+                RS[pid] = pack(result, add.z);
+                if (sq.want) {
+                    if (COUNT) ctr.n_shadow++;
+                    const Ray r = make_ray(sq.org, sq.dir);
+                    R0[pid] = pack(r.o, 0.0f);
+                    R1[pid] = pack(r.d, 0.0f);
+                    R2[pid] = pack(r.inv, 0.0f);
+                    TS[pid] = make_float4(sq.tmax, __uint_as_float(kNoPrim), __int_as_float(0), __int_as_float(MODE_SHADOW << 8));
+                    wf_push(mask, ST_NODE, lane, j);
+                } else {
+                    TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_SHADED << 8));
+                    wf_push(mask, ST_END, lane, j);
+                }
+            }
+        } else {
+            // ---- END: finish the segment (__miss__ms :833-847, shadow result, :760-778) and start the next ray --------
+            const int j = wf_pop(mask + ST_END * 32 + lane, m3, rot);
+            if (j >= 0) {
+                const int pid = j * 32 + lane;
+                const float4 ts = TS[pid];
+                const int mode = __float_as_int(ts.w) >> 8;
+                Path p;
+                p.o = p.d = f3(0.0f);
+                p.att = f3(1.0f);
+                p.seed = 0u;
+                p.depth = 0;
+                uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
+                float3 result = f3(0.0f);
+                bool need_pixel = false, need_sample = false, alive = true;
+                if (mode == MODE_FRESH) {
+                    need_pixel = true;
+                } else {
+                    const float4 p0 = P0[pid], p1 = P1[pid], rs = RS[pid];
+                    p.att = xyz(p0);
+                    p.seed = __float_as_uint(p0.w);
+                    const int dw = __float_as_int(p1.x);
+                    p.depth = dw & 0xff;
+                    bool done = ((dw >> 8) & 1) != 0;
+                    left = __float_as_uint(p1.y);
+                    pixel_seed = __float_as_uint(p1.z);
+                    const uint32_t pix = __float_as_uint(p1.w);
+                    ix = pix & 0xffffu;
+                    iy = pix >> 16;
+                    result = xyz(rs);
+                    float3 rad;
+                    if (mode == MODE_RAD) {                  // miss
+                        if (PROBE && left == lc.spp && p.depth == 0) {
+                            const uint32_t image_index = iy * lc.width + ix;
+                            if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
+                            if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = 0.0f;
+                        }
+                        rad = lc.background;
+                        done = true;
+                        result = result + f3(0.0f);                                            // emissionColor = 0, :760
+                        if (COUNT) ctr.n_miss++;
+                    } else {
+                        const float4 s0 = S0[pid], s1 = S1[pid];
+                        p.o = xyz(s0);
+                        p.d = xyz(s1);
+                        rad = f3(0.0f);
+                        if (done) rad = xyz(f.mat((int)((uint32_t)dw >> 16), 1));                               // emissive hit, :992-996
+                        if (mode == MODE_SHADOW && __float_as_uint(ts.y) == kNoPrim)
+                            rad = rad + f3(s0.w, s1.w, rs.w);                                  // unoccluded, :1019-1024
+                    }
+                    result = result + rad * p.att;                                             // :761
+                    const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                      // :763
+                    const bool rr = rnd(p.seed) > pr;                                          // :765
+                    if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                     // :767
+                        if (--left == 0u) {
+                            const uint32_t image_index = iy * lc.width + ix;
+                            write_pixel(lc, image_index, result);
+                            if (PROBE) {
+                                if (lc.dbg_final_path_seed) lc.dbg_final_path_seed[image_index] = p.seed;
+                                if (lc.dbg_final_pixel_seed) lc.dbg_final_pixel_seed[image_index] = pixel_seed;
+                            }
+                            need_pixel = true;
+                        } else {
+                            need_sample = true;
+                        }
+                    } else {
+                        p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
+                        ++p.depth;
+                    }
+                }
+                if (need_pixel) {
+                    alive = take_pixel(lc, n_work, atomicAdd(lc.work_counter, 1u), ix, iy);
+                    if (alive) {
+                        pixel_seed = tea4(iy * lc.width + ix, lc.frame);                       // :721
+                        result = f3(0.0f);
+                        left = lc.spp;
+                        need_sample = true;
+                    }
+                }
+                if (need_sample) {
+                    generate_camera_ray(lc, ix, iy, pixel_seed, p);                            // next sample, in place
+                    if (COUNT) ctr.n_samples++;
+                    if (PROBE && left == lc.spp) {
+                        const uint32_t image_index = iy * lc.width + ix;
+                        if (lc.dbg_seed_after_jitter) lc.dbg_seed_after_jitter[image_index] = pixel_seed;
+                        if (lc.dbg_primary_dir) {
+                            lc.dbg_primary_dir[3 * image_index + 0] = p.d.x;
+                            lc.dbg_primary_dir[3 * image_index + 1] = p.d.y;
+                            lc.dbg_primary_dir[3 * image_index + 2] = p.d.z;
+                        }
+                    }
+                }
+                if (alive) {
+                    if (COUNT) ctr.n_radiance++;
+                    const Ray r = make_ray(p.o, p.d);                                          // traceRadiance :577-635
+                    R0[pid] = pack(r.o, 0.0f);
+                    R1[pid] = pack(r.d, 0.0f);
+                    R2[pid] = pack(r.inv, 0.0f);
+                    TS[pid] = make_float4(1e16f, __uint_as_float(kNoPrim), __int_as_float(have_tris ? 0 : kTravDone),
+                                          __int_as_float(MODE_RAD << 8));                      // tmax :755
+                    P0[pid] = pack(p.att, __uint_as_float(p.seed));
+                    P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
+                                          __uint_as_float(ix | (iy << 16)));
+                    RS[pid] = pack(result, 0.0f);
+                    wf_push(mask, have_tris ? ST_NODE : ST_END, lane, j);
+                } else {
+                    atomicAdd(ctl, 1u);
+                }
+            }
+        }
+    }
+
+    if (COUNT && lc.counters) {
+        flush_counter(lc.counters + 0, ctr.n_samples);
+        flush_counter(lc.counters + 1, ctr.n_radiance);
+        flush_counter(lc.counters + 2, ctr.n_shadow);
+        flush_counter(lc.counters + 3, ctr.n_node);
+        flush_counter(lc.counters + 4, ctr.n_tri);
+        flush_counter(lc.counters + 5, ctr.n_hit0);
+        flush_counter(lc.counters + 6, ctr.n_hit1);
+        flush_counter(lc.counters + 7, ctr.n_hit2);
+        flush_counter(lc.counters + 8, ctr.n_miss);
+    }
+    if (threadIdx.x == 0 && vol_ld(ctl + 1)) atomicAdd(lc.error_flag, 1ull);   // watchdog fired
+}
+
+template <bool COUNT, bool PROBE, bool SMEM>
+cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc, size_t smem_bytes, cudaStream_t stream)
+{
+    auto kernel = render_wavefront_kernel<COUNT, PROBE, SMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t n_work = (uint64_t)lc.n_owned_tiles * 32u;
+    uint32_t grid = (uint32_t)sms;                                       // persistent: one CTA per SM
+    const uint32_t grid_needed = (uint32_t)((n_work + wc.np - 1) / wc.np);
+    if (grid > grid_needed) grid = grid_needed;
+    if (grid == 0) grid = 1;
+    e = cudaMemsetAsync(s.d_work_counter, 0, sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kWfBlock, smem_bytes, stream>>>(lc, wc);
+    s.last_grid = grid;
+    s.last_block = kWfBlock;
+    s.last_smem = (uint32_t)smem_bytes;
+    s.last_kernels = 1;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Can the wavefront pipeline hold this scene?  Fills the launch layout when it can.
+static bool wavefront_plan(const Scene& s, WfConst& wc, size_t& smem_bytes, bool& smem_scene)
+{
+    if (s.n_mats > 0xffffu) return false;                 // material id is packed into 16 bits of the path record
+    const uint32_t depth = s.bvh_depth + 1u;              // deferred children never exceed the tree depth
+    if (depth > 255u) return false;
+    const size_t scene_f4 = 4 * (size_t)s.n_nodes + 4 * (size_t)s.n_tris + 3 * (size_t)s.n_mats;
+    const size_t fixed = (size_t)kCtlF4 * 16;
+    const size_t per_path = (size_t)kStateF4 * 16 + 4 * (size_t)depth;
+    // scene copies: 8 if the paths still get >= 512 slots, else 4 / 2 / 1; larger scenes stay in global memory
+    for (int shift = 3; shift >= 0; --shift) {
+        const size_t scene_bytes = (scene_f4 * 16) << shift;
+        if (s.n_tris == 0 || scene_bytes + fixed + 512 * per_path > kMaxSmem) continue;
+        uint32_t P = (uint32_t)((kMaxSmem - fixed - scene_bytes) / (32 * per_path));
+        if (P > 32) P = 32;
+        wc.np = 32 * P;
+        wc.stack_depth = depth;
+        wc.copies_shift = (uint32_t)shift;
+        smem_bytes = fixed + wc.np * per_path + scene_bytes;
+        smem_scene = true;
+        return true;
+    }
+    // global-memory scene: keep about half of the SM's shared memory / L1 for the cache
+    uint32_t P = (uint32_t)((112 * 1024 - fixed) / (32 * per_path));
+    if (P > 32) P = 32;
+    if (P < 4) return false;
+    wc.np = 32 * P;
+    wc.stack_depth = depth;
+    wc.copies_shift = 0;
+    smem_bytes = fixed + wc.np * per_path;
+    smem_scene = false;
+    return true;
+}
+
+bool wavefront_supported(const Scene& s)
+{
+    WfConst wc;
+    size_t b;
+    bool ss;
+    return wavefront_plan(s, wc, b, ss);
+}
+
+cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaStream_t stream)
+{
+    WfConst wc = {};
+    size_t smem_bytes = 0;
+    bool smem_scene = false;
+    if (!wavefront_plan(s, wc, smem_bytes, smem_scene)) return cudaErrorInvalidConfiguration;
+    wc.node_steps = s.wf_tune[4];
+    wc.node_keep8 = s.wf_tune[5];
+    for (int i = 0; i < 4; ++i) wc.w[i] = s.wf_tune[i];
+    wc.full_cols = s.wf_tune[6];
+    if (const char* env = getenv("PTB_WF")) {   // tuning experiments: "w_node,w_leaf,w_shade,w_end,K,keep8[,P[,full_cols]]" (P = 0: default)
+        int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int n = sscanf(env, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
+        if (n >= 8 && v[7] >= 1 && v[7] <= 32) wc.full_cols = v[7];
+        if (n >= 6) {
+            for (int i = 0; i < 4; ++i) wc.w[i] = v[i];
+            wc.node_steps = v[4];
+            wc.node_keep8 = v[5];
+        }
+        if (n >= 7 && v[6] >= 1 && (uint32_t)v[6] * 32u < wc.np) {
+            const size_t per_path = (size_t)kStateF4 * 16 + 4 * (size_t)wc.stack_depth;
+            smem_bytes -= (wc.np - 32u * v[6]) * per_path;
+            wc.np = 32u * v[6];
+        }
+    }
+    const bool count = s.count_enabled;
+    if (probe) {
+        return smem_scene ? launch_wavefront<false, true, true>(s, lc, wc, smem_bytes, stream)
+                          : launch_wavefront<false, true, false>(s, lc, wc, smem_bytes, stream);
+    }
+    if (count) {
+        return smem_scene ? launch_wavefront<true, false, true>(s, lc, wc, smem_bytes, stream)
+                          : launch_wavefront<true, false, false>(s, lc, wc, smem_bytes, stream);
+    }
+    return smem_scene ? launch_wavefront<false, false, true>(s, lc, wc, smem_bytes, stream)
+                      : launch_wavefront<false, false, false>(s, lc, wc, smem_bytes, stream);
+}
+
+}  // namespace ptb
