@@ -48,6 +48,7 @@ def _load():
         "pt_launch_host": (i32, [PP, C.POINTER(u64), C.POINTER(u64)]),
         "pt_scene_enable_counters": (i32, [vp, i32]),
         "pt_scene_get_counters": (i32, [vp, C.POINTER(Counters), i32]),
+        "pt_scene_get_sched_stats": (i32, [vp, C.POINTER(u64), i32]),
         "pt_scene_set_pipeline": (i32, [vp, i32]),
         "pt_scene_last_launch_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "pt_bvh_export": (i32, [vp] * 8),
@@ -192,6 +193,17 @@ class Scene:
         c = Counters()
         _check(lib.pt_scene_get_counters(self._h, C.byref(c), int(reset)))
         return c.asdict()
+
+    def sched_stats(self, reset=True):
+        """Batch occupancy of counted wavefront launches: per stage batches, mean lanes per batch; NODE steps."""
+        a = (C.c_uint64 * 16)()
+        _check(lib.pt_scene_get_sched_stats(self._h, a, int(reset)))
+        names = ("node", "leaf", "shade", "end")
+        out = {n: {"batches": int(a[i]), "lanes_per_batch": (a[4 + i] / a[i]) if a[i] else 0.0} for i, n in enumerate(names)}
+        out["node_steps"] = int(a[8])
+        out["lanes_per_node_step"] = (a[9] / a[8]) if a[8] else 0.0
+        out["idle_votes"] = int(a[10])
+        return out
 
     def set_pipeline(self, pipeline):
         _check(lib.pt_scene_set_pipeline(self._h, pipeline))

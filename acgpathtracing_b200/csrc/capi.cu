@@ -162,7 +162,7 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
     A(dev_alloc(&s->d_nodes, 4 * (size_t)(s->n_nodes ? s->n_nodes : 1)));
     A(dev_alloc(&s->d_tris, 3 * n));
     A(dev_alloc(&s->d_work_counter, 4));
-    A(dev_alloc(&s->d_counters, 16));
+    A(dev_alloc(&s->d_counters, 32));
     if (e != cudaSuccess) {
         scene_free(s);
         return cuda_fail(e, "cudaMalloc(scene)");
@@ -181,7 +181,7 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
         d.emissive = sqrtf(l2) > 0.0f ? 1 : 0;
     }
     cudaStream_t stream = 0;
-    A(cudaMemsetAsync(s->d_counters, 0, 16 * sizeof(unsigned long long), stream));
+    A(cudaMemsetAsync(s->d_counters, 0, 32 * sizeof(unsigned long long), stream));
     if (n_verts) A(cudaMemcpyAsync(s->d_verts, verts_xyzw, sizeof(float4) * n_verts, cudaMemcpyHostToDevice, stream));
     if (n) {
         A(cudaMemcpyAsync(s->d_indices, indices, sizeof(uint32_t) * 3 * n, cudaMemcpyHostToDevice, stream));
@@ -357,6 +357,17 @@ int pt_scene_get_counters(pt_scene* scene, pt_counters* out, int reset)
     out->n_miss = h[8];
     if (h[15]) return fail(PT_ERR_CUDA, "render kernel watchdog fired (scheduler made no progress)");
     if (reset) PT_CUDA(cudaMemset(s->d_counters, 0, sizeof(h)));
+    return PT_OK;
+}
+
+int pt_scene_get_sched_stats(pt_scene* scene, uint64_t* out16, int reset)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s || !out16) return fail(PT_ERR_INVALID, "pt_scene_get_sched_stats: bad argument");
+    DeviceGuard g(s->device);
+    PT_CUDA(cudaDeviceSynchronize());
+    PT_CUDA(cudaMemcpy(out16, s->d_counters + 16, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (reset) PT_CUDA(cudaMemset(s->d_counters + 16, 0, 16 * sizeof(uint64_t)));
     return PT_OK;
 }
 

@@ -74,8 +74,8 @@ struct BvhView {
 // Where the scene records are read from.  Every kernel takes one of these "fetch" policies:
 //   FetchGlobal      global memory through the read-only path (L1/L2), one copy
 //   FetchShared      one copy staged in shared memory (plain LDS)
-//   FetchSharedBanked `1 << shift` interleaved copies in shared memory: element e of copy k lives at float4 index
-//                    (e << shift) + k and lane l reads copy l & (copies - 1).  With 8 copies the 8 lanes of every
+//   FetchSharedBanked `1 << SHIFT` interleaved copies in shared memory: element e of copy k lives at float4 index
+//                    (e << SHIFT) + k and lane l reads copy l & (copies - 1).  With 8 copies the 8 lanes of every
 //                    quarter-warp hit 8 different 16-byte bank groups whatever elements they ask for, so a
 //                    divergent LDS.128 costs exactly its 4 data wavefronts.
 struct FetchGlobal {
@@ -92,13 +92,13 @@ struct FetchShared {
     __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim]; }
     __device__ __forceinline__ float4 mat(int m, int q) const { return mats[3 * m + q]; }
 };
+template <int SHIFT>
 struct FetchSharedBanked {
     const float4 *nodes, *tris, *shade, *mats;   // each already offset by this lane's copy index
-    int shift;
-    __device__ __forceinline__ float4 node(int i, int q) const { return nodes[(4 * i + q) << shift]; }
-    __device__ __forceinline__ float4 tri(int i, int q) const { return tris[(3 * i + q) << shift]; }
-    __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim << shift]; }
-    __device__ __forceinline__ float4 mat(int m, int q) const { return mats[(3 * m + q) << shift]; }
+    __device__ __forceinline__ float4 node(int i, int q) const { return nodes[((4 * i) << SHIFT) + (q << SHIFT)]; }
+    __device__ __forceinline__ float4 tri(int i, int q) const { return tris[((3 * i) << SHIFT) + (q << SHIFT)]; }
+    __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim << SHIFT]; }
+    __device__ __forceinline__ float4 mat(int m, int q) const { return mats[((3 * m) << SHIFT) + (q << SHIFT)]; }
 };
 
 // Where a traversal keeps its stack of deferred children.
@@ -219,14 +219,15 @@ __device__ __forceinline__ void trav_node_step(Trav& t, const STK& stack, const 
     const bool h0 = ray_box(t.r, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), tmin, t.tfar, tn0);
     const bool h1 = ray_box(t.r, f3(q2.x, q2.y, q2.z), f3(q3.x, q3.y, q3.z), tmin, t.tfar, tn1);
     const int c0 = __float_as_int(q0.w), c1 = __float_as_int(q1.w);
-    if (h0 && h1) {
-        const bool swap = tn1 < tn0;
-        stack.put(t.sp++, swap ? c0 : c1);
-        t.cur = swap ? c1 : c0;
-    } else if (h0) {
-        t.cur = c0;
-    } else if (h1) {
-        t.cur = c1;
+    // selects instead of a branch ladder: the warp runs this once for all lanes
+    const bool both = h0 && h1;
+    const bool swap = both && tn1 < tn0;
+    const int far_child = swap ? c0 : c1;
+    const int near_child = (h0 && !swap) ? c0 : c1;
+    if (both) stack.put(t.sp, far_child);
+    t.sp += both ? 1 : 0;
+    if (h0 || h1) {
+        t.cur = near_child;
     } else {
         trav_pop(t, stack);
     }

@@ -103,22 +103,30 @@ __device__ __forceinline__ int wf_pop(uint32_t* word, uint32_t snapshot, int rot
     return -1;
 }
 
+// wf_pop loops a different number of times per lane; without an explicit reconvergence point the compiler lets the
+// lanes that won early run the whole stage body before the others (measured: 2.4 executions of the LEAF body per
+// batch).  Every stage therefore pops through this wrapper.
+__device__ __forceinline__ int wf_pop_converged(uint32_t* word, uint32_t snapshot, int rot)
+{
+    const int j = wf_pop(word, snapshot, rot);
+    __syncwarp();
+    return j;
+}
+
 __device__ __forceinline__ void wf_push(uint32_t* mask, int stage, int lane, int j)
 {
     __threadfence_block();                                  // release: state stores before the bit becomes visible
     atomicOr(mask + stage * 32 + lane, 1u << j);
 }
 
-template <bool SMEM> struct WfFetch { typedef FetchGlobal type; };
-template <> struct WfFetch<true> { typedef FetchSharedBanked type; };
-
-__device__ __forceinline__ void set_shift(FetchGlobal&, int) {}
-__device__ __forceinline__ void set_shift(FetchSharedBanked& f, int s) { f.shift = s; }
+// SCENE = -1: scene records in global memory; SCENE = s >= 0: 1 << s interleaved copies staged in shared memory
+template <int SCENE> struct WfFetch { typedef FetchSharedBanked<SCENE> type; };
+template <> struct WfFetch<-1> { typedef FetchGlobal type; };
 
 __device__ __forceinline__ float4 pack(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
 
-template <bool COUNT, bool PROBE, bool SMEM>
+template <bool COUNT, bool PROBE, int SCENE>
 __global__ void __launch_bounds__(kWfBlock, 1)
 render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_constant__ WfConst wc)
 {
@@ -139,13 +147,13 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     int* stack_mem = reinterpret_cast<int*>(S1 + NP);               // [stack_depth][NP]
     float4* scene = reinterpret_cast<float4*>(stack_mem + (size_t)wc.stack_depth * NP);
 
-    typename WfFetch<SMEM>::type f;
+    typename WfFetch<SCENE>::type f;
     f.nodes = lc.bvh.nodes;
     f.tris = lc.bvh.tris;
     f.shade = lc.tri_shade;
     f.mats = reinterpret_cast<const float4*>(lc.mats);
-    if (SMEM) {
-        const uint32_t shift = wc.copies_shift, copies = 1u << shift;
+    if (SCENE >= 0) {
+        const uint32_t shift = SCENE >= 0 ? (uint32_t)SCENE : 0u, copies = 1u << shift;
         const uint32_t n_nodes4 = 4 * lc.n_nodes, n_tris4 = 3 * lc.bvh.n_tris, n_sh = lc.bvh.n_tris, n_m4 = 3 * lc.n_mats;
         float4* s_nodes = scene;
         float4* s_tris = s_nodes + ((size_t)n_nodes4 << shift);
@@ -160,7 +168,6 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         f.tris = s_tris + k;
         f.shade = s_shade + k;
         f.mats = s_mats + k;
-        set_shift(f, (int)shift);
     }
 
     // every path starts "fresh": waiting in END for its first pixel
@@ -178,6 +185,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     const bool have_tris = lc.bvh.n_tris != 0;
     const uint32_t n_work = lc.n_owned_tiles * 32u;
     ThreadCounters ctr = {};
+    uint32_t st_batches[4] = {0, 0, 0, 0}, st_lanes[4] = {0, 0, 0, 0}, st_steps = 0, st_step_lanes = 0, st_idle = 0;
     uint32_t it = 0, idle_polls = 0;
 
     for (;;) {
@@ -195,30 +203,55 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 ctl[1] = 1u;
                 break;
             }
+            if (COUNT) st_idle++;
             __nanosleep(64);
             continue;
         }
         idle_polls = 0;
-        int s0, s1, s2, s3;
-        if (max(max(c0, c1), max(c2, c3)) >= wc.full_cols) {
-            const int t0 = __reduce_add_sync(kFull, __popc(m0)), t1 = __reduce_add_sync(kFull, __popc(m1));
-            const int t2 = __reduce_add_sync(kFull, __popc(m2)), t3 = __reduce_add_sync(kFull, __popc(m3));
-            s0 = c0 >= wc.full_cols ? t0 * wc.w[0] : 0;
-            s1 = c1 >= wc.full_cols ? t1 * wc.w[1] : 0;
-            s2 = c2 >= wc.full_cols ? t2 * wc.w[2] : 0;
-            s3 = c3 >= wc.full_cols ? t3 * wc.w[3] : 0;
+        int stage;
+        if (wc.w[0] == 0) {
+            // policy 0: the most downstream stage that can fill a warp (END > SHADE > LEAF > NODE) -- drains paths
+            // towards completion and leaves the NODE backlog as the reservoir; else the stage with the most columns
+            const int full = wc.full_cols;
+            if (c3 >= full) {
+                stage = ST_END;
+            } else if (c2 >= full) {
+                stage = ST_SHADE;
+            } else if (c1 >= full) {
+                stage = ST_LEAF;
+            } else if (c0 >= full) {
+                stage = ST_NODE;
+            } else {
+                int best = c0;
+                stage = ST_NODE;
+                if (c1 > best) stage = ST_LEAF, best = c1;
+                if (c2 > best) stage = ST_SHADE, best = c2;
+                if (c3 > best) stage = ST_END, best = c3;
+            }
         } else {
-            s0 = c0, s1 = c1, s2 = c2, s3 = c3;
+            // policy 1: among the stages that can fill a warp, the largest weighted backlog
+            int s0, s1, s2, s3;
+            if (max(max(c0, c1), max(c2, c3)) >= wc.full_cols) {
+                const int t0 = __reduce_add_sync(kFull, __popc(m0)), t1 = __reduce_add_sync(kFull, __popc(m1));
+                const int t2 = __reduce_add_sync(kFull, __popc(m2)), t3 = __reduce_add_sync(kFull, __popc(m3));
+                s0 = c0 >= wc.full_cols ? t0 * wc.w[0] : 0;
+                s1 = c1 >= wc.full_cols ? t1 * wc.w[1] : 0;
+                s2 = c2 >= wc.full_cols ? t2 * wc.w[2] : 0;
+                s3 = c3 >= wc.full_cols ? t3 * wc.w[3] : 0;
+            } else {
+                s0 = c0, s1 = c1, s2 = c2, s3 = c3;
+            }
+            int best = s0;
+            stage = ST_NODE;
+            if (s1 > best) stage = ST_LEAF, best = s1;
+            if (s2 > best) stage = ST_SHADE, best = s2;
+            if (s3 > best) stage = ST_END, best = s3;
         }
-        int stage = ST_NODE, best = s0;
-        if (s1 > best) stage = ST_LEAF, best = s1;
-        if (s2 > best) stage = ST_SHADE, best = s2;
-        if (s3 > best) stage = ST_END, best = s3;
         const int rot = (warp * 7 + (int)(it++)) & 31;
 
         if (stage == ST_NODE) {
             // ---- NODE: up to K slab-test steps for every lane that holds a path at an internal node ----------------
-            const int j = wf_pop(mask + ST_NODE * 32 + lane, m0, rot);
+            const int j = wf_pop_converged(mask + ST_NODE * 32 + lane, m0, rot);
             const bool active = j >= 0;
             const int pid = (active ? j : 0) * 32 + lane;
             Trav t;
@@ -241,13 +274,19 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
             const StackStrided stack{stack_mem + pid, (int)NP};
             const int n0 = __popc(__ballot_sync(kFull, active));
+            if (COUNT) st_batches[ST_NODE]++, st_lanes[ST_NODE] += n0;
             for (int step = 0; step < wc.node_steps; ++step) {
                 const bool at = t.cur >= 0;
                 const int n = __popc(__ballot_sync(kFull, at));
                 if (n == 0 || n * 8 < n0 * wc.node_keep8) break;
+                if (COUNT) st_steps++, st_step_lanes += n;
                 if (at) {
                     if (COUNT) ctr.n_node++;
                     trav_node_step(t, stack, f, 0.01f);                          // tmin :754
+                }
+                if (t.cur >= 0) {                                                // second step under the same vote
+                    if (COUNT) ctr.n_node++;
+                    trav_node_step(t, stack, f, 0.01f);
                 }
             }
             if (active) {
@@ -259,7 +298,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
         } else if (stage == ST_LEAF) {
             // ---- LEAF: one triangle test; a shadow ray ends on its first hit (traceOcclusion :651-684) ------------
-            const int j = wf_pop(mask + ST_LEAF * 32 + lane, m1, rot);
+            const int j = wf_pop_converged(mask + ST_LEAF * 32 + lane, m1, rot);
+            if (COUNT) st_batches[ST_LEAF]++, st_lanes[ST_LEAF] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
                 const float4 r0 = R0[pid], r1 = R1[pid], ts = TS[pid];
@@ -283,7 +323,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
         } else if (stage == ST_SHADE) {
             // ---- SHADE: __closesthit__diffuse__ch :866-1031 up to the occlusion trace -------------------------------
-            const int j = wf_pop(mask + ST_SHADE * 32 + lane, m2, rot);
+            const int j = wf_pop_converged(mask + ST_SHADE * 32 + lane, m2, rot);
+            if (COUNT) st_batches[ST_SHADE]++, st_lanes[ST_SHADE] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
                 const float4 r0 = R0[pid], r1 = R1[pid], ts = TS[pid], p0 = P0[pid], p1 = P1[pid], rs = RS[pid];
@@ -334,7 +375,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
         } else {
             // ---- END: finish the segment (__miss__ms :833-847, shadow result, :760-778) and start the next ray --------
-            const int j = wf_pop(mask + ST_END * 32 + lane, m3, rot);
+            const int j = wf_pop_converged(mask + ST_END * 32 + lane, m3, rot);
+            if (COUNT) st_batches[ST_END]++, st_lanes[ST_END] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
                 const float4 ts = TS[pid];
@@ -454,14 +496,23 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         flush_counter(lc.counters + 6, ctr.n_hit1);
         flush_counter(lc.counters + 7, ctr.n_hit2);
         flush_counter(lc.counters + 8, ctr.n_miss);
+        if (lane == 0) {
+            for (int i = 0; i < 4; ++i) {
+                atomicAdd(lc.counters + 16 + i, (unsigned long long)st_batches[i]);
+                atomicAdd(lc.counters + 20 + i, (unsigned long long)st_lanes[i]);
+            }
+            atomicAdd(lc.counters + 24, (unsigned long long)st_steps);
+            atomicAdd(lc.counters + 25, (unsigned long long)st_step_lanes);
+            atomicAdd(lc.counters + 26, (unsigned long long)st_idle);
+        }
     }
     if (threadIdx.x == 0 && vol_ld(ctl + 1)) atomicAdd(lc.error_flag, 1ull);   // watchdog fired
 }
 
-template <bool COUNT, bool PROBE, bool SMEM>
+template <bool COUNT, bool PROBE, int SCENE>
 cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc, size_t smem_bytes, cudaStream_t stream)
 {
-    auto kernel = render_wavefront_kernel<COUNT, PROBE, SMEM>;
+    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -493,8 +544,8 @@ static bool wavefront_plan(const Scene& s, WfConst& wc, size_t& smem_bytes, bool
     const size_t scene_f4 = 4 * (size_t)s.n_nodes + 4 * (size_t)s.n_tris + 3 * (size_t)s.n_mats;
     const size_t fixed = (size_t)kCtlF4 * 16;
     const size_t per_path = (size_t)kStateF4 * 16 + 4 * (size_t)depth;
-    // scene copies: 8 if the paths still get >= 512 slots, else 4 / 2 / 1; larger scenes stay in global memory
-    for (int shift = 3; shift >= 0; --shift) {
+    // scene copies: 8 if the paths still get >= 512 slots, else 1; larger scenes stay in global memory
+    for (int shift = 3; shift >= 0; shift -= 3) {
         const size_t scene_bytes = (scene_f4 * 16) << shift;
         if (s.n_tris == 0 || scene_bytes + fixed + 512 * per_path > kMaxSmem) continue;
         uint32_t P = (uint32_t)((kMaxSmem - fixed - scene_bytes) / (32 * per_path));
@@ -552,16 +603,15 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
         }
     }
     const bool count = s.count_enabled;
-    if (probe) {
-        return smem_scene ? launch_wavefront<false, true, true>(s, lc, wc, smem_bytes, stream)
-                          : launch_wavefront<false, true, false>(s, lc, wc, smem_bytes, stream);
-    }
-    if (count) {
-        return smem_scene ? launch_wavefront<true, false, true>(s, lc, wc, smem_bytes, stream)
-                          : launch_wavefront<true, false, false>(s, lc, wc, smem_bytes, stream);
-    }
-    return smem_scene ? launch_wavefront<false, false, true>(s, lc, wc, smem_bytes, stream)
-                      : launch_wavefront<false, false, false>(s, lc, wc, smem_bytes, stream);
+    const int scene = smem_scene ? (int)wc.copies_shift : -1;
+#define PTB_WF_DISPATCH(COUNT, PROBE)                                                             \
+    (scene == 3   ? launch_wavefront<COUNT, PROBE, 3>(s, lc, wc, smem_bytes, stream)              \
+     : scene == 0 ? launch_wavefront<COUNT, PROBE, 0>(s, lc, wc, smem_bytes, stream)              \
+                  : launch_wavefront<COUNT, PROBE, -1>(s, lc, wc, smem_bytes, stream))
+    if (probe) return PTB_WF_DISPATCH(false, true);
+    if (count) return PTB_WF_DISPATCH(true, false);
+    return PTB_WF_DISPATCH(false, false);
+#undef PTB_WF_DISPATCH
 }
 
 }  // namespace ptb

@@ -10,8 +10,9 @@ samples for every pixel folded into the running average; step i uses currentFram
 cpu_baseline, e2e, clocks, gpu_launches, grays_per_s).
 
 For N > 1 (torchrun, one rank per GPU) the scene and LBVH are replicated, 8x4-pixel tiles are interleaved over
-ranks, and every step ends with one NCCL all-gather of the owned pixels, so that each rank holds the complete
-image after each step.  Total work is fixed as N grows ("strong" scaling).
+ranks, every rank keeps the running average of its own pixels across the K launches, and the timed region ends with
+ONE exchange (pack -> NCCL all-gather -> unpack, acgpathtracing_b200/multirank.py) after which each rank holds the
+complete image.  Total work is fixed as N grows ("strong" scaling).
 """
 import argparse
 import json
@@ -198,12 +199,8 @@ def run_b200(args):
 
     acc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
     fb = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
-    cap = api.partition_capacity(w, h, world)
-    if world > 1:
-        my_acc = torch.zeros((cap, 4), dtype=torch.float32, device=dev)
-        my_fb = torch.zeros((cap, 4), dtype=torch.uint8, device=dev)
-        all_acc = torch.zeros((world, cap, 4), dtype=torch.float32, device=dev)
-        all_fb = torch.zeros((world, cap, 4), dtype=torch.uint8, device=dev)
+    from acgpathtracing_b200.multirank import ImageExchange
+    exchange = ImageExchange(w, h, rank, world, dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def params(frame):
@@ -216,13 +213,9 @@ def run_b200(args):
         p = params(frame)
         if world == 1:
             api.launch(p, stream)
-            return 1
-        api.launch_partition(p, rank, world, stream)
-        api.partition_pack(acc.data_ptr(), fb.data_ptr(), my_acc.data_ptr(), my_fb.data_ptr(), w, h, rank, world, stream)
-        dist.all_gather_into_tensor(all_acc, my_acc)
-        dist.all_gather_into_tensor(all_fb, my_fb)
-        api.partition_unpack(all_acc.data_ptr(), all_fb.data_ptr(), acc.data_ptr(), fb.data_ptr(), w, h, world, stream)
-        return 3
+        else:
+            api.launch_partition(p, rank, world, stream)
+        return 1
 
     def barrier():
         if world > 1:
@@ -232,6 +225,7 @@ def run_b200(args):
     # ---- warm-up ------------------------------------------------------------------------------------------------
     for i in range(args.warmup):
         step(i)
+    exchange.gather(acc, fb, stream)
     barrier()
 
     # ---- timed region: K steps, CUDA events around each step, L2 flushed between steps ------------------------
@@ -239,7 +233,7 @@ def run_b200(args):
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     launches = 0
     barrier()
     t_wall0 = time.perf_counter()
@@ -248,9 +242,13 @@ def run_b200(args):
         ev[i][0].record()
         launches += step(i)
         ev[i][1].record()
+    ev[-1][0].record()
+    launches += exchange.gather(acc, fb, stream)      # N > 1: the one exchange of the image (timed)
+    ev[-1][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    exchange_ms = step_ms[-1]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -266,8 +264,10 @@ def run_b200(args):
     scene.counters(reset=True)
     for i in range(args.steps):
         step(i)
+    exchange.gather(acc, fb, stream)
     barrier()
     c = scene.counters(reset=True)
+    sched = scene.sched_stats(reset=True)
     scene.enable_counters(False)
     ct = torch.tensor([c["n_samples"], c["n_radiance"], c["n_shadow"], c["n_node"], c["n_tri"], *c["n_hit"], c["n_miss"]],
                       dtype=torch.int64, device=dev)
@@ -308,7 +308,8 @@ def run_b200(args):
                "ms_per_step": 1e3 * t_e2e / args.steps,
                "checksum_matches_device_path": abs(float(h_acc[..., :3].double().mean().item()) - checksum) == 0.0}
     else:
-        # every rank: H2D of the previous full image, partition launch, exchange, D2H of the full image
+        # every rank, every step: H2D of its previous accumulation (pinned host buffer), partition launch, D2H of
+        # accumulation + frame buffer; after the last step the exchange and a D2H of the complete image
         h_acc = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
         h_fb = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
 
@@ -320,18 +321,27 @@ def run_b200(args):
             h_fb.copy_(fb, non_blocking=True)
             torch.cuda.synchronize()
 
+        def host_finish():
+            exchange.gather(acc, fb, stream)
+            h_acc.copy_(acc, non_blocking=True)
+            h_fb.copy_(fb, non_blocking=True)
+            torch.cuda.synchronize()
+
         host_step(0)
+        host_finish()
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
             host_step(i)
+        host_finish()
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         t_e2e = float(t_e2e.item())
         e2e = {"value": pixel_samples / t_e2e / 1e6, "unit": "Mpixel-samples/s",
-               "h2d_bytes_per_step": (args.steps - 1) * w * h * 16 // args.steps, "d2h_bytes_per_step": w * h * 20,
-               "ms_per_step": 1e3 * t_e2e / args.steps, "note": "bytes are per rank"}
+               "h2d_bytes_per_step": (args.steps - 1) * w * h * 16 // args.steps + 168,
+               "d2h_bytes_per_step": w * h * 20 + w * h * 20 // args.steps,
+               "ms_per_step": 1e3 * t_e2e / args.steps, "note": "bytes are per rank; the last term is the final full-image read"}
 
     # ---- roofline denominators measured on this device -----------------------------------------------------------
     roofline = None
@@ -347,11 +357,11 @@ def run_b200(args):
         l2_meas = api.bench_l2_bandwidth()
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         fp32_nominal = dinfo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
-        kernel_ms = total_ms / args.steps        # at N = 1 the step IS the kernel; at N > 1 it includes the exchange
+        kernel_ms = (total_ms - exchange_ms) / args.steps   # one render kernel per step (rank 0's exchange time removed)
         ach_tflops = flops / world / args.steps / (kernel_ms * 1e-3) / 1e12
         ach_gbs = tbytes / world / args.steps / (kernel_ms * 1e-3) / 1e9
         roofline = {
-            "kernel": "render_persistent_kernel" if (args.pipeline or 1) == 1 else "wavefront_kernel",
+            "kernel": "render_persistent_kernel" if args.pipeline == 1 else "render_wavefront_kernel",
             "bound": "fp32", "achieved": ach_tflops, "peak": fp32_meas, "unit": "TFLOP/s", "frac": ach_tflops / fp32_meas,
             "peak_source": "measured live by pt_bench_fp32_peak (dependent-free FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
             "peak_nominal": fp32_nominal, "traffic": None,
@@ -375,10 +385,12 @@ def run_b200(args):
                        "spp_per_step": spp, "max_depth": md, "direct_lighting": nee, "importance_sampling": imp,
                        "frames": f"0..{args.steps - 1}", "parallelism": f"pixel-tiles x{world}",
                        "l2": "flushed between timed steps (256 MiB fill)", "pipeline": scene.last_launch_info(),
+                       "exchange": "none (1 GPU)" if world == 1 else
+                       f"one all-gather of owned pixels per image, {exchange.bytes_per_rank()} B received per rank, {exchange_ms:.3f} ms on rank 0",
                        "lbvh_build_ms": info["build_ms"]},
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "rays_per_sample": rays / max(counters["n_samples"], 1),
-            "counters": counters, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "counters": counters, "sched_rank0": sched, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "image_mean_radiance": checksum,
         }

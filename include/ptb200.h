@@ -106,6 +106,10 @@ int pt_launch_host(const pt_params* params_host_buffers, uint64_t* h2d_bytes, ui
 /* ---- counters and tuning ----------------------------------------------------------------------------- */
 int pt_scene_enable_counters(pt_scene* scene, int enable);   /* counted launches use an instrumented kernel */
 int pt_scene_get_counters(pt_scene* scene, pt_counters* out, int reset);
+/* Scheduler statistics of counted launches (wavefront pipeline): out16[0..3] batches run per stage (NODE, LEAF,
+ * SHADE, END), [4..7] lanes that held a path in those batches, [8] NODE steps, [9] lanes active in NODE steps,
+ * [10] votes that found no work; cumulative until reset. */
+int pt_scene_get_sched_stats(pt_scene* scene, uint64_t* out16, int reset);
 /* kernel variant: 0 = auto, 1 = persistent thread-per-path, 2 = CTA-local wavefront */
 int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
 int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes,
