@@ -219,18 +219,18 @@ __device__ __forceinline__ void trav_node_step(Trav& t, const STK& stack, const 
     const bool h0 = ray_box(t.r, f3(q0.x, q0.y, q0.z), f3(q1.x, q1.y, q1.z), tmin, t.tfar, tn0);
     const bool h1 = ray_box(t.r, f3(q2.x, q2.y, q2.z), f3(q3.x, q3.y, q3.z), tmin, t.tfar, tn1);
     const int c0 = __float_as_int(q0.w), c1 = __float_as_int(q1.w);
-    // selects instead of a branch ladder: the warp runs this once for all lanes
+    // selects instead of a branch ladder: the warp runs this once for all lanes.  The stack top is read
+    // unconditionally (one word) so that "no child hit -> pop" needs no divergent branch either.
     const bool both = h0 && h1;
     const bool swap = both && tn1 < tn0;
     const int far_child = swap ? c0 : c1;
     const int near_child = (h0 && !swap) ? c0 : c1;
+    const bool none = !(h0 || h1);
+    const bool can_pop = t.sp > 0;
+    const int top = stack.get(can_pop ? t.sp - 1 : 0);
     if (both) stack.put(t.sp, far_child);
-    t.sp += both ? 1 : 0;
-    if (h0 || h1) {
-        t.cur = near_child;
-    } else {
-        trav_pop(t, stack);
-    }
+    t.cur = none ? (can_pop ? top : kTravDone) : near_child;
+    t.sp += both ? 1 : ((none && can_pop) ? -1 : 0);
 }
 
 // Leaf step.  any = false: closest hit in (tmin, tmax_closest) under (t, primIdx); any = true: the first hit in

@@ -25,7 +25,7 @@ struct Scene {
     float background[3] = {0.f, 0.f, 0.f};
     float build_ms = 0.f;
     int pipeline = 0;              // 0 auto (wavefront when it can hold the scene), 1 persistent lane-per-path, 2 CTA-local wavefront
-    int wf_tune[7] = {0, 1, 1, 1, 4, 3, 31};   // wavefront: vote weights NODE/LEAF/SHADE/END, NODE steps per batch, keep threshold / 8, full-warp columns
+    int wf_tune[8] = {0, 1, 1, 1, 4, 3, 32, 4};   // wavefront: vote weights NODE/LEAF/SHADE/END, NODE steps per batch, keep threshold / 8, full-warp columns, sticky repeats
     bool count_enabled = false;
     int sched[5] = {1, 1, 1, 1, 20};   // render-kernel stage weights (NODE, LEAF, SHADE, END) and NODE fast-path lane count
 

@@ -37,7 +37,7 @@ using namespace ptd;
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kWfBlock = 512;          // threads per CTA (16 warps); one CTA per SM
+constexpr int kWfBlock = 768;          // threads per CTA (16 warps); one CTA per SM
 constexpr int kCtlF4 = 33;             // float4s in front of the state arrays: mask[4][32] + 4 control words
 constexpr int kStateF4 = 9;            // float4 state arrays per path
 constexpr size_t kMaxSmem = 227 * 1024;
@@ -53,6 +53,7 @@ struct WfConst {
     int node_keep8;          // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
     int w[4];                // vote weights NODE, LEAF, SHADE, END (applied to the backlog of stages that can fill a warp)
     int full_cols;           // columns that count as "can fill a warp"
+    int sticky;              // repeats of the same stage without a full vote while it fills the whole warp
 };
 
 struct ThreadCounters {
@@ -187,71 +188,66 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     ThreadCounters ctr = {};
     uint32_t st_batches[4] = {0, 0, 0, 0}, st_lanes[4] = {0, 0, 0, 0}, st_steps = 0, st_step_lanes = 0, st_idle = 0;
     uint32_t it = 0, idle_polls = 0;
+    int stage = -1, sticky = 0;
 
     for (;;) {
         // ---- vote ---------------------------------------------------------------------------------------------------
-        // cols = columns with a waiting path (the lanes a batch of that stage would fill), tot = waiting paths.
-        // Among the stages that can fill (almost) a whole warp take the one with the largest weighted backlog, so
-        // that no stage starves behind NODE; if none can, take the stage with the most columns.
-        const uint32_t m0 = vol_ld(mask + 0 * 32 + lane), m1 = vol_ld(mask + 1 * 32 + lane);
-        const uint32_t m2 = vol_ld(mask + 2 * 32 + lane), m3 = vol_ld(mask + 3 * 32 + lane);
-        const int c0 = __popc(__ballot_sync(kFull, m0 != 0u)), c1 = __popc(__ballot_sync(kFull, m1 != 0u));
-        const int c2 = __popc(__ballot_sync(kFull, m2 != 0u)), c3 = __popc(__ballot_sync(kFull, m3 != 0u));
-        if ((c0 | c1 | c2 | c3) == 0) {
-            if (vol_ld(ctl) >= NP) break;                // every path has run out of pixels
-            if (++idle_polls > (1u << 26)) {             // watchdog: never spin forever
-                ctl[1] = 1u;
-                break;
+        // cols = columns with a waiting path = the lanes a batch of that stage would fill.
+        // Sticky: the stage just run is repeated (up to wc.sticky times) while it can fill the whole warp -- one LDS and
+        // one VOTE.ALL instead of the full vote, and the other stages' queues fill up meanwhile.
+        uint32_t msnap = 0u;
+        bool decided = false;
+        if (stage >= 0 && sticky < wc.sticky) {
+            msnap = vol_ld(mask + stage * 32 + lane);
+            if (__all_sync(kFull, msnap != 0u)) {
+                ++sticky;
+                decided = true;
             }
-            if (COUNT) st_idle++;
-            __nanosleep(64);
-            continue;
         }
-        idle_polls = 0;
-        int stage;
-        if (wc.w[0] == 0) {
-            // policy 0: the most downstream stage that can fill a warp (END > SHADE > LEAF > NODE) -- drains paths
-            // towards completion and leaves the NODE backlog as the reservoir; else the stage with the most columns
-            const int full = wc.full_cols;
-            if (c3 >= full) {
+        if (!decided) {
+            const uint32_t m0 = vol_ld(mask + 0 * 32 + lane), m1 = vol_ld(mask + 1 * 32 + lane);
+            const uint32_t m2 = vol_ld(mask + 2 * 32 + lane), m3 = vol_ld(mask + 3 * 32 + lane);
+            const uint32_t b0 = __ballot_sync(kFull, m0 != 0u), b1 = __ballot_sync(kFull, m1 != 0u);
+            const uint32_t b2 = __ballot_sync(kFull, m2 != 0u), b3 = __ballot_sync(kFull, m3 != 0u);
+            if ((b0 | b1 | b2 | b3) == 0u) {
+                if (vol_ld(ctl) >= NP) break;                // every path has run out of pixels
+                if (++idle_polls > (1u << 26)) {             // watchdog: never spin forever
+                    ctl[1] = 1u;
+                    break;
+                }
+                if (COUNT) st_idle++;
+                stage = -1;
+                __nanosleep(64);
+                continue;
+            }
+            idle_polls = 0;
+            sticky = 0;
+            // the most downstream stage that can fill a warp (END > SHADE > LEAF > NODE): drains paths towards
+            // completion and leaves the NODE backlog as the reservoir; else the stage with the most columns
+            const uint32_t fullmask = wc.full_cols >= 32 ? 0xffffffffu : 0u;
+            if (fullmask ? (b3 == fullmask) : (__popc(b3) >= wc.full_cols)) {
                 stage = ST_END;
-            } else if (c2 >= full) {
+            } else if (fullmask ? (b2 == fullmask) : (__popc(b2) >= wc.full_cols)) {
                 stage = ST_SHADE;
-            } else if (c1 >= full) {
+            } else if (fullmask ? (b1 == fullmask) : (__popc(b1) >= wc.full_cols)) {
                 stage = ST_LEAF;
-            } else if (c0 >= full) {
+            } else if (fullmask ? (b0 == fullmask) : (__popc(b0) >= wc.full_cols)) {
                 stage = ST_NODE;
             } else {
+                const int c0 = __popc(b0), c1 = __popc(b1), c2 = __popc(b2), c3 = __popc(b3);
                 int best = c0;
                 stage = ST_NODE;
                 if (c1 > best) stage = ST_LEAF, best = c1;
                 if (c2 > best) stage = ST_SHADE, best = c2;
                 if (c3 > best) stage = ST_END, best = c3;
             }
-        } else {
-            // policy 1: among the stages that can fill a warp, the largest weighted backlog
-            int s0, s1, s2, s3;
-            if (max(max(c0, c1), max(c2, c3)) >= wc.full_cols) {
-                const int t0 = __reduce_add_sync(kFull, __popc(m0)), t1 = __reduce_add_sync(kFull, __popc(m1));
-                const int t2 = __reduce_add_sync(kFull, __popc(m2)), t3 = __reduce_add_sync(kFull, __popc(m3));
-                s0 = c0 >= wc.full_cols ? t0 * wc.w[0] : 0;
-                s1 = c1 >= wc.full_cols ? t1 * wc.w[1] : 0;
-                s2 = c2 >= wc.full_cols ? t2 * wc.w[2] : 0;
-                s3 = c3 >= wc.full_cols ? t3 * wc.w[3] : 0;
-            } else {
-                s0 = c0, s1 = c1, s2 = c2, s3 = c3;
-            }
-            int best = s0;
-            stage = ST_NODE;
-            if (s1 > best) stage = ST_LEAF, best = s1;
-            if (s2 > best) stage = ST_SHADE, best = s2;
-            if (s3 > best) stage = ST_END, best = s3;
+            msnap = stage == ST_NODE ? m0 : (stage == ST_LEAF ? m1 : (stage == ST_SHADE ? m2 : m3));
         }
         const int rot = (warp * 7 + (int)(it++)) & 31;
 
         if (stage == ST_NODE) {
             // ---- NODE: up to K slab-test steps for every lane that holds a path at an internal node ----------------
-            const int j = wf_pop_converged(mask + ST_NODE * 32 + lane, m0, rot);
+            const int j = wf_pop_converged(mask + ST_NODE * 32 + lane, msnap, rot);
             const bool active = j >= 0;
             const int pid = (active ? j : 0) * 32 + lane;
             Trav t;
@@ -298,7 +294,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
         } else if (stage == ST_LEAF) {
             // ---- LEAF: one triangle test; a shadow ray ends on its first hit (traceOcclusion :651-684) ------------
-            const int j = wf_pop_converged(mask + ST_LEAF * 32 + lane, m1, rot);
+            const int j = wf_pop_converged(mask + ST_LEAF * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_LEAF]++, st_lanes[ST_LEAF] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
@@ -323,7 +319,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
         } else if (stage == ST_SHADE) {
             // ---- SHADE: __closesthit__diffuse__ch :866-1031 up to the occlusion trace -------------------------------
-            const int j = wf_pop_converged(mask + ST_SHADE * 32 + lane, m2, rot);
+            const int j = wf_pop_converged(mask + ST_SHADE * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_SHADE]++, st_lanes[ST_SHADE] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
@@ -375,7 +371,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
         } else {
             // ---- END: finish the segment (__miss__ms :833-847, shadow result, :760-778) and start the next ray --------
-            const int j = wf_pop_converged(mask + ST_END * 32 + lane, m3, rot);
+            const int j = wf_pop_converged(mask + ST_END * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_END]++, st_lanes[ST_END] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
@@ -587,10 +583,12 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     wc.node_keep8 = s.wf_tune[5];
     for (int i = 0; i < 4; ++i) wc.w[i] = s.wf_tune[i];
     wc.full_cols = s.wf_tune[6];
+    wc.sticky = s.wf_tune[7];
     if (const char* env = getenv("PTB_WF")) {   // tuning experiments: "w_node,w_leaf,w_shade,w_end,K,keep8[,P[,full_cols]]" (P = 0: default)
-        int v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        const int n = sscanf(env, "%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
+        int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const int n = sscanf(env, "%d,%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]);
         if (n >= 8 && v[7] >= 1 && v[7] <= 32) wc.full_cols = v[7];
+        if (n >= 9 && v[8] >= 0) wc.sticky = v[8];
         if (n >= 6) {
             for (int i = 0; i < 4; ++i) wc.w[i] = v[i];
             wc.node_steps = v[4];

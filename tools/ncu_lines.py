@@ -15,31 +15,42 @@ from collections import defaultdict
 
 
 def sass_lines(cubin, kernel_sub):
-    out = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
-    res = []          # per instruction: (file:line chain)
-    cur_fn = None
-    loc = "?"
+    """[(offset, sass text, "inner.cu:12 <- mid.cuh:3 <- outer.cu:99")] for the kernel whose name contains kernel_sub.
+    nvdisasm -gi prints the inline chain as consecutive //## lines, innermost first."""
+    out = subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
+    res = []
+    chain, pending = [], []
     take = False
     for ln in out.splitlines():
         m = re.match(r"\s*\.text\.(\S+):", ln)
         if m:
-            cur_fn = m.group(1)
-            take = kernel_sub in cur_fn
+            take = kernel_sub in m.group(1)
             continue
         if not take:
             continue
-        m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
+        m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            f = m.group(1).split("/")[-1]
-            loc = f"{f}:{m.group(2)}"
-            inl = re.findall(r'inlined at "([^"]+)", line (\d+)', m.group(3))
-            if inl:
-                loc += " <- " + " <- ".join(f"{a.split('/')[-1]}:{b}" for a, b in inl)
+            pending.append(f"{m.group(1).split('/')[-1]}:{m.group(2)}")
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
         if m:
-            res.append((int(m.group(1), 16), m.group(2).strip(), loc))
+            if pending:
+                chain, pending = pending, []
+            res.append((int(m.group(1), 16), m.group(2).strip(), " <- ".join(chain) if chain else "?"))
     return res
+
+
+def stage_of(loc, ranges):
+    """Map the outermost frame (a line of the kernel's own file) to a named source range."""
+    outer = loc.split(" <- ")[-1]
+    m = re.match(r"([\w.]+):(\d+)", outer)
+    if not m:
+        return outer
+    line = int(m.group(2))
+    for name, lo, hi in ranges:
+        if lo <= line < hi:
+            return name
+    return outer
 
 
 def main():
@@ -77,6 +88,23 @@ def main():
         tot[0] += ie
         tot[1] += tie
         tot[2] += smp
+    ranges = []
+    for a in sys.argv:
+        if a.startswith("--ranges="):     # e.g. --ranges=vote:190:260,NODE:260:310
+            for part in a[9:].split(","):
+                n, lo, hi = part.split(":")
+                ranges.append((n, int(lo), int(hi)))
+    if ranges:
+        st = defaultdict(lambda: [0, 0, 0])
+        for addr, txt, ie, tie, smp in prof:
+            e = by_off.get(addr - base)
+            k = stage_of(e[1] if e else "?", ranges)
+            st[k][0] += ie
+            st[k][1] += tie
+            st[k][2] += smp
+        print("per source range (outermost frame):")
+        for k, a in sorted(st.items(), key=lambda kv: -kv[1][0])[:20]:
+            print(f"  {k:28s} warp-inst {a[0] / 1e9:8.2f} G ({100 * a[0] / tot[0]:5.1f} %)  avg thr {a[1] / max(a[0], 1):5.2f}  samples {100 * a[2] / max(tot[2], 1):5.1f} %")
     print(f"total warp-inst {tot[0]:.4g}  thread-inst {tot[1]:.4g}  avg threads {tot[1] / max(tot[0], 1):.2f}  samples {tot[2]}  (unmapped sass: {miss})")
     print(f"{'warp-inst%':>10} {'thr-inst%':>9} {'avg thr':>7} {'samples%':>8} {'#sass':>5}  line")
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
