@@ -160,10 +160,10 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         float4* s_tris = s_nodes + ((size_t)n_nodes4 << shift);
         float4* s_shade = s_tris + ((size_t)n_tris4 << shift);
         float4* s_mats = s_shade + ((size_t)n_sh << shift);
-        for (uint32_t i = threadIdx.x; i < (n_nodes4 << shift); i += kWfBlock) s_nodes[i] = __ldg(f.nodes + (i >> shift));
-        for (uint32_t i = threadIdx.x; i < (n_tris4 << shift); i += kWfBlock) s_tris[i] = __ldg(f.tris + (i >> shift));
-        for (uint32_t i = threadIdx.x; i < (n_sh << shift); i += kWfBlock) s_shade[i] = __ldg(f.shade + (i >> shift));
-        for (uint32_t i = threadIdx.x; i < (n_m4 << shift); i += kWfBlock) s_mats[i] = __ldg(f.mats + (i >> shift));
+        for (uint32_t i = threadIdx.x; i < (n_nodes4 << shift); i += blockDim.x) s_nodes[i] = __ldg(f.nodes + (i >> shift));
+        for (uint32_t i = threadIdx.x; i < (n_tris4 << shift); i += blockDim.x) s_tris[i] = __ldg(f.tris + (i >> shift));
+        for (uint32_t i = threadIdx.x; i < (n_sh << shift); i += blockDim.x) s_shade[i] = __ldg(f.shade + (i >> shift));
+        for (uint32_t i = threadIdx.x; i < (n_m4 << shift); i += blockDim.x) s_mats[i] = __ldg(f.mats + (i >> shift));
         const uint32_t k = (uint32_t)lane & (copies - 1u);
         f.nodes = s_nodes + k;
         f.tris = s_tris + k;
@@ -172,8 +172,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     }
 
     // every path starts "fresh": waiting in END for its first pixel
-    for (uint32_t i = threadIdx.x; i < 132; i += kWfBlock) mask[i] = 0u;
-    for (uint32_t pid = threadIdx.x; pid < NP; pid += kWfBlock)
+    for (uint32_t i = threadIdx.x; i < 132; i += blockDim.x) mask[i] = 0u;
+    for (uint32_t pid = threadIdx.x; pid < NP; pid += blockDim.x)
         TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_FRESH << 8));
     __syncthreads();
     if (warp == 0) {
@@ -521,9 +521,17 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
     if (grid == 0) grid = 1;
     e = cudaMemsetAsync(s.d_work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kWfBlock, smem_bytes, stream>>>(lc, wc);
+    // threads: at most 3/4 of the paths, so that every column keeps waiting paths to form batches from
+    uint32_t block = (wc.np * 3u / 4u) & ~31u;
+    if (block > (uint32_t)kWfBlock) block = kWfBlock;
+    if (block < 128u) block = 128u;
+    if (const char* env = getenv("PTB_WF_BLOCK")) {
+        const long b = atol(env);
+        if (b >= 32 && b <= kWfBlock && b % 32 == 0) block = (uint32_t)b;
+    }
+    kernel<<<grid, block, smem_bytes, stream>>>(lc, wc);
     s.last_grid = grid;
-    s.last_block = kWfBlock;
+    s.last_block = block;
     s.last_smem = (uint32_t)smem_bytes;
     s.last_kernels = 1;
     return cudaGetLastError();
@@ -553,8 +561,14 @@ static bool wavefront_plan(const Scene& s, WfConst& wc, size_t& smem_bytes, bool
         smem_scene = true;
         return true;
     }
-    // global-memory scene: keep about half of the SM's shared memory / L1 for the cache
-    uint32_t P = (uint32_t)((112 * 1024 - fixed) / (32 * per_path));
+    // global-memory scene: node/triangle records come through L1/L2; the paths take most of the shared memory
+    // (batch occupancy needs many more paths than threads) and the rest stays L1
+    size_t budget = 200 * 1024;
+    if (const char* env = getenv("PTB_WF_SMEM_KB")) {
+        const long kb = atol(env);
+        if (kb >= 32 && kb <= 227) budget = (size_t)kb * 1024;
+    }
+    uint32_t P = (uint32_t)((budget - fixed) / (32 * per_path));
     if (P > 32) P = 32;
     if (P < 4) return false;
     wc.np = 32 * P;
