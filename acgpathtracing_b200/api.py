@@ -61,6 +61,9 @@ def _load():
         "pt_obj_counts": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "pt_obj_copy": (i32, [vp, vp, vp, vp, vp]),
         "pt_scene_create_from_obj": (i32, [vp, C.POINTER(vp)]),
+        "pt_image_write_ppm": (i32, [C.c_char_p, vp, u32, u32]),
+        "pt_accum_save": (i32, [C.c_char_p, vp, u32, u32, u32]),
+        "pt_accum_load": (i32, [C.c_char_p, vp, u32, u32, C.POINTER(u32)]),
         "pt_device_info": (i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.c_char_p]),
         "pt_bench_fp32_peak": (i32, [C.POINTER(C.c_double)]),
         "pt_bench_l2_bandwidth": (i32, [C.POINTER(C.c_double)]),

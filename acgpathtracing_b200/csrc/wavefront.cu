@@ -373,18 +373,19 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             // ---- END: finish the segment (__miss__ms :833-847, shadow result, :760-778) and start the next ray --------
             const int j = wf_pop_converged(mask + ST_END * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_END]++, st_lanes[ST_END] += __popc(__ballot_sync(kFull, j >= 0));
+            const int pid = (j >= 0 ? j : 0) * 32 + lane;
+            Path p;
+            p.o = p.d = f3(0.0f);
+            p.att = f3(1.0f);
+            p.seed = 0u;
+            p.depth = 0;
+            uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
+            float3 result = f3(0.0f);
+            bool alive = j >= 0;
             if (j >= 0) {
-                const int pid = j * 32 + lane;
                 const float4 ts = TS[pid];
                 const int mode = __float_as_int(ts.w) >> 8;
-                Path p;
-                p.o = p.d = f3(0.0f);
-                p.att = f3(1.0f);
-                p.seed = 0u;
-                p.depth = 0;
-                uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
-                float3 result = f3(0.0f);
-                bool need_pixel = false, need_sample = false, alive = true;
+                bool need_pixel = false, need_sample = false;
                 if (mode == MODE_FRESH) {
                     need_pixel = true;
                 } else {
@@ -462,22 +463,24 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                         }
                     }
                 }
-                if (alive) {
-                    if (COUNT) ctr.n_radiance++;
-                    const Ray r = make_ray(p.o, p.d);                                          // traceRadiance :577-635
-                    R0[pid] = pack(r.o, 0.0f);
-                    R1[pid] = pack(r.d, 0.0f);
-                    R2[pid] = pack(r.inv, 0.0f);
-                    TS[pid] = make_float4(1e16f, __uint_as_float(kNoPrim), __int_as_float(have_tris ? 0 : kTravDone),
-                                          __int_as_float(MODE_RAD << 8));                      // tmax :755
-                    P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                    P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
-                                          __uint_as_float(ix | (iy << 16)));
-                    RS[pid] = pack(result, 0.0f);
-                    wf_push(mask, have_tris ? ST_NODE : ST_END, lane, j);
-                } else {
-                    atomicAdd(ctl, 1u);
-                }
+                if (!alive) atomicAdd(ctl, 1u);
+            }
+            // "continue the path", "next sample" and "next pixel" took different branches above; reconverge before the
+            // part they share (set up the next ray), or it runs once per branch at half occupancy
+            __syncwarp();
+            if (alive) {
+                if (COUNT) ctr.n_radiance++;
+                const Ray r = make_ray(p.o, p.d);                                              // traceRadiance :577-635
+                R0[pid] = pack(r.o, 0.0f);
+                R1[pid] = pack(r.d, 0.0f);
+                R2[pid] = pack(r.inv, 0.0f);
+                TS[pid] = make_float4(1e16f, __uint_as_float(kNoPrim), __int_as_float(have_tris ? 0 : kTravDone),
+                                      __int_as_float(MODE_RAD << 8));                          // tmax :755
+                P0[pid] = pack(p.att, __uint_as_float(p.seed));
+                P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
+                                      __uint_as_float(ix | (iy << 16)));
+                RS[pid] = pack(result, 0.0f);
+                wf_push(mask, have_tris ? ST_NODE : ST_END, lane, j);
             }
         }
     }

@@ -146,6 +146,15 @@ int pt_obj_counts(const pt_obj* obj, uint32_t* n_vert_floats, uint32_t* n_indice
 int pt_obj_copy(const pt_obj* obj, float* verts_xyzw, uint32_t* indices, uint32_t* mat_ids, pt_material* materials);
 int pt_scene_create_from_obj(const pt_obj* obj, pt_scene** out);
 
+/* ---- image output and checkpoint (host only) -------------------------------------------------------------- */
+/* sutil::saveImage for a UNSIGNED_BYTE4 buffer and a ".ppm" file name (sutil/sutil.cpp:543-570): binary P6 with
+ * the vertical flip (row 0 of frameBuffer is the bottom of the picture), alpha dropped.  Host pointer. */
+int pt_image_write_ppm(const char* path, const void* frame_rgba8_host, uint32_t width, uint32_t height);
+/* The running average + the next currentFrameIdx are the renderer's whole resumable state
+ * (pathTracerPrograms.cu:803-811).  Host pointers; pt_accum_load checks the size. */
+int pt_accum_save(const char* path, const void* accum_float4_host, uint32_t width, uint32_t height, uint32_t next_frame_idx);
+int pt_accum_load(const char* path, void* accum_float4_host, uint32_t width, uint32_t height, uint32_t* next_frame_idx);
+
 /* ---- device microbenchmarks for the roofline denominators (bench.py) ----------------------------------- */
 int pt_device_info(int* sm_count, int* l2_bytes, int* clock_khz, char* name64);
 int pt_bench_fp32_peak(double* tflops);          /* dependent-free FFMA loop on every SM */

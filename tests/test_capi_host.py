@@ -243,3 +243,47 @@ def test_obj_loader_errors(api, tmp_path):
     assert e.value.code == api.PT_ERR_IO
     # (tinyobjloader v2.0.0 specifies "return false" for a zero index, tiny_obj_loader.h:830-841,2795-2806; the
     #  reference build itself crashes on this input, so it is not executed here.)
+
+
+# ---- image output + checkpoint (host only; sutil::saveImage convention, sutil/sutil.cpp:543-570) -----------------------
+def test_ppm_writer_flips_rows_and_drops_alpha(api, tmp_path):
+    w, h = 5, 3
+    img = np.arange(w * h * 4, dtype=np.uint8).reshape(h, w, 4)          # row 0 = bottom of the picture
+    path = str(tmp_path / "a.ppm")
+    api._check(api.lib.pt_image_write_ppm(path.encode(), img.ctypes.data, w, h))
+    raw = open(path, "rb").read()
+    head = f"P6\n{w} {h}\n255\n".encode()
+    assert raw.startswith(head) and len(raw) == len(head) + 3 * w * h
+    pix = np.frombuffer(raw[len(head):], np.uint8).reshape(h, w, 3)
+    assert np.array_equal(pix, img[::-1, :, :3])                          # written top-down
+    with pytest.raises(api.PtError) as e:
+        api._check(api.lib.pt_image_write_ppm(str(tmp_path / "no_dir" / "a.ppm").encode(), img.ctypes.data, w, h))
+    assert e.value.code == api.PT_ERR_IO
+    with pytest.raises(api.PtError):
+        api._check(api.lib.pt_image_write_ppm(path.encode(), None, w, h))
+
+
+def test_accumulation_checkpoint_round_trip(api, tmp_path):
+    w, h = 7, 4
+    acc = np.random.default_rng(3).random((h, w, 4)).astype(np.float32)
+    path = str(tmp_path / "acc.bin")
+    api._check(api.lib.pt_accum_save(path.encode(), acc.ctypes.data, w, h, 5))
+    back = np.zeros_like(acc)
+    nxt = C.c_uint32()
+    api._check(api.lib.pt_accum_load(path.encode(), back.ctypes.data, w, h, C.byref(nxt)))
+    assert nxt.value == 5 and np.array_equal(back.view(np.uint32), acc.view(np.uint32))
+    with pytest.raises(api.PtError) as e:                                 # wrong size
+        api._check(api.lib.pt_accum_load(path.encode(), back.ctypes.data, w + 1, h, C.byref(nxt)))
+    assert e.value.code == api.PT_ERR_INVALID
+    open(path, "wb").write(b"garbage")
+    with pytest.raises(api.PtError) as e:
+        api._check(api.lib.pt_accum_load(path.encode(), back.ctypes.data, w, h, C.byref(nxt)))
+    assert e.value.code == api.PT_ERR_IO
+
+
+def test_headless_driver_is_built_and_explains_itself():
+    exe = os.path.join(ROOT, "acgpathtracing_b200", "ptb_render")
+    assert os.path.exists(exe), "build with make -C acgpathtracing_b200/csrc"
+    import subprocess
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: ptb_render --obj" in r.stderr

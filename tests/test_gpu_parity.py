@@ -345,3 +345,47 @@ def test_full_size_c2_properties(api, port, scenes_cache):
     assert np.array_equal(a1[y0:y1, x0:x1].cpu().numpy().view(np.uint32), o1["accum"][y0:y1, x0:x1].view(np.uint32))
     mean = a1[..., :3].mean().item()
     assert 0.05 < mean < 2.0
+
+
+# ---- headless driver (the reference's main() on top of the C ABI) + image output + checkpoint / resume ---------------
+def _read_ppm(path):
+    raw = open(path, "rb").read()
+    parts = raw.split(b"\n", 3)
+    assert parts[0] == b"P6" and parts[2] == b"255"
+    w, h = (int(x) for x in parts[1].split())
+    return np.frombuffer(parts[3], np.uint8).reshape(h, w, 3)
+
+
+def test_headless_driver_matches_oracle_and_resumes(api, port, scenes_cache, tmp_path):
+    import os
+    import subprocess
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "acgpathtracing_b200", "ptb_render")
+    obj = tmp_path / "cornell32.obj"
+    obj.write_text(arr.obj_text)
+    (tmp_path / "cornell32.mtl").write_text(arr.mtl_text)
+    w, h, spp, md = 96, 54, 4, 16
+    base = [exe, "--obj", str(obj), "--width", str(w), "--height", str(h), "--spp", str(spp), "--depth", str(md),
+            "--direct", "--importance"]
+    r = subprocess.run(base + ["--frames", "2", "--out", str(tmp_path / "two.ppm"), "--accum-out", str(tmp_path / "two.acc")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Frame Render Time:" in r.stdout and "Total Samples 8" in r.stdout        # PathTracerMain.cpp:726,738
+    acc_o = None
+    for f in range(2):
+        p = api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs)
+        o = osc.render(p, accum=acc_o, math_mode=1, use_bvh=True)
+        acc_o = o["accum"]
+    assert np.array_equal(_read_ppm(tmp_path / "two.ppm"), o["fb"][::-1, :, :3])     # saveImage flips rows
+    # one frame, checkpoint, resume for one more frame == two frames in one go
+    r1 = subprocess.run(base + ["--frames", "1", "--out", str(tmp_path / "a.ppm"), "--accum-out", str(tmp_path / "a.acc")],
+                        capture_output=True, text=True, timeout=300)
+    r2 = subprocess.run(base + ["--frames", "1", "--out", str(tmp_path / "b.ppm"), "--accum-in", str(tmp_path / "a.acc"),
+                                "--accum-out", str(tmp_path / "b.acc")], capture_output=True, text=True, timeout=300)
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+    assert "Resuming at frame 1" in r2.stdout
+    assert open(tmp_path / "b.acc", "rb").read() == open(tmp_path / "two.acc", "rb").read()
+    assert open(tmp_path / "b.ppm", "rb").read() == open(tmp_path / "two.ppm", "rb").read()
+    bad = subprocess.run([exe, "--obj", str(tmp_path / "missing.obj")], capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 1 and "Caught exception:" in bad.stderr                # main's catch block, :742-744
