@@ -389,3 +389,90 @@ def test_headless_driver_matches_oracle_and_resumes(api, port, scenes_cache, tmp
     assert open(tmp_path / "b.ppm", "rb").read() == open(tmp_path / "two.ppm", "rb").read()
     bad = subprocess.run([exe, "--obj", str(tmp_path / "missing.obj")], capture_output=True, text=True, timeout=120)
     assert bad.returncode == 1 and "Caught exception:" in bad.stderr                # main's catch block, :742-744
+
+
+# ---- BASELINE configs C3 / C4 / C5 at full size: size-independent properties + crops against the oracle ---------------
+def _crop_check(api, gs, osc, w, h, spp, md, crop, frames=1, pipelines=(0,)):
+    import torch
+    x0, x1, y0, y1 = crop
+    acc_o = None
+    outs = []
+    for pl in pipelines:
+        gs.set_pipeline(pl)
+        acc, fb = _dev_buffers(w, h)
+        for f in range(frames):
+            p = api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs)
+            _launch_dev(api, gs, p, acc, fb)
+        torch.cuda.synchronize()
+        outs.append((acc.clone(), fb.clone()))
+    gs.set_pipeline(0)
+    for f in range(frames):
+        p = api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs)
+        o = osc.render(p, accum=acc_o, math_mode=1, use_bvh=True, region=crop)
+        acc_o = o["accum"]
+    for acc, fb in outs:
+        assert bool(torch.isfinite(acc).all()) and bool((acc[..., 3] == 1.0).all())
+        ga = acc[y0:y1, x0:x1].cpu().numpy()
+        assert np.array_equal(ga.view(np.uint32), o["accum"][y0:y1, x0:x1].view(np.uint32))
+        assert np.array_equal(fb[y0:y1, x0:x1].cpu().numpy(), o["fb"][y0:y1, x0:x1])
+    for acc, fb in outs[1:]:                       # both render kernels agree on every pixel
+        assert torch.equal(acc.view(torch.int32), outs[0][0].view(torch.int32)) and torch.equal(fb, outs[0][1])
+    return outs[0]
+
+
+def test_full_size_c3_material_scene(api, port):
+    """C3 shape: dielectric + conductor spheres in the Cornell box, 1920x1080, 28 bounces, IS + NEE; one launch at a
+    reduced 16 spp (the per-pixel arithmetic does not depend on the image size or on the other pixels).  A crop through
+    the glass sphere and one through the metal sphere are bit-identical to the oracle; wavefront == fallback kernel."""
+    arr = S.material_scene(3)
+    gs, osc = api.Scene(arr), O.OracleScene(port, arr)
+    try:
+        _crop_check(api, gs, osc, 1920, 1080, 16, 28, (700, 724, 300, 312), frames=2, pipelines=(0, 1))
+        _crop_check(api, gs, osc, 1920, 1080, 16, 28, (1180, 1204, 330, 342))
+    finally:
+        gs.destroy()
+
+
+def test_full_size_c4_two_million_triangles(api, port):
+    """C4: the 2.0 M-triangle tessellated scene.  LBVH products bit-identical to the CPU statement (Morton keys, sort
+    permutation, topology, node boxes), 4096 random rays through the device traversal == CPU LBVH == brute force on a
+    subset, and a 1080p 8-bounce crop bit-identical to the oracle."""
+    arr = S.tessellated_scene(1000)
+    assert arr.n_tri >= 2_000_000
+    gs, osc = api.Scene(arr), O.OracleScene(port, arr)
+    try:
+        g, o = gs.bvh_export(), osc.bvh()
+        assert np.array_equal(g["sorted_keys"], o["sorted_keys"])
+        assert np.all(np.diff(g["sorted_keys"].astype(np.uint64)) > 0)            # strictly ascending: keys are unique
+        assert np.array_equal(np.sort(g["sorted_prim"]), np.arange(arr.n_tri, dtype=g["sorted_prim"].dtype))
+        assert np.array_equal(g["parent"], o["parent"])
+        gn, on = g["nodes"].copy(), o["nodes"].copy()
+        gn[:, [11, 15]] = 0
+        on[:, [11, 15]] = 0
+        assert np.array_equal(gn, on)
+        org, d = _rays(arr, 4096, 23)
+        gp, gt, ga, gc = gs.trace(org, d, 0.01, 1e16, want_any=True)
+        op, ot, oa, oc = osc.trace(org, d, 0.01, 1e16, use_bvh=True, want_any=True)
+        assert np.array_equal(gp, op) and np.array_equal(gt.view(np.uint32), ot.view(np.uint32)) and np.array_equal(ga, oa)
+        assert gc.tolist() == oc.tolist()
+        bp, bt, ba, _ = osc.trace(org[:96], d[:96], 0.01, 1e16, use_bvh=False, want_any=True)
+        assert np.array_equal(gp[:96], bp) and np.array_equal(gt[:96].view(np.uint32), bt.view(np.uint32))
+        _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432), pipelines=(0, 1))
+    finally:
+        gs.destroy()
+
+
+def test_full_size_c5_4k(api, port, scenes_cache):
+    """C5 shape: 3840x2160, 28 bounces, IS + NEE, one 32-spp launch + a second folded in: determinism, every pixel
+    written, crop bit-identical to the oracle, and the 8-rank pixel partition reproduces the image."""
+    import torch
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    w, h, spp, md = 3840, 2160, 32, 28
+    acc, fb = _crop_check(api, gs, osc, w, h, spp, md, (1900, 1932, 1000, 1016), frames=2)
+    acc2, fb2 = _dev_buffers(w, h)
+    for f in range(2):
+        p = api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs)
+        for r in range(8):
+            _launch_dev(api, gs, p, acc2, fb2, rank=r, n=8)
+    torch.cuda.synchronize()
+    assert torch.equal(acc.view(torch.int32), acc2.view(torch.int32)) and torch.equal(fb, fb2)
