@@ -73,7 +73,7 @@ static void scene_free(Scene* s)
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
                     s->d_node_hi, s->d_nodes, s->d_tris, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
-                    s->d_wf_state};
+                    s->d_wf_state, s->d_tile_order};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     s->magic = 0;
@@ -198,6 +198,7 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
         A(cudaStreamSynchronize(stream));
         if (e == cudaSuccess) cudaEventElapsedTime(&s->build_ms, e0, e1);
         if (e == cudaSuccess && n) A(cudaMemcpy(&s->bvh_depth, s->d_work_counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (e == cudaSuccess && n) A(cudaMemcpy(s->h_bounds, s->d_bounds, 6 * sizeof(float), cudaMemcpyDeviceToHost));
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);

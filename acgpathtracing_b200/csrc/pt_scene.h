@@ -64,6 +64,15 @@ struct Scene {
     size_t stage_pixels = 0;
     void* d_wf_state = nullptr;                 // unused
 
+    // work order of the render kernels (render.cu tile_order_update): this rank's tiles, those a camera ray can hit
+    // the scene through first.  Rebuilt when the key (image size, camera, partition) changes.
+    float h_bounds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // scene AABB (lo xyz, hi xyz)
+    uint32_t* d_tile_order = nullptr;
+    size_t tile_order_capacity = 0;
+    uint32_t tile_order_count = 0;
+    float tile_order_key[16] = {-1.f};
+    bool tile_order_enabled = true;
+
     // last launch
     uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0;
 };

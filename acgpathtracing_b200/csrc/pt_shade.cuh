@@ -35,6 +35,9 @@ struct LaunchConst {   // everything a launch needs, passed by value as a kernel
     const DevMaterial* mats;      // 3 x float4 per material
     // pixel partition (tiles of 8x4 pixels; tile L owned by rank L % n_ranks)
     uint32_t tiles_x, tiles_y, rank, n_ranks, n_owned_tiles;
+    // work order: image tile of this rank's k-th work tile (expensive tiles first, render.cu tile_order_update);
+    // null = natural order rank + k * n_ranks
+    const uint32_t* tile_order;
     // optional outputs
     unsigned long long* counters;   // pt_counters layout, or null
     uint32_t* work_counter;         // dynamic pixel fetch

@@ -19,6 +19,10 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "pt_scene.h"
 #include "pt_shade.cuh"
@@ -63,7 +67,7 @@ __device__ __forceinline__ bool take_pixel(const LaunchConst& lc, uint32_t n_wor
 {
     for (;;) {
         if (j >= n_work) return false;
-        const uint32_t tile = lc.rank + (j >> 5) * lc.n_ranks;
+        const uint32_t tile = lc.tile_order ? __ldg(lc.tile_order + (j >> 5)) : lc.rank + (j >> 5) * lc.n_ranks;
         const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
         ix = tx * 8u + (j & 7u);
         iy = ty * 4u + ((j >> 3) & 3u);
@@ -412,6 +416,71 @@ cudaError_t partition_unpack(const void* accum_compact_all, const void* frame_co
 // ---- launch ---------------------------------------------------------------------------------------------------------
 static inline float3 to3(const pt_float3& v) { return make_float3(v.x, v.y, v.z); }
 
+// Work order.  A pixel whose camera rays cannot reach the scene costs one node test per sample; one that looks into
+// the scene costs a whole path.  Paths take pixels from a counter, so the order decides the tail of the launch: with
+// the expensive tiles first the cheap ones fill the gaps at the end (longest-processing-time-first).  A tile counts as
+// expensive when the camera ray through its centre or one of its corners hits the scene's bounding box (host, double
+// precision; only the ORDER depends on it, never a pixel value).  Returns the device array or null (natural order).
+static const uint32_t* tile_order_update(Scene& s, const pt_params& p, uint32_t rank, uint32_t n_ranks, uint32_t owned,
+                                         cudaStream_t stream)
+{
+    static const bool env_off = getenv("PTB_TILE_ORDER") && atoi(getenv("PTB_TILE_ORDER")) == 0;   // A/B experiments
+    if (env_off || !s.tile_order_enabled || s.n_tris == 0 || owned == 0) return nullptr;
+    const float key[16] = {(float)p.width, (float)p.height, (float)rank, (float)n_ranks, p.cameraEye.x, p.cameraEye.y,
+                           p.cameraEye.z, p.cameraU.x, p.cameraU.y, p.cameraU.z, p.cameraV.x, p.cameraV.y, p.cameraV.z,
+                           p.cameraW.x, p.cameraW.y, p.cameraW.z};
+    if (s.d_tile_order && s.tile_order_count == owned && memcmp(key, s.tile_order_key, sizeof(key)) == 0) return s.d_tile_order;
+    const uint32_t tiles_x = (p.width + 7) / 8;
+    const double lo[3] = {s.h_bounds[0], s.h_bounds[1], s.h_bounds[2]}, hi[3] = {s.h_bounds[3], s.h_bounds[4], s.h_bounds[5]};
+    const double o[3] = {p.cameraEye.x, p.cameraEye.y, p.cameraEye.z};
+    auto hits = [&](double px, double py) {
+        const double dx = 2.0 * (px / (double)p.width) - 1.0, dy = 2.0 * (py / (double)p.height) - 1.0;   // :732-737
+        const double d[3] = {dx * p.cameraU.x + dy * p.cameraV.x + p.cameraW.x, dx * p.cameraU.y + dy * p.cameraV.y + p.cameraW.y,
+                             dx * p.cameraU.z + dy * p.cameraV.z + p.cameraW.z};
+        double tn = 0.0, tf = 1e300;
+        for (int a = 0; a < 3; ++a) {
+            if (d[a] == 0.0) {
+                if (o[a] < lo[a] || o[a] > hi[a]) return false;
+                continue;
+            }
+            double t0 = (lo[a] - o[a]) / d[a], t1 = (hi[a] - o[a]) / d[a];
+            if (t0 > t1) std::swap(t0, t1);
+            tn = std::max(tn, t0);
+            tf = std::min(tf, t1);
+        }
+        return tn <= tf;
+    };
+    std::vector<uint32_t> order(owned);
+    uint32_t front = 0, back = owned;
+    std::vector<uint32_t> cheap;
+    cheap.reserve(owned);
+    for (uint32_t k = 0; k < owned; ++k) {
+        const uint32_t tile = rank + k * n_ranks;
+        const double x0 = (tile % tiles_x) * 8.0, y0 = (tile / tiles_x) * 4.0;
+        const bool expensive = hits(x0 + 4.0, y0 + 2.0) || hits(x0, y0) || hits(x0 + 8.0, y0) || hits(x0, y0 + 4.0) ||
+                               hits(x0 + 8.0, y0 + 4.0);
+        if (expensive) order[front++] = tile;
+        else cheap.push_back(tile);
+    }
+    (void)back;
+    for (uint32_t t : cheap) order[front++] = t;
+    if (s.tile_order_capacity < owned) {
+        if (s.d_tile_order) cudaFree(s.d_tile_order);
+        s.d_tile_order = nullptr;
+        s.tile_order_capacity = 0;
+        if (cudaMalloc((void**)&s.d_tile_order, sizeof(uint32_t) * owned) != cudaSuccess) return nullptr;
+        s.tile_order_capacity = owned;
+    }
+    // pageable source: the copy is staged before the call returns, so `order` may go out of scope
+    if (cudaMemcpyAsync(s.d_tile_order, order.data(), sizeof(uint32_t) * owned, cudaMemcpyHostToDevice, stream) != cudaSuccess) {
+        s.tile_order_count = 0;
+        return nullptr;
+    }
+    s.tile_order_count = owned;
+    memcpy(s.tile_order_key, key, sizeof(key));
+    return s.d_tile_order;
+}
+
 template <bool COUNT, bool PROBE, bool SMEM>
 static cudaError_t launch_persistent(Scene& s, const LaunchConst& lc, size_t smem_bytes, cudaStream_t stream)
 {
@@ -477,6 +546,7 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.rank = rank;
     lc.n_ranks = n_ranks;
     lc.n_owned_tiles = partition_owned_tiles(params.width, params.height, rank, n_ranks);
+    lc.tile_order = tile_order_update(s, params, rank, n_ranks, lc.n_owned_tiles, stream);
     lc.counters = s.count_enabled ? s.d_counters : nullptr;
     lc.work_counter = s.d_work_counter;
     lc.error_flag = s.d_counters + 15;

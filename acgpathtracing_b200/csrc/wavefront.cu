@@ -77,7 +77,7 @@ __device__ __forceinline__ bool take_pixel(const LaunchConst& lc, uint32_t n_wor
 {
     for (;;) {
         if (j >= n_work) return false;
-        const uint32_t tile = lc.rank + (j >> 5) * lc.n_ranks;
+        const uint32_t tile = lc.tile_order ? __ldg(lc.tile_order + (j >> 5)) : lc.rank + (j >> 5) * lc.n_ranks;
         const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
         ix = tx * 8u + (j & 7u);
         iy = ty * 4u + ((j >> 3) & 3u);
