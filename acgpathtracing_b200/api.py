@@ -42,6 +42,8 @@ def _load():
         "pt_scene_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_float)]),
         "pt_launch": (i32, [PP, vp]),
         "pt_launch_partition": (i32, [PP, u32, u32, vp]),
+        "pt_launch_raw": (i32, [PP, u32, u32, vp]),
+        "pt_fold_frames": (i32, [vp, vp, C.POINTER(vp), u32, u32, u32, u32, vp]),
         "pt_partition_capacity": (u64, [u32, u32, u32]),
         "pt_partition_pack": (i32, [vp, vp, vp, vp, u32, u32, u32, u32, vp]),
         "pt_partition_unpack": (i32, [vp, vp, vp, vp, u32, u32, u32, vp]),
@@ -282,6 +284,18 @@ def launch(params: PathTraceParams, stream=None):
 
 def launch_partition(params: PathTraceParams, rank, n_ranks, stream=None):
     _check(lib.pt_launch_partition(C.byref(params), rank, n_ranks, C.c_void_p(stream) if stream else None))
+
+
+def launch_raw(params, rank=0, n_ranks=1, stream=None):
+    """This launch's own per-pixel mean into params.accumulationBuffer (no fold, no frame buffer)."""
+    _check(lib.pt_launch_raw(C.byref(params), rank, n_ranks, C.c_void_p(stream) if stream else None))
+
+
+def fold_frames(accum, frame_out, frame_means, first_frame_idx, width, height, stream=None):
+    """accum / frame_out / frame_means[k]: raw device addresses.  Running average over the frames, in order."""
+    arr = (C.c_void_p * len(frame_means))(*[C.c_void_p(int(p)) for p in frame_means])
+    _check(lib.pt_fold_frames(C.c_void_p(int(accum)), C.c_void_p(int(frame_out)) if frame_out else None, arr,
+                              first_frame_idx, len(frame_means), width, height, C.c_void_p(stream) if stream else None))
 
 
 def partition_capacity(width, height, n_ranks):

@@ -262,6 +262,28 @@ int pt_launch_partition(const pt_params* params, uint32_t rank, uint32_t n_ranks
 
 int pt_launch(const pt_params* params, void* cuda_stream) { return pt_launch_partition(params, 0, 1, cuda_stream); }
 
+int pt_launch_raw(const pt_params* params, uint32_t rank, uint32_t n_ranks, void* cuda_stream)
+{
+    Scene* s = nullptr;
+    int rc = validate_params(params, &s);
+    if (rc != PT_OK) return rc;
+    if (n_ranks == 0 || rank >= n_ranks) return fail(PT_ERR_INVALID, "rank out of range");
+    DeviceGuard g(s->device);
+    PT_CUDA(render_launch(*s, *params, rank, n_ranks, (cudaStream_t)cuda_stream, nullptr, true));
+    return PT_OK;
+}
+
+int pt_fold_frames(void* accum, void* frame_out, const void* const* frame_means, uint32_t first_frame_idx, uint32_t n_frames,
+                   uint32_t width, uint32_t height, void* cuda_stream)
+{
+    if (!accum || !frame_means || n_frames == 0 || width == 0 || height == 0) return fail(PT_ERR_INVALID, "pt_fold_frames: bad argument");
+    if (n_frames > kMaxFoldFrames) return fail(PT_ERR_INVALID, "pt_fold_frames: at most 64 frames per call");
+    for (uint32_t k = 0; k < n_frames; ++k)
+        if (!frame_means[k]) return fail(PT_ERR_INVALID, "pt_fold_frames: NULL frame");
+    PT_CUDA(fold_frames(accum, frame_out, frame_means, first_frame_idx, n_frames, width, height, (cudaStream_t)cuda_stream));
+    return PT_OK;
+}
+
 uint64_t pt_partition_capacity(uint32_t width, uint32_t height, uint32_t n_ranks)
 {
     if (n_ranks == 0) return 0;

@@ -25,7 +25,7 @@ struct Scene {
     float background[3] = {0.f, 0.f, 0.f};
     float build_ms = 0.f;
     int pipeline = 0;              // 0 auto (wavefront when it can hold the scene), 1 persistent lane-per-path, 2 CTA-local wavefront
-    int wf_tune[8] = {0, 1, 1, 1, 4, 3, 32, 4};   // wavefront: vote weights NODE/LEAF/SHADE/END, NODE steps per batch, keep threshold / 8, full-warp columns, sticky repeats
+    int wf_tune[9] = {0, 1, 1, 1, 4, 3, 32, 4, 24};   // wavefront: vote weights NODE/LEAF/SHADE/END, NODE steps per batch, keep threshold / 8, full-warp columns, sticky repeats, tail-mode column sum
     bool count_enabled = false;
     int sched[5] = {1, 1, 1, 1, 20};   // render-kernel stage weights (NODE, LEAF, SHADE, END) and NODE fast-path lane count
 
@@ -81,8 +81,11 @@ struct Scene {
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
 
 // render.cu
+constexpr uint32_t kMaxFoldFrames = 64;
 cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint32_t n_ranks, cudaStream_t stream,
-                          const ptd::LaunchConst* probe_overrides);
+                          const ptd::LaunchConst* probe_overrides, bool raw_mean = false);
+cudaError_t fold_frames(void* accum, void* frame_out, const void* const* means, uint32_t first_frame, uint32_t n_frames,
+                        uint32_t width, uint32_t height, cudaStream_t stream);
 cudaError_t trace_rays_device(Scene& s, const float* d_org, const float* d_dir, const float* d_tmin, const float* d_tmax,
                               uint64_t n, int32_t* d_prim, float* d_t, uint8_t* d_any, unsigned long long* d_counters2,
                               cudaStream_t stream);

@@ -25,6 +25,7 @@ struct LaunchConst {   // everything a launch needs, passed by value as a kernel
     float3 eye, U, V, W;
     float3 l_corner, l_v1, l_v2, l_normal, l_emission;
     int use_nee, use_is;
+    int raw_mean;                 // 1: write this launch's own mean (no fold into the running average, no frame buffer)
     float3 background;            // MissData.backgroundColor, PathTracerMain.cpp:568
     float4* accum;
     uchar4* frame_buffer;         // may be null
@@ -317,7 +318,7 @@ __device__ __forceinline__ void generate_camera_ray(const LaunchConst& lc, uint3
 __device__ __forceinline__ void write_pixel(const LaunchConst& lc, uint32_t image_index, float3 result)
 {
     float3 accum = div_by_scalar(result, (float)lc.spp);                                // :784
-    if ((int)lc.frame > 0) {                                                            // :803-810
+    if (!lc.raw_mean && (int)lc.frame > 0) {                                            // :803-810
         const float a = 1.0f / (float)((int)lc.frame + 1);
         const float4 prev4 = lc.accum[image_index];
         const float3 prev = f3(prev4.x, prev4.y, prev4.z);

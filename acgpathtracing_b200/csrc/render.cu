@@ -513,10 +513,54 @@ static cudaError_t launch_persistent(Scene& s, const LaunchConst& lc, size_t sme
     return cudaGetLastError();
 }
 
+// ---- frame fold: the running average of pathTracerPrograms.cu:803-811 applied to per-launch means, in frame order ----
+struct FoldArgs {
+    const float4* means[kMaxFoldFrames];
+    uint32_t n_frames, first_frame;
+};
+
+__global__ void __launch_bounds__(256) fold_frames_kernel(float4* __restrict__ accum, uchar4* __restrict__ frame_out,
+                                                          const __grid_constant__ FoldArgs a, uint32_t n_pixels)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    float3 acc;
+    uint32_t k = 0;
+    if (a.first_frame == 0u) {                       // frame 0 overwrites (:803: only frames > 0 read the buffer)
+        const float4 x = a.means[0][i];
+        acc = f3(x.x, x.y, x.z);
+        k = 1;
+    } else {
+        const float4 p = accum[i];
+        acc = f3(p.x, p.y, p.z);
+    }
+    for (; k < a.n_frames; ++k) {
+        const float w = 1.0f / (float)((int)(a.first_frame + k) + 1);
+        const float4 x4 = a.means[k][i];
+        const float3 x = f3(x4.x, x4.y, x4.z);
+        acc = acc + w * (x - acc);                   // lerp(prev, accum, a), vec_math.h:500 -- same order as write_pixel
+    }
+    accum[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+    if (frame_out) frame_out[i] = make_color(acc);
+}
+
+cudaError_t fold_frames(void* accum, void* frame_out, const void* const* means, uint32_t first_frame, uint32_t n_frames,
+                        uint32_t width, uint32_t height, cudaStream_t stream)
+{
+    FoldArgs a = {};
+    for (uint32_t k = 0; k < n_frames; ++k) a.means[k] = (const float4*)means[k];
+    a.n_frames = n_frames;
+    a.first_frame = first_frame;
+    const uint32_t n = width * height;
+    fold_frames_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>((float4*)accum, (uchar4*)frame_out, a, n);
+    return cudaGetLastError();
+}
+
 cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint32_t n_ranks, cudaStream_t stream,
-                          const LaunchConst* probe_overrides)
+                          const LaunchConst* probe_overrides, bool raw_mean)
 {
     LaunchConst lc = {};
+    lc.raw_mean = raw_mean ? 1 : 0;
     lc.frame = params.currentFrameIdx;
     lc.width = params.width;
     lc.height = params.height;
@@ -535,7 +579,7 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.use_is = params.useImportanceSampling ? 1 : 0;
     lc.background = make_float3(s.background[0], s.background[1], s.background[2]);
     lc.accum = (float4*)params.accumulationBuffer;
-    lc.frame_buffer = (uchar4*)params.frameBuffer;
+    lc.frame_buffer = raw_mean ? nullptr : (uchar4*)params.frameBuffer;
     lc.bvh = BvhView{s.d_nodes, s.d_tris, s.n_tris};
     lc.n_nodes = s.n_nodes;
     lc.n_mats = s.n_mats;

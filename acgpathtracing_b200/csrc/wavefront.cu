@@ -42,7 +42,7 @@ constexpr int kCtlF4 = 33;             // float4s in front of the state arrays: 
 constexpr int kStateF4 = 9;            // float4 state arrays per path
 constexpr size_t kMaxSmem = 227 * 1024;
 
-enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3 };
+enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3, ST_TAIL = 4 };   // 0..3 have queues; TAIL serves NODE + LEAF
 enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3 };
 
 struct WfConst {
@@ -54,6 +54,7 @@ struct WfConst {
     int w[4];                // vote weights NODE, LEAF, SHADE, END (applied to the backlog of stages that can fill a warp)
     int full_cols;           // columns that count as "can fill a warp"
     int sticky;              // repeats of the same stage without a full vote while it fills the whole warp
+    int tail_cols;           // tail mode when the non-empty columns of all four queues add up to at most this
 };
 
 struct ThreadCounters {
@@ -195,9 +196,9 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         // cols = columns with a waiting path = the lanes a batch of that stage would fill.
         // Sticky: the stage just run is repeated (up to wc.sticky times) while it can fill the whole warp -- one LDS and
         // one VOTE.ALL instead of the full vote, and the other stages' queues fill up meanwhile.
-        uint32_t msnap = 0u;
+        uint32_t msnap = 0u, msnap2 = 0u;
         bool decided = false;
-        if (stage >= 0 && sticky < wc.sticky) {
+        if (stage >= 0 && stage != ST_TAIL && sticky < wc.sticky) {
             msnap = vol_ld(mask + stage * 32 + lane);
             if (__all_sync(kFull, msnap != 0u)) {
                 ++sticky;
@@ -240,12 +241,67 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 if (c1 > best) stage = ST_LEAF, best = c1;
                 if (c2 > best) stage = ST_SHADE, best = c2;
                 if (c3 > best) stage = ST_END, best = c3;
+                // Tail of the launch (few paths left in this CTA): regrouping cannot fill warps any more and every queue
+                // hop only adds latency to the last pixels, so traversals run to completion in one go.
+                if (stage <= ST_LEAF && c0 + c1 + c2 + c3 <= wc.tail_cols) {
+                    stage = ST_TAIL;
+                    msnap = m0;
+                    msnap2 = m1;
+                }
             }
-            msnap = stage == ST_NODE ? m0 : (stage == ST_LEAF ? m1 : (stage == ST_SHADE ? m2 : m3));
+            if (stage != ST_TAIL) msnap = stage == ST_NODE ? m0 : (stage == ST_LEAF ? m1 : (stage == ST_SHADE ? m2 : m3));
         }
         const int rot = (warp * 7 + (int)(it++)) & 31;
 
-        if (stage == ST_NODE) {
+        if (stage == ST_TAIL) {
+            // ---- TAIL: every lane takes a waiting traversal (at a node or at a leaf) and finishes it ----------------
+            int j = wf_pop(mask + ST_NODE * 32 + lane, msnap, rot);
+            if (j < 0) j = wf_pop(mask + ST_LEAF * 32 + lane, msnap2, rot);
+            __syncwarp();
+            const bool active = j >= 0;
+            const int pid = (active ? j : 0) * 32 + lane;
+            Trav t;
+            int mode = 0;
+            t.cur = kTravDone;
+            t.sp = 0;
+            t.tfar = 0.0f;
+            t.prim = kNoPrim;
+            t.r.o = t.r.d = t.r.inv = t.r.ood = f3(0.0f);
+            if (active) {
+                const float4 r0 = R0[pid], r1 = R1[pid], r2 = R2[pid], ts = TS[pid];
+                t.r.o = xyz(r0);
+                t.r.d = xyz(r1);
+                t.r.inv = xyz(r2);
+                t.r.ood = f3(r0.x * r2.x, r0.y * r2.y, r0.z * r2.z);          // make_ray: o * inv
+                t.tfar = ts.x;
+                t.prim = __float_as_uint(ts.y);
+                t.cur = __float_as_int(ts.z);
+                const int spm = __float_as_int(ts.w);
+                t.sp = spm & 0xff;
+                mode = spm >> 8;
+            }
+            const StackStrided stack{stack_mem + pid, (int)NP};
+            for (;;) {
+                const bool at_node = t.cur >= 0;
+                const bool at_leaf = t.cur < 0 && t.cur != kTravDone;
+                const uint32_t bn = __ballot_sync(kFull, at_node), bl = __ballot_sync(kFull, at_leaf);
+                if ((bn | bl) == 0u) break;
+                if (__popc(bn) >= __popc(bl)) {
+                    if (at_node) {
+                        if (COUNT) ctr.n_node++;
+                        trav_node_step(t, stack, f, 0.01f);
+                    }
+                } else if (at_leaf) {
+                    if (COUNT) ctr.n_tri++;
+                    trav_leaf_step(t, stack, f, mode == MODE_SHADOW, 0.01f, 1e16f);
+                }
+            }
+            if (active) {
+                TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(kTravDone), __int_as_float(t.sp | (mode << 8)));
+                wf_push(mask, (mode == MODE_RAD && t.prim != kNoPrim) ? ST_SHADE : ST_END, lane, j);
+            }
+            stage = -1;
+        } else if (stage == ST_NODE) {
             // ---- NODE: up to K slab-test steps for every lane that holds a path at an internal node ----------------
             const int j = wf_pop_converged(mask + ST_NODE * 32 + lane, msnap, rot);
             const bool active = j >= 0;
@@ -601,11 +657,14 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     for (int i = 0; i < 4; ++i) wc.w[i] = s.wf_tune[i];
     wc.full_cols = s.wf_tune[6];
     wc.sticky = s.wf_tune[7];
+    wc.tail_cols = s.wf_tune[8];
+    if (const char* tc = getenv("PTB_WF_TAIL")) wc.tail_cols = atoi(tc);
     if (const char* env = getenv("PTB_WF")) {   // tuning experiments: "w_node,w_leaf,w_shade,w_end,K,keep8[,P[,full_cols]]" (P = 0: default)
         int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         const int n = sscanf(env, "%d,%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]);
         if (n >= 8 && v[7] >= 1 && v[7] <= 32) wc.full_cols = v[7];
         if (n >= 9 && v[8] >= 0) wc.sticky = v[8];
+
         if (n >= 6) {
             for (int i = 0; i < 4; ++i) wc.w[i] = v[i];
             wc.node_steps = v[4];

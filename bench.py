@@ -10,9 +10,12 @@ samples for every pixel folded into the running average; step i uses currentFram
 cpu_baseline, e2e, clocks, gpu_launches, grays_per_s).
 
 For N > 1 (torchrun, one rank per GPU) the scene and LBVH are replicated, 8x4-pixel tiles are interleaved over
-ranks, every rank keeps the running average of its own pixels across the K launches, and the timed region ends with
-ONE exchange (pack -> NCCL all-gather -> unpack, acgpathtracing_b200/multirank.py) after which each rank holds the
-complete image.  Total work is fixed as N grows ("strong" scaling).
+ranks.  The K launches of the image are dealt to the ranks as WHOLE frames (frame k -> rank k % N, K // N rounds; the
+mean image of a frame depends only on (pixel, frame index), pathTracerPrograms.cu:721); the K % N leftover frames are
+rendered by all ranks together, 8x4-pixel tiles interleaved.  The timed region ends with ONE exchange (NCCL all-gather of
+the per-frame means) and the reference's running average applied in frame order (pt_fold_frames), after which every
+rank holds the complete image, bit-identical to K launches on one GPU (acgpathtracing_b200/multirank.py).
+`--partition tiles` forces the pure tile partition instead.  Total work is fixed as N grows ("strong" scaling).
 """
 import argparse
 import json
@@ -199,23 +202,44 @@ def run_b200(args):
 
     acc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
     fb = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
-    from acgpathtracing_b200.multirank import ImageExchange
+    from acgpathtracing_b200.multirank import FrameParallel, ImageExchange
     exchange = ImageExchange(w, h, rank, world, dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    frame_mode = world > 1 and args.partition == "auto"
 
-    def params(frame):
+    def params(frame, acc_ptr=None, fb_ptr=None):
         p = api.make_params(w, h, spp, md, frame=frame, nee=nee, importance=imp, scene=scene)
-        p.accumulationBuffer, p.frameBuffer = acc.data_ptr(), fb.data_ptr()
+        p.accumulationBuffer = acc.data_ptr() if acc_ptr is None else acc_ptr
+        p.frameBuffer = fb.data_ptr() if fb_ptr is None else fb_ptr
         return p
 
-    def step(frame):
+    def render_raw(frame, r, n, out):
+        api.launch_raw(params(frame, out.data_ptr(), 0), r, n, stream)
+
+    fp = FrameParallel(w, h, rank, world, dev, args.steps, render_raw) if frame_mode else None
+
+    def my_steps():
+        """The launches this rank issues for one image: [(frame, kind)]."""
+        return fp.my_frames() if frame_mode else [(i, "seq") for i in range(args.steps)]
+
+    def step(frame, kind="seq"):
         """One launch of the hot path with device-resident buffers; returns the number of our kernels launched."""
+        if kind != "seq":
+            return fp.render(frame, kind)
         p = params(frame)
-        if world == 1:
+        if args.emulate_ranks > 1:
+            api.launch_partition(p, 0, args.emulate_ranks, stream)   # tuning aid: one rank's share of an N-rank job
+        elif world == 1:
             api.launch(p, stream)
         else:
             api.launch_partition(p, rank, world, stream)
         return 1
+
+    def finish():
+        """N > 1: the one exchange of the image; returns the number of our kernels launched."""
+        if frame_mode:
+            return fp.finish(acc, fb, stream)
+        return exchange.gather(acc, fb, stream)
 
     def barrier():
         if world > 1:
@@ -223,27 +247,35 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ------------------------------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step(i)
-    exchange.gather(acc, fb, stream)
+    if frame_mode:                                    # at least args.warmup launches per rank, in whole images
+        reps = -(-args.warmup // max(len(my_steps()), 1))
+        for _ in range(max(reps, 1)):
+            for f, kind in my_steps():
+                step(f, kind)
+    else:
+        for i in range(args.warmup):
+            step(i)
+    finish()
     barrier()
 
-    # ---- timed region: K steps, CUDA events around each step, L2 flushed between steps ------------------------
+    # ---- timed region: the image's K launches (this rank's share of them), CUDA events around each, L2 flushed between
+    # launches, then the exchange ---------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
+    todo = my_steps()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(len(todo) + 1)]
     launches = 0
     barrier()
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
+    for i, (f, kind) in enumerate(todo):
         flush_buf.fill_(i & 0xFF)                     # evict L2 (untimed)
         ev[i][0].record()
-        launches += step(i)
+        launches += step(f, kind)
         ev[i][1].record()
     ev[-1][0].record()
-    launches += exchange.gather(acc, fb, stream)      # N > 1: the one exchange of the image (timed)
+    launches += finish()                              # N > 1: exchange (+ ordered fold), timed
     ev[-1][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -257,15 +289,15 @@ def run_b200(args):
     checksum = float(acc[..., :3].double().mean().item())
     acc_after_timed = acc.clone()           # for the bit-for-bit comparison with the host-buffer path below
 
-    pixel_samples = float(w) * h * spp * args.steps
+    pixel_samples = float(w) * h * spp * args.steps / max(args.emulate_ranks, 1)
     value = pixel_samples / (total_ms * 1e-3) / 1e6
 
     # ---- work counters for the timed frames (instrumented kernel, untimed) -> Grays/s and algorithmic flops ----
     scene.enable_counters(True)
     scene.counters(reset=True)
-    for i in range(args.steps):
-        step(i)
-    exchange.gather(acc, fb, stream)
+    for f, kind in my_steps():
+        step(f, kind)
+    finish()
     barrier()
     c = scene.counters(reset=True)
     sched = scene.sched_stats(reset=True)
@@ -309,40 +341,57 @@ def run_b200(args):
                "ms_per_step": 1e3 * t_e2e / args.steps,
                "bit_identical_to_device_path": bool(torch.equal(h_acc.view(torch.int32), acc_after_timed.cpu().view(torch.int32)))}
     else:
-        # every rank, every step: H2D of its previous accumulation (pinned host buffer), partition launch, D2H of
-        # accumulation + frame buffer; after the last step the exchange and a D2H of the complete image
+        # every rank: per launch the params record goes up and the launch's result comes down to a pinned host buffer
+        # (tile mode: previous accumulation up, accumulation + frame buffer down); after the last launch the exchange and
+        # a read of the complete image
         h_acc = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
         h_fb = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
+        up = down = 0
 
-        def host_step(frame):
-            if frame > 0:
-                acc.copy_(h_acc, non_blocking=True)
-            step(frame)
-            h_acc.copy_(acc, non_blocking=True)
-            h_fb.copy_(fb, non_blocking=True)
+        def host_step(i, f, kind):
+            nonlocal up, down
+            if kind == "seq":
+                if f > 0:
+                    acc.copy_(h_acc, non_blocking=True)
+                    up += w * h * 16
+                step(f, kind)
+                h_acc.copy_(acc, non_blocking=True)
+                h_fb.copy_(fb, non_blocking=True)
+                down += w * h * 20
+            else:
+                step(f, kind)
+                src = fp.mine[f // world] if kind == "whole" else fp.shared[f - fp.rounds * world]
+                h_acc.copy_(src, non_blocking=True)
+                down += w * h * 16
+            up += 168
             torch.cuda.synchronize()
 
         def host_finish():
-            exchange.gather(acc, fb, stream)
+            nonlocal down
+            finish()
             h_acc.copy_(acc, non_blocking=True)
             h_fb.copy_(fb, non_blocking=True)
+            down += w * h * 20
             torch.cuda.synchronize()
 
-        host_step(0)
+        for i, (f, kind) in enumerate(todo[:1]):
+            host_step(i, f, kind)
         host_finish()
         barrier()
+        up = down = 0
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            host_step(i)
+        for i, (f, kind) in enumerate(todo):
+            host_step(i, f, kind)
         host_finish()
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         t_e2e = float(t_e2e.item())
         e2e = {"value": pixel_samples / t_e2e / 1e6, "unit": "Mpixel-samples/s",
-               "h2d_bytes_per_step": (args.steps - 1) * w * h * 16 // args.steps + 168,
-               "d2h_bytes_per_step": w * h * 20 + w * h * 20 // args.steps,
-               "ms_per_step": 1e3 * t_e2e / args.steps, "note": "bytes are per rank; the last term is the final full-image read"}
+               "h2d_bytes_per_step": up // args.steps, "d2h_bytes_per_step": down // args.steps,
+               "ms_per_step": 1e3 * t_e2e / args.steps,
+               "note": "bytes moved by rank 0 divided by the image's K steps; includes the final full-image read",
+               "bit_identical_to_device_path": bool(torch.equal(h_acc.view(torch.int32), acc_after_timed.cpu().view(torch.int32)))}
 
     # ---- roofline denominators measured on this device -----------------------------------------------------------
     roofline = None
@@ -358,9 +407,13 @@ def run_b200(args):
         l2_meas = api.bench_l2_bandwidth()
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         fp32_nominal = dinfo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
-        kernel_ms = (total_ms - exchange_ms) / args.steps   # one render kernel per step (rank 0's exchange time removed)
-        ach_tflops = flops / world / args.steps / (kernel_ms * 1e-3) / 1e12
-        ach_gbs = tbytes / world / args.steps / (kernel_ms * 1e-3) / 1e9
+        # average duration of one render kernel on rank 0 (its own launches, exchange excluded)
+        kernel_ms = sum(step_ms[:-1]) / max(len(todo), 1)
+        per_launch_share = 1.0 / args.steps if (world == 1 or frame_mode) else 1.0 / args.steps / world
+        if frame_mode and fp.leftover:        # mixed whole / tile launches: use the job-wide average per launch issued
+            per_launch_share = 1.0 / (world * len(todo))
+        ach_tflops = flops * per_launch_share / (kernel_ms * 1e-3) / 1e12
+        ach_gbs = tbytes * per_launch_share / (kernel_ms * 1e-3) / 1e9
         roofline = {
             "kernel": "render_persistent_kernel" if args.pipeline == 1 else "render_wavefront_kernel",
             "bound": "fp32", "achieved": ach_tflops, "peak": fp32_meas, "unit": "TFLOP/s", "frac": ach_tflops / fp32_meas,
@@ -368,7 +421,7 @@ def run_b200(args):
             "peak_nominal": fp32_nominal, "traffic": None,
             "l2": {"achieved": ach_gbs, "peak": l2_meas, "unit": "GB/s", "frac": ach_gbs / l2_meas,
                    "note": "node/triangle record bytes; served from shared memory when the scene is staged there"},
-            "hbm": {"achieved": (w * h * (36 if True else 0)) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
+            "hbm": {"achieved": (w * h * 36) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
                     "unit": "GB/s", "note": "image traffic only: 16 B read + 16 B write + 4 B framebuffer per pixel per launch"},
             "algorithmic_flops_per_launch": flops / args.steps, "algorithmic_bytes_per_launch": tbytes / args.steps,
             "per_gpu": world > 1,
@@ -384,10 +437,14 @@ def run_b200(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "scene": scene_name, "triangles": info["n_tris"], "width": w, "height": h,
                        "spp_per_step": spp, "max_depth": md, "direct_lighting": nee, "importance_sampling": imp,
-                       "frames": f"0..{args.steps - 1}", "parallelism": f"pixel-tiles x{world}",
+                       "frames": f"0..{args.steps - 1}",
+                       "parallelism": f"pixel-tiles x{world}" + (f" (EMULATED rank 0 of {args.emulate_ranks}: not a bench value)" if args.emulate_ranks > 1 else ""),
                        "l2": "flushed between timed steps (256 MiB fill)", "pipeline": scene.last_launch_info(),
-                       "exchange": "none (1 GPU)" if world == 1 else
-                       f"one all-gather of owned pixels per image, {exchange.bytes_per_rank()} B received per rank, {exchange_ms:.3f} ms on rank 0",
+                       "exchange": "none (1 GPU)" if world == 1 else (
+                           f"frames dealt to ranks ({fp.rounds} whole frame(s) per rank, {len(fp.leftover)} tile-partitioned); one "
+                           f"all-gather of per-frame means + ordered fold per image, {fp.bytes_received()} B received per rank, "
+                           f"{exchange_ms:.3f} ms on rank 0" if frame_mode else
+                           f"one all-gather of owned pixels per image, {exchange.bytes_per_rank()} B received per rank, {exchange_ms:.3f} ms on rank 0"),
                        "lbvh_build_ms": info["build_ms"]},
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "rays_per_sample": rays / max(counters["n_samples"], 1),
@@ -410,6 +467,10 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per launch")
     ap.add_argument("--pipeline", type=int, default=0, help="0 auto, 1 persistent state machine, 2 CTA-local wavefront")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="auto", choices=["auto", "tiles"],
+                    help="N > 1: auto = whole frames per rank + tile-partitioned leftovers; tiles = every launch tile-partitioned")
+    ap.add_argument("--emulate-ranks", type=int, default=0,
+                    help="tuning aid (1 GPU): render only rank 0's tiles of an R-rank partition; value counts those pixels only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

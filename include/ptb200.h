@@ -88,6 +88,17 @@ int pt_launch(const pt_params* params, void* cuda_stream);
  * the union over ranks is bit-identical to pt_launch. */
 int pt_launch_partition(const pt_params* params, uint32_t rank, uint32_t n_ranks, void* cuda_stream);
 
+/* Frame-parallel rendering (multi-GPU, several launches per image).  pt_launch_raw renders the tiles of `rank` like
+ * pt_launch_partition but writes the launch's OWN mean (result / samplesPerPixel, alpha 1) into accumulationBuffer:
+ * nothing is read, nothing is folded, frameBuffer is ignored.  The mean of frame k depends only on (pixel, k)
+ * (pathTracerPrograms.cu:721), so different ranks can render different frames.  pt_fold_frames then applies the
+ * reference's running average (:803-811: acc += (mean_k - acc) / (k + 1)) to n_frames (<= 64) device images in frame
+ * order k = first_frame_idx .., reading `accum` first when first_frame_idx > 0, and writes accum + the sRGB frame
+ * buffer (may be NULL): bit-identical to the same frames rendered one after the other with pt_launch. */
+int pt_launch_raw(const pt_params* params, uint32_t rank, uint32_t n_ranks, void* cuda_stream);
+int pt_fold_frames(void* accum, void* frame_out, const void* const* frame_means, uint32_t first_frame_idx,
+                   uint32_t n_frames, uint32_t width, uint32_t height, void* cuda_stream);
+
 /* Owned-pixel exchange helpers (one NCCL all-gather per image sits between them).
  * pack: full-size accumulation/frame buffers -> this rank's compact tile-major buffers
  *       (pt_partition_capacity() pixels: float4 and uchar4 each).

@@ -476,3 +476,42 @@ def test_full_size_c5_4k(api, port, scenes_cache):
             _launch_dev(api, gs, p, acc2, fb2, rank=r, n=8)
     torch.cuda.synchronize()
     assert torch.equal(acc.view(torch.int32), acc2.view(torch.int32)) and torch.equal(fb, fb2)
+
+
+# ---- frame-parallel rendering: raw per-launch means + ordered fold == launches one after the other -------------------
+@pytest.mark.parametrize("name,w,h,spp,md,frames", [("cornell", 250, 122, 3, 16, 5), ("material", 160, 90, 2, 28, 3)])
+def test_raw_means_plus_fold_equal_sequential_launches(api, port, scenes_cache, name, w, h, spp, md, frames):
+    import torch
+    from acgpathtracing_b200 import multirank as M
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    stream = torch.cuda.current_stream().cuda_stream
+    acc, fb = _dev_buffers(w, h)
+    for f in range(frames):
+        _launch_dev(api, gs, api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs), acc, fb)
+    means = torch.zeros((frames, h, w, 4), dtype=torch.float32, device="cuda")
+    junk = torch.full((h, w, 4), 7, dtype=torch.uint8, device="cuda")
+    for f in range(frames):
+        p = api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs)
+        q = PathTraceParams.from_buffer_copy(p)
+        q.handle, q.accumulationBuffer, q.frameBuffer = gs.handle, means[f].data_ptr(), junk.data_ptr()
+        if f % 2 == 0:
+            api.launch_raw(q, 0, 1, stream)
+        else:                                           # the tile partition composes with raw launches
+            for r in range(3):
+                api.launch_raw(q, r, 3, stream)
+    assert bool((junk == 7).all())                      # raw launches leave the frame buffer alone
+    acc2, fb2 = _dev_buffers(w, h)
+    api.fold_frames(acc2.data_ptr(), fb2.data_ptr(), [means[f].data_ptr() for f in range(frames)], 0, w, h, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(acc.view(torch.int32), acc2.view(torch.int32)) and torch.equal(fb, fb2)
+    # resume: fold the first two, then the rest on top of the stored running average
+    acc3, fb3 = _dev_buffers(w, h)
+    api.fold_frames(acc3.data_ptr(), None, [means[f].data_ptr() for f in range(2)], 0, w, h, stream)
+    api.fold_frames(acc3.data_ptr(), fb3.data_ptr(), [means[f].data_ptr() for f in range(2, frames)], 2, w, h, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(acc.view(torch.int32), acc3.view(torch.int32)) and torch.equal(fb, fb3)
+    # the CPU mirror used by the gloo tests computes the same bits
+    cpu = M.fold_numpy([means[f].cpu().numpy() for f in range(frames)])
+    assert np.array_equal(cpu.view(np.uint32), acc.cpu().numpy().view(np.uint32))
+    with pytest.raises(api.PtError):
+        api.fold_frames(acc3.data_ptr(), None, [means[0].data_ptr()] * 65, 0, w, h, stream)

@@ -81,3 +81,76 @@ def test_exchange_is_identity_for_one_rank():
     ex = M.ImageExchange(16, 8, 0, 1, "cpu")
     a = torch.ones((8, 16, 4))
     assert ex.gather(a, torch.zeros((8, 16, 4), dtype=torch.uint8)) == 0 and ex.bytes_per_rank() == 0
+
+
+# ---- frame-parallel plan: whole frames dealt round-robin + tile-partitioned leftovers, ordered fold --------------------
+def _fake_mean(frame):
+    """Stand-in for a launch's mean image: any deterministic function of (pixel, frame)."""
+    rng = np.random.default_rng(1000 + frame)
+    x = rng.random((H, W, 4), dtype=np.float32)
+    x[..., 3] = 1.0
+    return x
+
+
+def _fp_worker(rank, world, port, out_dir, n_frames):
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from acgpathtracing_b200 import multirank as M
+
+        def render_raw(frame, r, n, out):
+            mask = M.owned_mask(W, H, r, n)
+            out.zero_()
+            out.numpy()[mask] = _fake_mean(frame)[mask]
+
+        fp = M.FrameParallel(W, H, rank, world, "cpu", n_frames, render_raw)
+        mine = fp.my_frames()
+        assert len(mine) == n_frames // world + n_frames % world
+        for f, kind in mine:
+            fp.render(f, kind)
+        acc = torch.zeros((H, W, 4), dtype=torch.float32)
+        fp.finish(acc, None)
+        np.save(os.path.join(out_dir, f"fp{rank}.npy"), acc.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_frames", [(2, 4), (2, 5), (3, 2), (3, 7)])
+def test_frame_parallel_equals_sequential_fold(tmp_path, world, n_frames):
+    from acgpathtracing_b200 import multirank as M
+    mp.spawn(_fp_worker, args=(world, _free_port(), str(tmp_path), n_frames), nprocs=world, join=True)
+    want = M.fold_numpy([_fake_mean(f) for f in range(n_frames)])
+    for r in range(world):
+        got = np.load(tmp_path / f"fp{r}.npy")
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_frame_plan_covers_every_frame_once():
+    from acgpathtracing_b200 import multirank as M
+    for world in (1, 2, 3, 4, 8):
+        for n in (1, 2, 5, 8, 9, 16):
+            rounds, left = M.frame_plan(n, world)
+            whole = sorted(i * world + r for r in range(world) for i in range(rounds))
+            assert whole + left == list(range(n))
+
+
+def test_fold_numpy_first_frame_and_weights(port, cornell):
+    """Frame 0 overwrites (pathTracerPrograms.cu:803 reads the buffer only for frames > 0) and frame k enters with weight
+    1/(k+1) in float32: the fold of [x, x, x] is x again wherever (x - x) is exact, and a constant offset converges as
+    the reference's lerp chain does.  (The GPU tests compare pt_fold_frames with real launches bit for bit.)"""
+    import oracle_api as O
+    from acgpathtracing_b200 import multirank as M
+    osc = O.OracleScene(port, cornell)
+    w, h = 24, 16
+    first = osc.render(O.make_params(port, w, h, 2, 4, frame=0, nee=True, importance=True), math_mode=1, use_bvh=True)["accum"]
+    assert np.array_equal(M.fold_numpy([first]).view(np.uint32), first.view(np.uint32))
+    assert np.array_equal(M.fold_numpy([first, first, first]).view(np.uint32), first.view(np.uint32))
+    a = np.zeros((h, w, 4), np.float32)
+    b = np.full((h, w, 4), 3.0, np.float32)
+    got = M.fold_numpy([a, b, b])                    # 0 -> 0 + (3-0)/2 = 1.5 -> 1.5 + (3-1.5)/3 = 2
+    assert np.all(got[..., :3] == np.float32(1.5) + np.float32(1.0) / np.float32(3) * np.float32(1.5))
+    resumed = M.fold_numpy([b], first_frame=2, acc=M.fold_numpy([a, b]))
+    assert np.array_equal(resumed.view(np.uint32), got.view(np.uint32))
