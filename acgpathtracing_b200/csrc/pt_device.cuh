@@ -80,6 +80,12 @@ struct BvhView {
 //                    divergent LDS.128 costs exactly its 4 data wavefronts.
 struct FetchGlobal {
     const float4 *nodes, *tris, *shade, *mats;
+    // a deferred child will be fetched after the subtree of its sibling: start pulling its record towards L2/L1 now
+    __device__ __forceinline__ void prefetch_child(int c) const
+    {
+        const void* p = c >= 0 ? (const void*)(nodes + 4 * c) : (const void*)(tris + 3 * (~c));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
     __device__ __forceinline__ float4 node(int i, int q) const { return __ldg(nodes + 4 * i + q); }
     __device__ __forceinline__ float4 tri(int i, int q) const { return __ldg(tris + 3 * i + q); }
     __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return __ldg(shade + prim); }
@@ -87,6 +93,7 @@ struct FetchGlobal {
 };
 struct FetchShared {
     const float4 *nodes, *tris, *shade, *mats;
+    __device__ __forceinline__ void prefetch_child(int) const {}
     __device__ __forceinline__ float4 node(int i, int q) const { return nodes[4 * i + q]; }
     __device__ __forceinline__ float4 tri(int i, int q) const { return tris[3 * i + q]; }
     __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim]; }
@@ -95,6 +102,7 @@ struct FetchShared {
 template <int SHIFT>
 struct FetchSharedBanked {
     const float4 *nodes, *tris, *shade, *mats;   // each already offset by this lane's copy index
+    __device__ __forceinline__ void prefetch_child(int) const {}
     __device__ __forceinline__ float4 node(int i, int q) const { return nodes[((4 * i) << SHIFT) + (q << SHIFT)]; }
     __device__ __forceinline__ float4 tri(int i, int q) const { return tris[((3 * i) << SHIFT) + (q << SHIFT)]; }
     __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim << SHIFT]; }
@@ -228,7 +236,10 @@ __device__ __forceinline__ void trav_node_step(Trav& t, const STK& stack, const 
     const bool none = !(h0 || h1);
     const bool can_pop = t.sp > 0;
     const int top = stack.get(can_pop ? t.sp - 1 : 0);
-    if (both) stack.put(t.sp, far_child);
+    if (both) {
+        stack.put(t.sp, far_child);
+        f.prefetch_child(far_child);
+    }
     t.cur = none ? (can_pop ? top : kTravDone) : near_child;
     t.sp += both ? 1 : ((none && can_pop) ? -1 : 0);
 }

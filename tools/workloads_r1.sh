@@ -3,14 +3,13 @@ run() { echo "== $*"; env "${@:2}" timeout 600 python bench.py --workload $1 --s
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('RESULT', round(d['value'],1), 'Mps/s', round(d['ms_per_step'],2),'ms', d['config']['pipeline'], 'tris', d['config']['triangles']); print('SCHED', json.dumps(d.get('sched_rank0'))[:400])
+        d=json.loads(l); print('RESULT', round(d['value'],1), 'Mps/s', round(d['ms_per_step'],2),'ms', d['config']['pipeline'], 'tris', d['config']['triangles'])
     else: print(l.rstrip()[-300:])
 "; }
-run c3 A=1
-run c3 PTB_WF_SMEM_KB=160
-run c3 PTB_WF_SMEM_KB=112 PTB_WF_BLOCK=384
-run c3 PTB_WF_BLOCK=512
 run c4 A=1
-run c4 PTB_WF_SMEM_KB=160
-run c4 PTB_WF_BLOCK=512
-run c4 PTB_WF_SMEM_KB=112 PTB_WF_BLOCK=384
+run c4 PTB_WF_BLOCK=640
+run c4 PTB_WF_BLOCK=736
+run c4 PTB_WF_SMEM_KB=224
+run c4 PTB_WF_SMEM_KB=224 PTB_WF_BLOCK=768
+run c3 A=1
+run c3 PTB_WF_SMEM_KB=224
