@@ -8,15 +8,17 @@
 // Russian roulette, next ray / next sample / next pixel).  With one path per lane held in registers the 32 lanes
 // of a warp are spread over the four kinds and each kind runs with a handful of lanes (ncu: 25 % useful SIMT
 // efficiency, profiles/r1_v2_*).  Here paths live in SHARED MEMORY and lanes are just workers:
-//   * one persistent CTA per SM owns NP = 32 * P paths (P <= 32); path id = 32 * j + c belongs to "column" c and
-//     is only ever processed by lane c of some warp;
+//   * one persistent CTA per SM (up to 768 threads) owns NP = 32 * P paths (P <= 32; 1024 for the Cornell box);
+//     path id = 32 * j + c belongs to "column" c and is only ever processed by lane c of some warp;
 //   * the queues are four 32-bit words per column (one per stage): bit j of mask[stage][c] says that path
 //     32 * j + c waits for that stage.  Push = atomicOr, pop = atomicAnd on the lane's own word: no ring buffers,
 //     no slots to spin on, nothing to overflow, and every queue word sits in its own bank;
-//   * a warp repeatedly votes for the stage with the most non-empty columns (ballot + popc), every lane pops one
-//     path of its column, the warp runs that stage's code ONCE for (typically) 30+ lanes, and every lane pushes its
-//     path to the stage it needs next.  NODE batches run up to K slab-test steps and stop early when too many lanes
-//     have left the NODE state;
+//   * a warp repeatedly votes (ballot + popc) for the most downstream stage that can fill all 32 lanes, else the
+//     stage with the most non-empty columns; every lane pops one path of its column, the warp runs that stage's code
+//     ONCE for (measured) 27-28 lanes, and every lane pushes its path to the stage it needs next.  NODE batches run
+//     several slab-test steps and stop early when too many lanes have left the NODE state.  When only a few paths
+//     are left in the CTA (end of the launch) traversals run to completion instead of hopping between queues;
+//   * pixels are taken from a global counter, expensive tiles first (render.cu tile_order_update);
 //   * bank conflicts are designed out: all per-path state is float4 arrays indexed by path id (ids of a batch are
 //     distinct mod 32, hence distinct mod 8 inside every quarter-warp => conflict-free LDS.128/STS.128), traversal
 //     stacks are level-major word arrays (bank = column), and a scene small enough is staged as 8 interleaved
@@ -37,7 +39,7 @@ using namespace ptd;
 namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
-constexpr int kWfBlock = 768;          // threads per CTA (16 warps); one CTA per SM
+constexpr int kWfBlock = 768;          // most threads per CTA (24 warps, 80 registers); one CTA per SM
 constexpr int kCtlF4 = 33;             // float4s in front of the state arrays: mask[4][32] + 4 control words
 constexpr int kStateF4 = 9;            // float4 state arrays per path
 constexpr size_t kMaxSmem = 227 * 1024;
@@ -51,7 +53,6 @@ struct WfConst {
     uint32_t copies_shift;   // staged scene copies = 1 << copies_shift
     int node_steps;          // K: slab-test steps per NODE batch
     int node_keep8;          // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
-    int w[4];                // vote weights NODE, LEAF, SHADE, END (applied to the backlog of stages that can fill a warp)
     int full_cols;           // columns that count as "can fill a warp"
     int sticky;              // repeats of the same stage without a full vote while it fills the whole warp
     int tail_cols;           // tail mode when the non-empty columns of all four queues add up to at most this
@@ -656,7 +657,6 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     if (!wavefront_plan(s, wc, smem_bytes, smem_scene)) return cudaErrorInvalidConfiguration;
     wc.node_steps = s.wf_tune[4];
     wc.node_keep8 = s.wf_tune[5];
-    for (int i = 0; i < 4; ++i) wc.w[i] = s.wf_tune[i];
     wc.full_cols = s.wf_tune[6];
     wc.sticky = s.wf_tune[7];
     wc.tail_cols = s.wf_tune[8];
@@ -668,7 +668,6 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
         if (n >= 9 && v[8] >= 0) wc.sticky = v[8];
 
         if (n >= 6) {
-            for (int i = 0; i < 4; ++i) wc.w[i] = v[i];
             wc.node_steps = v[4];
             wc.node_keep8 = v[5];
         }
