@@ -72,6 +72,7 @@ struct Scene {
     uint32_t tile_order_count = 0;
     float tile_order_key[16] = {-1.f};
     bool tile_order_enabled = true;
+    bool shortlist_enabled = true;     // per-pixel candidate lists for camera rays (wavefront.cu pixel_candidates)
 
     // last launch
     uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0;

@@ -40,12 +40,16 @@ namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kWfBlock = 768;          // most threads per CTA (24 warps, 80 registers); one CTA per SM
-constexpr int kCtlF4 = 33;             // float4s in front of the state arrays: mask[4][32] + 4 control words
+constexpr int kCtlF4 = 41;             // float4s in front of the state arrays: mask[5][32] + 4 control words
 constexpr int kStateF4 = 9;            // float4 state arrays per path
 constexpr size_t kMaxSmem = 227 * 1024;
 
-enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3, ST_TAIL = 4 };   // 0..3 have queues; TAIL serves NODE + LEAF
-enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3 };
+enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3, ST_PIXEL = 4, ST_TAIL = 5 };   // 0..4 have queues; TAIL serves NODE + LEAF
+constexpr int kQueues = 5;
+constexpr int kMissLoop = 16;                     // samples of an all-miss pixel finished per END visit
+constexpr uint32_t kCandNone = 0xffffffffu;       // per-pixel candidate list: no triangle can be hit by a camera ray
+constexpr uint32_t kCandOverflow = 0xfffffffeu;   // more than 4 candidates (or lists disabled): traverse the BVH
+enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3, MODE_NEWPIX = 4 };
 
 struct WfConst {
     uint32_t np;             // paths per CTA
@@ -56,6 +60,7 @@ struct WfConst {
     int full_cols;           // columns that count as "can fill a warp"
     int sticky;              // repeats of the same stage without a full vote while it fills the whole warp
     int tail_cols;           // tail mode when the non-empty columns of all four queues add up to at most this
+    int miss_loop;           // samples of an all-miss pixel finished per END visit
 };
 
 struct ThreadCounters {
@@ -129,7 +134,48 @@ template <> struct WfFetch<-1> { typedef FetchGlobal type; };
 __device__ __forceinline__ float4 pack(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
 
-template <bool COUNT, bool PROBE, int SCENE>
+// Candidate list of a pixel: the (at most 4) leaves whose triangle can be reached by ANY camera ray of the pixel.
+// All sample rays of pixel (ix, iy) start at the eye and point into the pyramid spanned by the un-normalised
+// directions d(dx, dy) = dx U + dy V + W (:732-737) at the pixel's four corners (jitter in [0, 1)).  A triangle whose
+// three vertices lie outside one of the pyramid's four side planes, by more than a margin of 2e-4 of their distance
+// (a quarter of a 1080p pixel; float error of the ray/triangle test is ~1e-6), cannot be hit.  Only a superset is
+// needed: the list decides which triangles are TESTED, never what a test returns.
+template <class FETCH>
+__device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, const FETCH& f, uint32_t ix, uint32_t iy)
+{
+    const float w = (float)(int)lc.width, h = (float)(int)lc.height;
+    const float dx0 = 2.0f * (((float)ix + 0.0f) / w) - 1.0f, dx1 = 2.0f * (((float)ix + 1.0f) / w) - 1.0f;
+    const float dy0 = 2.0f * (((float)iy + 0.0f) / h) - 1.0f, dy1 = 2.0f * (((float)iy + 1.0f) / h) - 1.0f;
+    const float3 c00 = dx0 * lc.U + dy0 * lc.V + lc.W, c10 = dx1 * lc.U + dy0 * lc.V + lc.W;
+    const float3 c11 = dx1 * lc.U + dy1 * lc.V + lc.W, c01 = dx0 * lc.U + dy1 * lc.V + lc.W;
+    const float3 cc = (0.5f * (dx0 + dx1)) * lc.U + (0.5f * (dy0 + dy1)) * lc.V + lc.W;
+    float3 n[4] = {cross(c00, c10), cross(c10, c11), cross(c11, c01), cross(c01, c00)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        n[i] = normalize(n[i]);
+        if (dot(n[i], cc) < 0.0f) n[i] = -n[i];             // inside the pyramid = positive side
+    }
+    uint32_t cand = kCandNone;
+    int count = 0;
+    for (uint32_t leaf = 0; leaf < lc.bvh.n_tris; ++leaf) {
+        const float4 t0 = f.tri((int)leaf, 0), t1 = f.tri((int)leaf, 1), t2 = f.tri((int)leaf, 2);
+        const float3 v0 = xyz(t0) - lc.eye, v1 = v0 + xyz(t1), v2 = v0 + xyz(t2);
+        const float reach = fmaxf(fmaxf(fabsf(v0.x) + fabsf(v0.y) + fabsf(v0.z), fabsf(v1.x) + fabsf(v1.y) + fabsf(v1.z)),
+                                  fabsf(v2.x) + fabsf(v2.y) + fabsf(v2.z));
+        const float m = -2e-4f * reach;
+        bool outside = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) outside = outside || (dot(n[i], v0) < m && dot(n[i], v1) < m && dot(n[i], v2) < m);
+        if (!outside) {
+            if (count == 4 || leaf >= 0xfeu) return kCandOverflow;
+            cand = (cand & ~(0xffu << (8 * count))) | (leaf << (8 * count));
+            ++count;
+        }
+    }
+    return cand;
+}
+
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT>
 __global__ void __launch_bounds__(kWfBlock, 1)
 render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_constant__ WfConst wc)
 {
@@ -137,7 +183,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t NP = wc.np;
     uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);            // [4][32]
-    uint32_t* ctl = mask + 128;                                     // [0] idle paths  [1] error flag
+    uint32_t* ctl = mask + kQueues * 32;                            // [0] idle paths  [1] error flag
     float4* R0 = smem4 + kCtlF4;        // (ray origin, -)
     float4* R1 = R0 + NP;               // (ray direction, -)
     float4* R2 = R1 + NP;               // (1 / direction, -)
@@ -147,7 +193,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     float4* RS = P1 + NP;               // (result, add.z)
     float4* S0 = RS + NP;               // (next ray origin, add.x)     add = NEE term, applied when the shadow ray is free
     float4* S1 = S0 + NP;               // (next ray direction, add.y)
-    int* stack_mem = reinterpret_cast<int*>(S1 + NP);               // [stack_depth][NP]
+    uint32_t* CAND = reinterpret_cast<uint32_t*>(S1 + NP);          // per pixel: up to 4 leaves a camera ray can hit
+    int* stack_mem = reinterpret_cast<int*>(CAND + NP);             // [stack_depth][NP]
     float4* scene = reinterpret_cast<float4*>(stack_mem + (size_t)wc.stack_depth * NP);
 
     typename WfFetch<SCENE>::type f;
@@ -173,14 +220,14 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         f.mats = s_mats + k;
     }
 
-    // every path starts "fresh": waiting in END for its first pixel
-    for (uint32_t i = threadIdx.x; i < 132; i += blockDim.x) mask[i] = 0u;
+    // every path starts "fresh": waiting in PIXEL for its first pixel
+    for (uint32_t i = threadIdx.x; i < kQueues * 32 + 4; i += blockDim.x) mask[i] = 0u;
     for (uint32_t pid = threadIdx.x; pid < NP; pid += blockDim.x)
         TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_FRESH << 8));
     __syncthreads();
     if (warp == 0) {
         const uint32_t P = NP >> 5;
-        mask[ST_END * 32 + lane] = P >= 32u ? 0xffffffffu : ((1u << P) - 1u);
+        mask[ST_PIXEL * 32 + lane] = P >= 32u ? 0xffffffffu : ((1u << P) - 1u);
     }
     __syncthreads();
 
@@ -209,9 +256,11 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         if (!decided) {
             const uint32_t m0 = vol_ld(mask + 0 * 32 + lane), m1 = vol_ld(mask + 1 * 32 + lane);
             const uint32_t m2 = vol_ld(mask + 2 * 32 + lane), m3 = vol_ld(mask + 3 * 32 + lane);
+            const uint32_t m4 = vol_ld(mask + 4 * 32 + lane);
             const uint32_t b0 = __ballot_sync(kFull, m0 != 0u), b1 = __ballot_sync(kFull, m1 != 0u);
             const uint32_t b2 = __ballot_sync(kFull, m2 != 0u), b3 = __ballot_sync(kFull, m3 != 0u);
-            if ((b0 | b1 | b2 | b3) == 0u) {
+            const uint32_t b4 = __ballot_sync(kFull, m4 != 0u);
+            if ((b0 | b1 | b2 | b3 | b4) == 0u) {
                 if (vol_ld(ctl) >= NP) break;                // every path has run out of pixels
                 if (++idle_polls > (1u << 26)) {             // watchdog: never spin forever
                     ctl[1] = 1u;
@@ -224,10 +273,12 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
             idle_polls = 0;
             sticky = 0;
-            // the most downstream stage that can fill a warp (END > SHADE > LEAF > NODE): drains paths towards
+            // the most downstream stage that can fill a warp (PIXEL > END > SHADE > LEAF > NODE): drains paths towards
             // completion and leaves the NODE backlog as the reservoir; else the stage with the most columns
             const uint32_t fullmask = wc.full_cols >= 32 ? 0xffffffffu : 0u;
-            if (fullmask ? (b3 == fullmask) : (__popc(b3) >= wc.full_cols)) {
+            if (__popc(b4) >= 16) {                          // long and rare batches: half a warp is worth running
+                stage = ST_PIXEL;
+            } else if (fullmask ? (b3 == fullmask) : (__popc(b3) >= wc.full_cols)) {
                 stage = ST_END;
             } else if (fullmask ? (b2 == fullmask) : (__popc(b2) >= wc.full_cols)) {
                 stage = ST_SHADE;
@@ -236,21 +287,23 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             } else if (fullmask ? (b0 == fullmask) : (__popc(b0) >= wc.full_cols)) {
                 stage = ST_NODE;
             } else {
-                const int c0 = __popc(b0), c1 = __popc(b1), c2 = __popc(b2), c3 = __popc(b3);
+                const int c0 = __popc(b0), c1 = __popc(b1), c2 = __popc(b2), c3 = __popc(b3), c4 = __popc(b4);
                 int best = c0;
                 stage = ST_NODE;
                 if (c1 > best) stage = ST_LEAF, best = c1;
                 if (c2 > best) stage = ST_SHADE, best = c2;
                 if (c3 > best) stage = ST_END, best = c3;
+                if (c4 > best) stage = ST_PIXEL, best = c4;
                 // Tail of the launch (few paths left in this CTA): regrouping cannot fill warps any more and every queue
                 // hop only adds latency to the last pixels, so traversals run to completion in one go.
-                if (stage <= ST_LEAF && c0 + c1 + c2 + c3 <= wc.tail_cols) {
+                if (stage <= ST_LEAF && c0 + c1 + c2 + c3 + c4 <= wc.tail_cols) {
                     stage = ST_TAIL;
                     msnap = m0;
                     msnap2 = m1;
                 }
             }
-            if (stage != ST_TAIL) msnap = stage == ST_NODE ? m0 : (stage == ST_LEAF ? m1 : (stage == ST_SHADE ? m2 : m3));
+            if (stage != ST_TAIL)
+                msnap = stage == ST_NODE ? m0 : (stage == ST_LEAF ? m1 : (stage == ST_SHADE ? m2 : (stage == ST_END ? m3 : m4)));
         }
         const int rot = (warp * 7 + (int)(it++)) & 31;
 
@@ -426,6 +479,36 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     wf_push(mask, ST_END, lane, j);
                 }
             }
+        } else if (stage == ST_PIXEL) {
+            // ---- PIXEL: write a finished pixel (:784-814), take the next one from the work counter, build its list of
+            // triangles a camera ray can reach.  Rare per sample (once per samplesPerPixel) and long, so it has its own
+            // queue instead of running for one or two lanes inside END.
+            const int j = wf_pop_converged(mask + ST_PIXEL * 32 + lane, msnap, rot);
+            if (j >= 0) {
+                const int pid = j * 32 + lane;
+                const int mode = __float_as_int(TS[pid].w) >> 8;
+                if (mode != MODE_FRESH) {
+                    const float4 p0 = P0[pid], p1 = P1[pid], rs = RS[pid];
+                    const uint32_t pix = __float_as_uint(p1.w);
+                    const uint32_t image_index = (pix >> 16) * lc.width + (pix & 0xffffu);
+                    write_pixel(lc, image_index, xyz(rs));
+                    if (PROBE) {
+                        if (lc.dbg_final_path_seed) lc.dbg_final_path_seed[image_index] = __float_as_uint(p0.w);
+                        if (lc.dbg_final_pixel_seed) lc.dbg_final_pixel_seed[image_index] = __float_as_uint(p1.z);
+                    }
+                }
+                uint32_t ix = 0u, iy = 0u;
+                if (take_pixel(lc, n_work, atomicAdd(lc.work_counter, 1u), ix, iy)) {
+                    const uint32_t pixel_seed = tea4(iy * lc.width + ix, lc.frame);            // :721
+                    CAND[pid] = SHORT ? pixel_candidates(lc, f, ix, iy) : kCandOverflow;
+                    P1[pid] = make_float4(__int_as_float(0), __uint_as_float(lc.spp), __uint_as_float(pixel_seed),
+                                          __uint_as_float(ix | (iy << 16)));
+                    TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_NEWPIX << 8));
+                    wf_push(mask, ST_END, lane, j);
+                } else {
+                    atomicAdd(ctl, 1u);                       // this path is done for the launch
+                }
+            }
         } else {
             // ---- END: finish the segment (__miss__ms :833-847, shadow result, :760-778) and start the next ray --------
             const int j = wf_pop_converged(mask + ST_END * 32 + lane, msnap, rot);
@@ -438,25 +521,25 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             p.depth = 0;
             uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
             float3 result = f3(0.0f);
-            bool alive = j >= 0;
+            bool alive = j >= 0, need_sample = false;
             if (j >= 0) {
                 const float4 ts = TS[pid];
                 const int mode = __float_as_int(ts.w) >> 8;
-                bool need_pixel = false, need_sample = false;
-                if (mode == MODE_FRESH) {
-                    need_pixel = true;
+                const float4 p1 = P1[pid];
+                left = __float_as_uint(p1.y);
+                pixel_seed = __float_as_uint(p1.z);
+                const uint32_t pix = __float_as_uint(p1.w);
+                ix = pix & 0xffffu;
+                iy = pix >> 16;
+                if (mode == MODE_NEWPIX) {
+                    need_sample = true;                      // first sample of a new pixel; result starts at 0
                 } else {
-                    const float4 p0 = P0[pid], p1 = P1[pid], rs = RS[pid];
+                    const float4 p0 = P0[pid], rs = RS[pid];
                     p.att = xyz(p0);
                     p.seed = __float_as_uint(p0.w);
                     const int dw = __float_as_int(p1.x);
                     p.depth = dw & 0xff;
                     bool done = ((dw >> 8) & 1) != 0;
-                    left = __float_as_uint(p1.y);
-                    pixel_seed = __float_as_uint(p1.z);
-                    const uint32_t pix = __float_as_uint(p1.w);
-                    ix = pix & 0xffffu;
-                    iy = pix >> 16;
                     result = xyz(rs);
                     float3 rad;
                     if (mode == MODE_RAD) {                  // miss
@@ -474,7 +557,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                         p.o = xyz(s0);
                         p.d = xyz(s1);
                         rad = f3(0.0f);
-                        if (done) rad = xyz(f.mat((int)((uint32_t)dw >> 16), 1));                               // emissive hit, :992-996
+                        if (done) rad = xyz(f.mat((int)((uint32_t)dw >> 16), 1));               // emissive hit, :992-996
                         if (mode == MODE_SHADOW && __float_as_uint(ts.y) == kNoPrim)
                             rad = rad + f3(s0.w, s1.w, rs.w);                                  // unoccluded, :1019-1024
                     }
@@ -482,29 +565,18 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                      // :763
                     const bool rr = rnd(p.seed) > pr;                                          // :765
                     if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                     // :767
-                        if (--left == 0u) {
-                            const uint32_t image_index = iy * lc.width + ix;
-                            write_pixel(lc, image_index, result);
-                            if (PROBE) {
-                                if (lc.dbg_final_path_seed) lc.dbg_final_path_seed[image_index] = p.seed;
-                                if (lc.dbg_final_pixel_seed) lc.dbg_final_pixel_seed[image_index] = pixel_seed;
-                            }
-                            need_pixel = true;
+                        if (--left == 0u) {                  // pixel finished: the PIXEL stage writes it
+                            P0[pid] = pack(p.att, __uint_as_float(p.seed));
+                            P1[pid] = make_float4(p1.x, __uint_as_float(0u), p1.z, p1.w);
+                            RS[pid] = pack(result, 0.0f);
+                            wf_push(mask, ST_PIXEL, lane, j);
+                            alive = false;
                         } else {
                             need_sample = true;
                         }
                     } else {
                         p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
                         ++p.depth;
-                    }
-                }
-                if (need_pixel) {
-                    alive = take_pixel(lc, n_work, atomicAdd(lc.work_counter, 1u), ix, iy);
-                    if (alive) {
-                        pixel_seed = tea4(iy * lc.width + ix, lc.frame);                       // :721
-                        result = f3(0.0f);
-                        left = lc.spp;
-                        need_sample = true;
                     }
                 }
                 if (need_sample) {
@@ -520,24 +592,74 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                         }
                     }
                 }
-                if (!alive) atomicAdd(ctl, 1u);
             }
-            // "continue the path", "next sample" and "next pixel" took different branches above; reconverge before the
-            // part they share (set up the next ray), or it runs once per branch at half occupancy
+            // "continue the path" and "next sample" took different branches above; reconverge before the part they share
+            // (set up the next ray), or it runs once per branch at half occupancy
             __syncwarp();
             if (alive) {
                 if (COUNT) ctr.n_radiance++;
-                const Ray r = make_ray(p.o, p.d);                                              // traceRadiance :577-635
-                R0[pid] = pack(r.o, 0.0f);
-                R1[pid] = pack(r.d, 0.0f);
-                R2[pid] = pack(r.inv, 0.0f);
-                TS[pid] = make_float4(1e16f, __uint_as_float(kNoPrim), __int_as_float(have_tris ? 0 : kTravDone),
-                                      __int_as_float(MODE_RAD << 8));                          // tmax :755
                 P0[pid] = pack(p.att, __uint_as_float(p.seed));
                 P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
                                       __uint_as_float(ix | (iy << 16)));
                 RS[pid] = pack(result, 0.0f);
-                wf_push(mask, have_tris ? ST_NODE : ST_END, lane, j);
+                const uint32_t cand = (SHORT && need_sample) ? CAND[pid] : kCandOverflow;
+                if (SHORT && cand == kCandNone) {
+                    // No triangle can be reached from this pixel: every camera ray is a miss.  Finish up to
+                    // kMissLoop samples right here, each exactly as the miss branch above does (:833-847, :760-772):
+                    // background times attenuation 1, the Russian-roulette draw, next sample.  Background tiles are
+                    // handed out together (tile order), so the lanes of a batch take this loop together.
+                    for (int rep = 0; rep < wc.miss_loop && left > 1u; ++rep) {
+                        if (PROBE && left == lc.spp) {
+                            const uint32_t image_index = iy * lc.width + ix;
+                            if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
+                            if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = 0.0f;
+                        }
+                        result = result + f3(0.0f);                                            // :760
+                        result = result + lc.background * p.att;                               // :761
+                        (void)rnd(p.seed);                                                     // :765 (done anyway)
+                        --left;
+                        generate_camera_ray(lc, ix, iy, pixel_seed, p);
+                    }
+                    P0[pid] = pack(p.att, __uint_as_float(p.seed));
+                    P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
+                                          __uint_as_float(ix | (iy << 16)));
+                    RS[pid] = pack(result, 0.0f);
+                }
+                if (SHORT && cand != kCandOverflow) {
+                    // camera ray of a pixel with a candidate list: closest hit among <= 4 triangles, no traversal.  The
+                    // list holds every triangle any camera ray of the pixel can reach (pixel_candidates), and the
+                    // closest hit under (t, primIdx) does not depend on the order of the tests => same (t, prim).
+                    Ray r;
+                    r.o = p.o;
+                    r.d = p.d;
+                    r.inv = r.ood = f3(0.0f);
+                    float best_t = 1e16f;                                                      // tmax :755
+                    uint32_t best_prim = kNoPrim;
+                    for (uint32_t c = cand; (c & 0xffu) != 0xffu; c = (c >> 8) | 0xff000000u) {
+                        const int leaf = (int)(c & 0xffu);
+                        const float4 t0 = f.tri(leaf, 0), t1 = f.tri(leaf, 1), t2 = f.tri(leaf, 2);
+                        float th;
+                        if (ray_tri(r, xyz(t0), xyz(t1), xyz(t2), 0.01f, 1e16f, th)) {         // tmin :754
+                            const uint32_t prim = __float_as_uint(t0.w);
+                            if (th < best_t || (th == best_t && prim < best_prim)) {
+                                best_t = th;
+                                best_prim = prim;
+                            }
+                        }
+                    }
+                    R0[pid] = pack(r.o, 0.0f);
+                    R1[pid] = pack(r.d, 0.0f);
+                    TS[pid] = make_float4(best_t, __uint_as_float(best_prim), __int_as_float(kTravDone), __int_as_float(MODE_RAD << 8));
+                    wf_push(mask, best_prim != kNoPrim ? ST_SHADE : ST_END, lane, j);
+                } else {
+                    const Ray r = make_ray(p.o, p.d);                                          // traceRadiance :577-635
+                    R0[pid] = pack(r.o, 0.0f);
+                    R1[pid] = pack(r.d, 0.0f);
+                    R2[pid] = pack(r.inv, 0.0f);
+                    TS[pid] = make_float4(1e16f, __uint_as_float(kNoPrim), __int_as_float(have_tris ? 0 : kTravDone),
+                                          __int_as_float(MODE_RAD << 8));                      // tmax :755
+                    wf_push(mask, have_tris ? ST_NODE : ST_END, lane, j);
+                }
             }
         }
     }
@@ -565,10 +687,10 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     if (threadIdx.x == 0 && vol_ld(ctl + 1)) atomicAdd(lc.error_flag, 1ull);   // watchdog fired
 }
 
-template <bool COUNT, bool PROBE, int SCENE>
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT>
 cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc, size_t smem_bytes, cudaStream_t stream)
 {
-    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE>;
+    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE, SHORT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -609,7 +731,7 @@ static bool wavefront_plan(const Scene& s, WfConst& wc, size_t& smem_bytes, bool
     if (depth > 255u) return false;
     const size_t scene_f4 = 4 * (size_t)s.n_nodes + 4 * (size_t)s.n_tris + 3 * (size_t)s.n_mats;
     const size_t fixed = (size_t)kCtlF4 * 16;
-    const size_t per_path = (size_t)kStateF4 * 16 + 4 * (size_t)depth;
+    const size_t per_path = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;   // state, candidate word, stack
     // scene copies: 8 if the paths still get >= 512 slots, else 1; larger scenes stay in global memory
     for (int shift = 3; shift >= 0; shift -= 3) {
         const size_t scene_bytes = (scene_f4 * 16) << shift;
@@ -660,7 +782,9 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     wc.full_cols = s.wf_tune[6];
     wc.sticky = s.wf_tune[7];
     wc.tail_cols = s.wf_tune[8];
+    wc.miss_loop = kMissLoop;
     if (const char* tc = getenv("PTB_WF_TAIL")) wc.tail_cols = atoi(tc);
+    if (const char* ml = getenv("PTB_WF_MISSLOOP")) wc.miss_loop = atoi(ml);
     if (const char* env = getenv("PTB_WF")) {   // tuning experiments: "w_node,w_leaf,w_shade,w_end,K,keep8[,P[,full_cols]]" (P = 0: default)
         int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         const int n = sscanf(env, "%d,%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]);
@@ -672,20 +796,25 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
             wc.node_keep8 = v[5];
         }
         if (n >= 7 && v[6] >= 1 && (uint32_t)v[6] * 32u < wc.np) {
-            const size_t per_path = (size_t)kStateF4 * 16 + 4 * (size_t)wc.stack_depth;
+            const size_t per_path = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)wc.stack_depth;
             smem_bytes -= (wc.np - 32u * v[6]) * per_path;
             wc.np = 32u * v[6];
         }
     }
     const bool count = s.count_enabled;
     const int scene = smem_scene ? (int)wc.copies_shift : -1;
-#define PTB_WF_DISPATCH(COUNT, PROBE)                                                             \
-    (scene == 3   ? launch_wavefront<COUNT, PROBE, 3>(s, lc, wc, smem_bytes, stream)              \
-     : scene == 0 ? launch_wavefront<COUNT, PROBE, 0>(s, lc, wc, smem_bytes, stream)              \
-                  : launch_wavefront<COUNT, PROBE, -1>(s, lc, wc, smem_bytes, stream))
-    if (probe) return PTB_WF_DISPATCH(false, true);
-    if (count) return PTB_WF_DISPATCH(true, false);
-    return PTB_WF_DISPATCH(false, false);
+    // Per-pixel candidate lists for camera rays: only where building one (a loop over all triangles per pixel) is
+    // cheap, i.e. tiny scenes staged with 8 copies.  The counted kernel always traverses, so that its node / triangle
+    // counters stay the ones of the specified traversal (and equal to the oracle's).
+    static const bool short_off = getenv("PTB_WF_SHORT") && atoi(getenv("PTB_WF_SHORT")) == 0;   // A/B experiments
+    const bool use_short = scene == 3 && s.n_tris <= 64 && s.shortlist_enabled && !short_off;
+#define PTB_WF_DISPATCH(COUNT, PROBE, SHORT)                                                      \
+    (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT>(s, lc, wc, smem_bytes, stream)       \
+     : scene == 0 ? launch_wavefront<COUNT, PROBE, 0, false>(s, lc, wc, smem_bytes, stream)       \
+                  : launch_wavefront<COUNT, PROBE, -1, false>(s, lc, wc, smem_bytes, stream))
+    if (probe) return use_short ? PTB_WF_DISPATCH(false, true, true) : PTB_WF_DISPATCH(false, true, false);
+    if (count) return PTB_WF_DISPATCH(true, false, false);
+    return use_short ? PTB_WF_DISPATCH(false, false, true) : PTB_WF_DISPATCH(false, false, false);
 #undef PTB_WF_DISPATCH
 }
 
