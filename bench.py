@@ -420,13 +420,16 @@ def run_b200(args):
             "peak_source": "measured live by pt_bench_fp32_peak (dependent-free FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
             "peak_nominal": fp32_nominal,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this
-            # command on C2 (profiles/r1_v3e_wavefront_ncu_summary.txt: 368,896 + 494,336 B); other workloads: not captured
-            "traffic": 863232 if (args.workload == "c2" and args.pipeline != 1 and not args.spp) else None,
+            # command on C2 (profiles/r1_v3f_wavefront_ncu_summary.txt: 415,744 + 548,096 B); other workloads: not captured
+            "traffic": 963840 if (args.workload == "c2" and args.pipeline != 1 and not args.spp) else None,
             "l2": {"achieved": ach_gbs, "peak": l2_meas, "unit": "GB/s", "frac": ach_gbs / l2_meas,
                    "note": "node/triangle record bytes; served from shared memory when the scene is staged there"},
             "hbm": {"achieved": (w * h * 36) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
                     "unit": "GB/s", "note": "image traffic only: 16 B read + 16 B write + 4 B framebuffer per pixel per launch"},
             "algorithmic_flops_per_launch": flops / args.steps, "algorithmic_bytes_per_launch": tbytes / args.steps,
+            "algorithmic_note": "work of the SPECIFIED traversal (every ray through the LBVH), counted by the instrumented kernel and "
+                                "equal to the oracle's counts; the timed kernel resolves camera rays of tiny scenes from per-pixel "
+                                "candidate lists instead, which lowers the work done, not the work credited",
             "per_gpu": world > 1,
         }
         if world == 1 and not args.no_cpu_baseline:
