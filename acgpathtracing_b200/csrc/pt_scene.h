@@ -17,6 +17,21 @@ namespace ptb {
 
 constexpr uint64_t kSceneMagic = 0x5054423230305343ull;   // "PTB200SC"
 
+// Scheduling constants of render_wavefront_kernel; the defaults are the measured optimum on C2 (profiles/README.md).
+// PTB_TUNE="key=value,..." overrides them per process for experiments (wavefront.cu wavefront_launch).
+struct WfTune {
+    int node_votes = 6;      // votes (of two slab-test steps each) per NODE batch
+    int node_keep8 = 2;      // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
+    int full_cols = 32;      // a downstream stage is taken as soon as this many columns have a waiting path
+    int sticky = 4;          // repeats of the same stage without a full vote while it fills the whole warp
+    int tail_cols = 24;      // tail mode when the non-empty columns of all queues add up to at most this
+    int miss_loop = 16;      // samples of an all-miss pixel finished per END visit
+    int paths32 = 0;         // paths per CTA / 32 (0 = as many as fit)
+    int block = 0;           // threads per CTA (0 = derived from the paths)
+    int smem_kb = 200;       // shared-memory budget for the paths when the scene is read from global memory
+    int shortlist = 1;       // per-pixel candidate lists for camera rays (tiny scenes)
+};
+
 struct Scene {
     uint64_t magic = kSceneMagic;
     int device = 0;
@@ -25,7 +40,7 @@ struct Scene {
     float background[3] = {0.f, 0.f, 0.f};
     float build_ms = 0.f;
     int pipeline = 0;              // 0 auto (wavefront when it can hold the scene), 1 persistent lane-per-path, 2 CTA-local wavefront
-    int wf_tune[9] = {0, 1, 1, 1, 4, 3, 32, 4, 24};   // wavefront: vote weights NODE/LEAF/SHADE/END, NODE steps per batch, keep threshold / 8, full-warp columns, sticky repeats, tail-mode column sum
+    WfTune wf;                     // scheduling constants of the wavefront kernel (measured defaults)
     bool count_enabled = false;
     int sched[5] = {1, 1, 1, 1, 20};   // render-kernel stage weights (NODE, LEAF, SHADE, END) and NODE fast-path lane count
 
@@ -62,7 +77,6 @@ struct Scene {
     float4* d_stage_accum = nullptr;            // pt_launch_host staging
     uchar4* d_stage_frame = nullptr;
     size_t stage_pixels = 0;
-    void* d_wf_state = nullptr;                 // unused
 
     // work order of the render kernels (render.cu tile_order_update): this rank's tiles, those a camera ray can hit
     // the scene through first.  Rebuilt when the key (image size, camera, partition) changes.
@@ -72,7 +86,6 @@ struct Scene {
     uint32_t tile_order_count = 0;
     float tile_order_key[16] = {-1.f};
     bool tile_order_enabled = true;
-    bool shortlist_enabled = true;     // per-pixel candidate lists for camera rays (wavefront.cu pixel_candidates)
 
     // last launch
     uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0;

@@ -424,8 +424,7 @@ static inline float3 to3(const pt_float3& v) { return make_float3(v.x, v.y, v.z)
 static const uint32_t* tile_order_update(Scene& s, const pt_params& p, uint32_t rank, uint32_t n_ranks, uint32_t owned,
                                          cudaStream_t stream)
 {
-    static const bool env_off = getenv("PTB_TILE_ORDER") && atoi(getenv("PTB_TILE_ORDER")) == 0;   // A/B experiments
-    if (env_off || !s.tile_order_enabled || s.n_tris == 0 || owned == 0) return nullptr;
+    if (!s.tile_order_enabled || s.n_tris == 0 || owned == 0) return nullptr;
     const float key[16] = {(float)p.width, (float)p.height, (float)rank, (float)n_ranks, p.cameraEye.x, p.cameraEye.y,
                            p.cameraEye.z, p.cameraU.x, p.cameraU.y, p.cameraU.z, p.cameraV.x, p.cameraV.y, p.cameraV.z,
                            p.cameraW.x, p.cameraW.y, p.cameraW.z};
@@ -595,11 +594,6 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.work_counter = s.d_work_counter;
     lc.error_flag = s.d_counters + 15;
     for (int i = 0; i < 5; ++i) lc.sched[i] = s.sched[i];
-    if (const char* env = getenv("PTB_SCHED")) {   // tuning experiments: "w_node,w_leaf,w_shade,w_end,node_min"
-        int v[5];
-        if (sscanf(env, "%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4]) == 5)
-            for (int i = 0; i < 5; ++i) lc.sched[i] = v[i];
-    }
     bool probe = false;
     if (probe_overrides) {
         lc.dbg_seed_after_jitter = probe_overrides->dbg_seed_after_jitter;

@@ -28,6 +28,9 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <string>
 
 #include "pt_scene.h"
 #include "pt_shade.cuh"
@@ -46,7 +49,6 @@ constexpr size_t kMaxSmem = 227 * 1024;
 
 enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3, ST_PIXEL = 4, ST_TAIL = 5 };   // 0..4 have queues; TAIL serves NODE + LEAF
 constexpr int kQueues = 5;
-constexpr int kMissLoop = 16;                     // samples of an all-miss pixel finished per END visit
 constexpr uint32_t kCandNone = 0xffffffffu;       // per-pixel candidate list: no triangle can be hit by a camera ray
 constexpr uint32_t kCandOverflow = 0xfffffffeu;   // more than 4 candidates (or lists disabled): traverse the BVH
 enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3, MODE_NEWPIX = 4 };
@@ -61,6 +63,7 @@ struct WfConst {
     int sticky;              // repeats of the same stage without a full vote while it fills the whole warp
     int tail_cols;           // tail mode when the non-empty columns of all four queues add up to at most this
     int miss_loop;           // samples of an all-miss pixel finished per END visit
+    int block_override;      // host only: threads per CTA when set by PTB_TUNE
 };
 
 struct ThreadCounters {
@@ -605,7 +608,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 const uint32_t cand = (SHORT && need_sample) ? CAND[pid] : kCandOverflow;
                 if (SHORT && cand == kCandNone) {
                     // No triangle can be reached from this pixel: every camera ray is a miss.  Finish up to
-                    // kMissLoop samples right here, each exactly as the miss branch above does (:833-847, :760-772):
+                    // wc.miss_loop samples right here, each exactly as the miss branch above does (:833-847, :760-772):
                     // background times attenuation 1, the Russian-roulette draw, next sample.  Background tiles are
                     // handed out together (tile order), so the lanes of a batch take this loop together.
                     for (int rep = 0; rep < wc.miss_loop && left > 1u; ++rep) {
@@ -709,10 +712,7 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
     uint32_t block = SCENE >= 0 ? ((wc.np * 3u / 4u) & ~31u) : (wc.np & ~31u);
     if (block > (uint32_t)kWfBlock) block = kWfBlock;
     if (block < 128u) block = 128u;
-    if (const char* env = getenv("PTB_WF_BLOCK")) {
-        const long b = atol(env);
-        if (b >= 32 && b <= kWfBlock && b % 32 == 0) block = (uint32_t)b;
-    }
+    if (wc.block_override >= 32 && wc.block_override <= kWfBlock && wc.block_override % 32 == 0) block = (uint32_t)wc.block_override;
     kernel<<<grid, block, smem_bytes, stream>>>(lc, wc);
     s.last_grid = grid;
     s.last_block = block;
@@ -724,7 +724,7 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
 }  // namespace
 
 // Can the wavefront pipeline hold this scene?  Fills the launch layout when it can.
-static bool wavefront_plan(const Scene& s, WfConst& wc, size_t& smem_bytes, bool& smem_scene)
+static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size_t& smem_bytes, bool& smem_scene)
 {
     if (s.n_mats > 0xffffu) return false;                 // material id is packed into 16 bits of the path record
     const uint32_t depth = s.bvh_depth + 1u;              // deferred children never exceed the tree depth
@@ -738,6 +738,7 @@ static bool wavefront_plan(const Scene& s, WfConst& wc, size_t& smem_bytes, bool
         if (s.n_tris == 0 || scene_bytes + fixed + 512 * per_path > kMaxSmem) continue;
         uint32_t P = (uint32_t)((kMaxSmem - fixed - scene_bytes) / (32 * per_path));
         if (P > 32) P = 32;
+        if (tune.paths32 >= 1 && (uint32_t)tune.paths32 < P) P = (uint32_t)tune.paths32;
         wc.np = 32 * P;
         wc.stack_depth = depth;
         wc.copies_shift = (uint32_t)shift;
@@ -747,14 +748,11 @@ static bool wavefront_plan(const Scene& s, WfConst& wc, size_t& smem_bytes, bool
     }
     // global-memory scene: node/triangle records come through L1/L2; the paths take most of the shared memory
     // (batch occupancy needs many more paths than threads) and the rest stays L1
-    size_t budget = 200 * 1024;
-    if (const char* env = getenv("PTB_WF_SMEM_KB")) {
-        const long kb = atol(env);
-        if (kb >= 32 && kb <= 227) budget = (size_t)kb * 1024;
-    }
+    const size_t budget = (size_t)(tune.smem_kb >= 32 && tune.smem_kb <= 227 ? tune.smem_kb : 200) * 1024;
     uint32_t P = (uint32_t)((budget - fixed) / (32 * per_path));
     if (P > 32) P = 32;
-    if (P < 4) return false;
+    if (tune.paths32 >= 1 && (uint32_t)tune.paths32 < P) P = (uint32_t)tune.paths32;
+    if (P < 4 && tune.paths32 < 1) return false;
     wc.np = 32 * P;
     wc.stack_depth = depth;
     wc.copies_shift = 0;
@@ -768,46 +766,59 @@ bool wavefront_supported(const Scene& s)
     WfConst wc;
     size_t b;
     bool ss;
-    return wavefront_plan(s, wc, b, ss);
+    return wavefront_plan(s, s.wf, wc, b, ss);
+}
+
+// PTB_TUNE="node_votes=6,tail_cols=40,..." -- experiment overrides of WfTune, read once per process.
+static WfTune tuned(const WfTune& base)
+{
+    WfTune t = base;
+    const char* env = getenv("PTB_TUNE");
+    if (!env) return t;
+    struct Key {
+        const char* name;
+        int WfTune::*field;
+    };
+    static const Key keys[] = {{"node_votes", &WfTune::node_votes}, {"node_keep8", &WfTune::node_keep8},
+                               {"full_cols", &WfTune::full_cols},   {"sticky", &WfTune::sticky},
+                               {"tail_cols", &WfTune::tail_cols},   {"miss_loop", &WfTune::miss_loop},
+                               {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
+                               {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist}};
+    std::string str(env);
+    size_t pos = 0;
+    while (pos < str.size()) {
+        size_t end = str.find(',', pos);
+        if (end == std::string::npos) end = str.size();
+        const std::string item = str.substr(pos, end - pos);
+        const size_t eq = item.find('=');
+        if (eq != std::string::npos)
+            for (const Key& k : keys)
+                if (item.compare(0, eq, k.name) == 0 && eq == strlen(k.name)) t.*(k.field) = atoi(item.c_str() + eq + 1);
+        pos = end + 1;
+    }
+    return t;
 }
 
 cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaStream_t stream)
 {
+    const WfTune tune = tuned(s.wf);
     WfConst wc = {};
     size_t smem_bytes = 0;
     bool smem_scene = false;
-    if (!wavefront_plan(s, wc, smem_bytes, smem_scene)) return cudaErrorInvalidConfiguration;
-    wc.node_steps = s.wf_tune[4];
-    wc.node_keep8 = s.wf_tune[5];
-    wc.full_cols = s.wf_tune[6];
-    wc.sticky = s.wf_tune[7];
-    wc.tail_cols = s.wf_tune[8];
-    wc.miss_loop = kMissLoop;
-    if (const char* tc = getenv("PTB_WF_TAIL")) wc.tail_cols = atoi(tc);
-    if (const char* ml = getenv("PTB_WF_MISSLOOP")) wc.miss_loop = atoi(ml);
-    if (const char* env = getenv("PTB_WF")) {   // tuning experiments: "w_node,w_leaf,w_shade,w_end,K,keep8[,P[,full_cols]]" (P = 0: default)
-        int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        const int n = sscanf(env, "%d,%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8]);
-        if (n >= 8 && v[7] >= 1 && v[7] <= 32) wc.full_cols = v[7];
-        if (n >= 9 && v[8] >= 0) wc.sticky = v[8];
-
-        if (n >= 6) {
-            wc.node_steps = v[4];
-            wc.node_keep8 = v[5];
-        }
-        if (n >= 7 && v[6] >= 1 && (uint32_t)v[6] * 32u < wc.np) {
-            const size_t per_path = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)wc.stack_depth;
-            smem_bytes -= (wc.np - 32u * v[6]) * per_path;
-            wc.np = 32u * v[6];
-        }
-    }
+    if (!wavefront_plan(s, tune, wc, smem_bytes, smem_scene)) return cudaErrorInvalidConfiguration;
+    wc.node_steps = tune.node_votes;
+    wc.node_keep8 = tune.node_keep8;
+    wc.full_cols = tune.full_cols;
+    wc.sticky = tune.sticky;
+    wc.tail_cols = tune.tail_cols;
+    wc.miss_loop = tune.miss_loop;
+    wc.block_override = tune.block;
     const bool count = s.count_enabled;
     const int scene = smem_scene ? (int)wc.copies_shift : -1;
     // Per-pixel candidate lists for camera rays: only where building one (a loop over all triangles per pixel) is
     // cheap, i.e. tiny scenes staged with 8 copies.  The counted kernel always traverses, so that its node / triangle
     // counters stay the ones of the specified traversal (and equal to the oracle's).
-    static const bool short_off = getenv("PTB_WF_SHORT") && atoi(getenv("PTB_WF_SHORT")) == 0;   // A/B experiments
-    const bool use_short = scene == 3 && s.n_tris <= 64 && s.shortlist_enabled && !short_off;
+    const bool use_short = scene == 3 && s.n_tris <= 64 && tune.shortlist != 0;
 #define PTB_WF_DISPATCH(COUNT, PROBE, SHORT)                                                      \
     (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT>(s, lc, wc, smem_bytes, stream)       \
      : scene == 0 ? launch_wavefront<COUNT, PROBE, 0, false>(s, lc, wc, smem_bytes, stream)       \

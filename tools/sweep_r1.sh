@@ -1,5 +1,6 @@
-cd /root/repo
-run() { echo "== PTB_WF=$1"; PTB_WF=$1 timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+# usage: bash tools/sweep_r1.sh "node_votes=6,tail_cols=40" "shortlist=0" ...   (one bench run per PTB_TUNE string)
+cd "$(dirname "$0")/.."
+run() { echo "== PTB_TUNE=$1"; PTB_TUNE=$1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline ${BENCH_ARGS:-} 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
