@@ -580,3 +580,61 @@ def test_render_matches_oracle_for_other_cameras(api, port, scenes_cache, cam):
         gprim, oprobe = gs.debug_primary(pp), osc.render(pp, math_mode=1, use_bvh=True, probes=True)
         assert np.array_equal(gprim["prim"], oprobe["prim"])
         assert np.array_equal(gprim["t"].view(np.uint32), oprobe["t"].view(np.uint32))
+
+
+# ---- random triangle soups x random cameras: the candidate lists must stay a superset of what a camera ray can hit -----
+def _random_soup(rng, n_tri):
+    """Triangles of very different shapes inside the Cornell box volume: big, tiny, slivers, edge-on, shared vertices."""
+    verts, faces = [], []
+    for k in range(n_tri):
+        c = rng.uniform([0, 0, 0], [556, 548, 559])
+        kind = k % 5
+        if kind == 0:                                   # big
+            e1, e2 = rng.normal(size=3) * 250, rng.normal(size=3) * 250
+        elif kind == 1:                                 # tiny
+            e1, e2 = rng.normal(size=3) * 2, rng.normal(size=3) * 2
+        elif kind == 2:                                 # sliver
+            e1 = rng.normal(size=3) * 300
+            e2 = e1 * rng.uniform(0.2, 0.9) + rng.normal(size=3) * 0.5
+        elif kind == 3:                                 # axis-aligned quad half, like the box walls
+            a = rng.integers(0, 3)
+            e1, e2 = np.zeros(3), np.zeros(3)
+            e1[(a + 1) % 3], e2[(a + 2) % 3] = rng.uniform(50, 400), rng.uniform(50, 400)
+        else:                                           # medium
+            e1, e2 = rng.normal(size=3) * 60, rng.normal(size=3) * 60
+        base = len(verts)
+        verts += [c, c + e1, c + e2]
+        faces.append((base, base + 1, base + 2))
+    v = np.ones((len(verts), 4), np.float32)
+    v[:, :3] = np.asarray(verts, np.float32)
+    mats = [dict(name="white", Kd=(0.8, 0.8, 0.8), Ke=(0, 0, 0)), dict(name="glow", Kd=(0.7, 0.6, 0.5), Ke=(4, 3, 2)),
+            dict(name="MetallicThing", Kd=(0.9, 0.8, 0.7), Ke=(0, 0, 0)), dict(name="RefractiveThing", Kd=(1, 1, 1), Ke=(0, 0, 0), Ni=1.5)]
+    mat_ids = rng.integers(0, len(mats), n_tri).astype(np.uint32)
+    return S.SceneArrays(verts=v, indices=np.asarray(faces, np.uint32), mat_ids=mat_ids, materials=mats, name="soup")
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_soups_and_cameras(api, port, seed):
+    rng = np.random.default_rng(100 + seed)
+    n_tri = int(rng.choice([1, 2, 7, 31, 48, 64, 65, 200]))          # <= 64: candidate lists on; above: traversal only
+    arr = _random_soup(rng, n_tri)
+    gs, osc = api.Scene(arr), O.OracleScene(port, arr)
+    try:
+        for view in range(3):
+            eye = rng.uniform([-300, -100, -900], [850, 700, 800])
+            lookat = rng.uniform([100, 100, 100], [450, 450, 450])
+            up = rng.normal(size=3)
+            fovy = float(rng.uniform(10, 110))
+            w, h = int(rng.integers(9, 120)), int(rng.integers(9, 80))
+            pp = _with_camera(api, api.make_params(w, h, 3, 4, frame=view, scene=gs), eye, lookat, up, fovy)
+            g, o = gs.debug_primary(pp), osc.render(pp, math_mode=1, use_bvh=True, probes=True)
+            assert np.array_equal(g["prim"], o["prim"]), (seed, view)
+            assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32)), (seed, view)
+            p = _with_camera(api, api.make_params(w, h, 5, 9, frame=view, nee=True, importance=bool(view & 1), scene=gs),
+                             eye, lookat, up, fovy)
+            gr, orr = gs.launch_host(p), osc.render(p, math_mode=1, use_bvh=True)
+            # (frames > 0 fold into a zero previous accumulation on both sides)
+            assert np.array_equal(gr["accum"].view(np.uint32), orr["accum"].view(np.uint32)), (seed, view)
+            assert np.array_equal(gr["fb"], orr["fb"]), (seed, view)
+    finally:
+        gs.destroy()
