@@ -52,6 +52,9 @@ def _load():
         "pt_scene_get_counters": (i32, [vp, C.POINTER(Counters), i32]),
         "pt_scene_get_sched_stats": (i32, [vp, C.POINTER(u64), i32]),
         "pt_scene_set_pipeline": (i32, [vp, i32]),
+        "pt_scene_set_traversal": (i32, [vp, i32]),
+        "pt_scene_last_traversal": (i32, [vp]),
+        "pt_bvh_export_wide": (i32, [vp, C.POINTER(u32), vp, vp]),
         "pt_scene_last_launch_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "pt_bvh_export": (i32, [vp] * 8),
         "pt_trace_rays": (i32, [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]),
@@ -213,10 +216,24 @@ class Scene:
     def set_pipeline(self, pipeline):
         _check(lib.pt_scene_set_pipeline(self._h, pipeline))
 
+    def set_traversal(self, traversal):
+        """0 auto, 1 binary LBVH, 2 wide nodes (pt_scene_set_traversal)."""
+        _check(lib.pt_scene_set_traversal(self._h, traversal))
+
     def last_launch_info(self):
         g, b, s, k = (C.c_uint32() for _ in range(4))
         _check(lib.pt_scene_last_launch_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(k)))
-        return dict(grid=g.value, block=b.value, smem_bytes=s.value, kernels=k.value)
+        return dict(grid=g.value, block=b.value, smem_bytes=s.value, kernels=k.value,
+                    traversal={0: "binary", 1: "wide", 2: "binary-coop"}.get(lib.pt_scene_last_traversal(self._h), "?"))
+
+    def bvh_export_wide(self):
+        """Wide nodes (two LBVH levels per 128-byte record): dict(n_wide, wide_index[n_nodes], wnodes[n_wide, 32] u32)."""
+        n = C.c_uint32()
+        _check(lib.pt_bvh_export_wide(self._h, C.byref(n), None, None))
+        idx = np.zeros(self.info()["n_nodes"], np.uint32)
+        wn = np.zeros((n.value, 32), np.uint32)
+        _check(lib.pt_bvh_export_wide(self._h, C.byref(n), _ptr(idx), _ptr(wn)))
+        return dict(n_wide=n.value, wide_index=idx, wnodes=wn)
 
     def bvh_export(self):
         info = self.info()

@@ -72,7 +72,7 @@ static void scene_free(Scene* s)
     void* ptrs[] = {s->d_verts, s->d_indices, s->d_mat_ids, s->d_mats, s->d_tri_in, s->d_tri_bb, s->d_tri_shade,
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
-                    s->d_node_hi, s->d_nodes, s->d_tris, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
+                    s->d_node_hi, s->d_nodes, s->d_tris, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
                     s->d_tile_order};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -156,7 +156,8 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
     A(dev_alloc(&s->d_right, n));
     A(dev_alloc(&s->d_node_parent, n));
     A(dev_alloc(&s->d_leaf_parent, n));
-    A(dev_alloc(&s->d_visit, n));
+    A(dev_alloc(&s->d_visit, n + 1));
+    A(dev_alloc(&s->d_wide_index, n + 1));
     A(dev_alloc(&s->d_node_lo, n));
     A(dev_alloc(&s->d_node_hi, n));
     A(dev_alloc(&s->d_nodes, 4 * (size_t)(s->n_nodes ? s->n_nodes : 1)));
@@ -194,9 +195,22 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
     if (e == cudaSuccess) {
         A(cudaEventRecord(e0, stream));
         A(lbvh_build(*s, stream));
+        A(wide_count(*s, stream));
         A(cudaEventRecord(e1, stream));
         A(cudaStreamSynchronize(stream));
         if (e == cudaSuccess) cudaEventElapsedTime(&s->build_ms, e0, e1);
+        // wide nodes: the count is known only now; one more kernel writes the records
+        if (e == cudaSuccess && n) A(cudaMemcpy(&s->n_wide, s->d_wide_index + s->n_nodes, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (e == cudaSuccess && n) {
+            A(dev_alloc(&s->d_wnodes, 8 * (size_t)s->n_wide));
+            A(cudaEventRecord(e0, stream));
+            A(wide_emit(*s, stream));
+            A(cudaEventRecord(e1, stream));
+            A(cudaStreamSynchronize(stream));
+            float ms = 0.f;
+            if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+            s->build_ms += ms;
+        }
         if (e == cudaSuccess && n) A(cudaMemcpy(&s->bvh_depth, s->d_work_counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (e == cudaSuccess && n) A(cudaMemcpy(s->h_bounds, s->d_bounds, 6 * sizeof(float), cudaMemcpyDeviceToHost));
     }
@@ -400,6 +414,32 @@ int pt_scene_set_pipeline(pt_scene* scene, int pipeline)
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
     if (pipeline < 0 || pipeline > 2) return fail(PT_ERR_INVALID, "pipeline must be 0, 1 or 2");
     s->pipeline = pipeline;
+    return PT_OK;
+}
+
+int pt_scene_set_traversal(pt_scene* scene, int traversal)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    if (traversal < 0 || traversal > 3) return fail(PT_ERR_INVALID, "traversal must be 0, 1, 2 or 3");
+    s->traversal = traversal;
+    return PT_OK;
+}
+
+int pt_scene_last_traversal(const pt_scene* scene)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    return s ? (int)s->last_wide : -1;
+}
+
+int pt_bvh_export_wide(const pt_scene* scene, uint32_t* n_wide, uint32_t* wide_index, void* wnodes128)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    DeviceGuard g(s->device);
+    if (n_wide) *n_wide = s->n_wide;
+    if (wide_index && s->n_nodes) PT_CUDA(cudaMemcpy(wide_index, s->d_wide_index, sizeof(uint32_t) * s->n_nodes, cudaMemcpyDeviceToHost));
+    if (wnodes128 && s->n_wide) PT_CUDA(cudaMemcpy(wnodes128, s->d_wnodes, 128 * (size_t)s->n_wide, cudaMemcpyDeviceToHost));
     return PT_OK;
 }
 

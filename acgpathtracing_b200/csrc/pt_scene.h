@@ -30,6 +30,8 @@ struct WfTune {
     int block = 0;           // threads per CTA (0 = derived from the paths)
     int smem_kb = 200;       // shared-memory budget for the paths when the scene is read from global memory
     int shortlist = 1;       // per-pixel candidate lists for camera rays (tiny scenes)
+    int wide = -1;           // -1: follow Scene::traversal; 0 / 1: binary / wide nodes for scenes in global memory
+    int coop = -1;           // -1 / 1: warp-cooperative fetch of the binary nodes of a scene in global memory; 0: per lane
 };
 
 struct Scene {
@@ -70,6 +72,10 @@ struct Scene {
     float4* d_node_hi = nullptr;
     float4* d_nodes = nullptr;        // 4 per node
     float4* d_tris = nullptr;         // 3 per leaf (leaf order)
+    uint32_t* d_wide_index = nullptr; // per binary node: index of the wide node rooted there (lbvh.cu wide_count)
+    float4* d_wnodes = nullptr;       // wide nodes, 8 per node (two binary levels per record)
+    uint32_t n_wide = 0;
+    int traversal = 0;                // pt_scene_set_traversal: 0 auto, 1 binary per lane, 2 wide (global), 3 binary cooperative (global)
 
     // launch-time scratch
     uint32_t* d_work_counter = nullptr;         // [0] pixel fetch counter  [1] LBVH depth (build)
@@ -88,11 +94,13 @@ struct Scene {
     bool tile_order_enabled = true;
 
     // last launch
-    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0;
+    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_wide = 0;   // last_wide: 0 binary per lane, 1 wide nodes, 2 binary cooperative
 };
 
 // lbvh.cu
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
+cudaError_t wide_count(Scene& s, cudaStream_t stream);
+cudaError_t wide_emit(Scene& s, cudaStream_t stream);
 
 // render.cu
 constexpr uint32_t kMaxFoldFrames = 64;

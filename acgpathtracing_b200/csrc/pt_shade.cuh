@@ -31,6 +31,7 @@ struct LaunchConst {   // everything a launch needs, passed by value as a kernel
     uchar4* frame_buffer;         // may be null
     // scene (global memory; kernels may stage it into shared memory)
     BvhView bvh;
+    const float4* wnodes;         // wide nodes (lbvh.cu wide_emit_kernel), 8 float4 each
     uint32_t n_nodes, n_mats;
     const float4* tri_shade;      // per primitive: (N_0.xyz, material id)
     const DevMaterial* mats;      // 3 x float4 per material

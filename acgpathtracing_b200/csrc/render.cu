@@ -580,6 +580,7 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.accum = (float4*)params.accumulationBuffer;
     lc.frame_buffer = raw_mean ? nullptr : (uchar4*)params.frameBuffer;
     lc.bvh = BvhView{s.d_nodes, s.d_tris, s.n_tris};
+    lc.wnodes = s.d_wnodes;
     lc.n_nodes = s.n_nodes;
     lc.n_mats = s.n_mats;
     lc.tri_shade = s.d_tri_shade;
@@ -609,6 +610,7 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     // pipeline 2 (wavefront.cu) whenever it can hold the scene, unless pipeline 1 was asked for
     if (s.pipeline != 1 && wavefront_supported(s)) return wavefront_launch(s, lc, probe, stream);
     if (s.pipeline == 2) return cudaErrorInvalidConfiguration;
+    s.last_wide = 0;
 
     const size_t staged = staged_scene_float4s(s.n_nodes, s.n_tris, s.n_mats) * sizeof(float4);
     const bool smem = s.n_tris > 0 && staged <= kSmemSceneLimit;

@@ -178,7 +178,15 @@ __device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, cons
     return cand;
 }
 
-template <bool COUNT, bool PROBE, int SCENE, bool SHORT>
+// TRAV (scenes in global memory only; 0 elsewhere): how NODE batches read the tree.
+//   TRAV_DIRECT  every lane reads its own 64-byte LBVH node (LDG.128 x4)
+//   TRAV_COOP    the warp reads its 32 nodes cooperatively, four lanes per record, and transposes through a per-warp
+//                staging buffer (pt_device.cuh coop_fetch64): 8 lines per instruction instead of 32
+//   TRAV_WIDE    wide nodes -- four child boxes, two LBVH levels, per 128-byte record (trav_wide_step)
+enum : int { TRAV_DIRECT = 0, TRAV_WIDE = 1, TRAV_COOP = 2 };
+constexpr int kStageF4 = 128;          // float4s of staging per warp (TRAV_COOP)
+
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV>
 __global__ void __launch_bounds__(kWfBlock, 1)
 render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_constant__ WfConst wc)
 {
@@ -198,13 +206,15 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     float4* S1 = S0 + NP;               // (next ray direction, add.y)
     uint32_t* CAND = reinterpret_cast<uint32_t*>(S1 + NP);          // per pixel: up to 4 leaves a camera ray can hit
     int* stack_mem = reinterpret_cast<int*>(CAND + NP);             // [stack_depth][NP]
-    float4* scene = reinterpret_cast<float4*>(stack_mem + (size_t)wc.stack_depth * NP);
+    float4* scene = reinterpret_cast<float4*>(stack_mem + (size_t)wc.stack_depth * NP);   // staged scene, or staging (TRAV_COOP)
+    constexpr bool WIDE = TRAV == TRAV_WIDE;
 
     typename WfFetch<SCENE>::type f;
     f.nodes = lc.bvh.nodes;
     f.tris = lc.bvh.tris;
     f.shade = lc.tri_shade;
     f.mats = reinterpret_cast<const float4*>(lc.mats);
+    if constexpr (SCENE < 0) f.wnodes = lc.wnodes;
     if (SCENE >= 0) {
         const uint32_t shift = SCENE >= 0 ? (uint32_t)SCENE : 0u, copies = 1u << shift;
         const uint32_t n_nodes4 = 4 * lc.n_nodes, n_tris4 = 3 * lc.bvh.n_tris, n_sh = lc.bvh.n_tris, n_m4 = 3 * lc.n_mats;
@@ -346,7 +356,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 if (__popc(bn) >= __popc(bl)) {
                     if (at_node) {
                         if (COUNT) ctr.n_node++;
-                        trav_node_step(t, stack, f, 0.01f);
+                        if constexpr (WIDE) trav_wide_step(t, stack, f, 0.01f);
+                        else trav_node_step(t, stack, f, 0.01f);
                     }
                 } else if (at_leaf) {
                     if (COUNT) ctr.n_tri++;
@@ -389,13 +400,30 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 const int n = __popc(__ballot_sync(kFull, at));
                 if (n == 0 || n * 8 < n0 * wc.node_keep8) break;
                 if (COUNT) st_steps++, st_step_lanes += n;
-                if (at) {
-                    if (COUNT) ctr.n_node++;
-                    trav_node_step(t, stack, f, 0.01f);                          // tmin :754
-                }
-                if (t.cur >= 0) {                                                // second step under the same vote
-                    if (COUNT) ctr.n_node++;
-                    trav_node_step(t, stack, f, 0.01f);
+                if constexpr (TRAV == TRAV_COOP) {
+                    float4 q0, q1, q2, q3;
+                    coop_fetch64(f.nodes, t.cur, scene + warp * kStageF4, lane, q0, q1, q2, q3);
+                    if (at) {
+                        if (COUNT) ctr.n_node++;
+                        trav_node_apply(t, stack, f, 0.01f, q0, q1, q2, q3);
+                    }
+                    if (__any_sync(kFull, t.cur >= 0)) {                         // second step under the same vote
+                        coop_fetch64(f.nodes, t.cur, scene + warp * kStageF4, lane, q0, q1, q2, q3);
+                        if (t.cur >= 0) {
+                            if (COUNT) ctr.n_node++;
+                            trav_node_apply(t, stack, f, 0.01f, q0, q1, q2, q3);
+                        }
+                    }
+                } else {
+                    if (at) {
+                        if (COUNT) ctr.n_node++;
+                        if constexpr (WIDE) trav_wide_step(t, stack, f, 0.01f);
+                        else trav_node_step(t, stack, f, 0.01f);                 // tmin :754
+                    }
+                    if (!WIDE && t.cur >= 0) {                                   // second step under the same vote
+                        if (COUNT) ctr.n_node++;
+                        trav_node_step(t, stack, f, 0.01f);
+                    }
                 }
             }
             if (active) {
@@ -690,10 +718,10 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     if (threadIdx.x == 0 && vol_ld(ctl + 1)) atomicAdd(lc.error_flag, 1ull);   // watchdog fired
 }
 
-template <bool COUNT, bool PROBE, int SCENE, bool SHORT>
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV>
 cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc, size_t smem_bytes, cudaStream_t stream)
 {
-    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE, SHORT>;
+    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE, SHORT, TRAV>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -723,19 +751,34 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
 
 }  // namespace
 
+// How NODE batches read a scene that stays in global memory (pt_scene_set_traversal; PTB_TUNE wide= / coop= override).
+// Measured on B200 (gpurun wide1/wide2 logs): per-lane fetch of the binary LBVH is the fastest on C3 and
+// C4 (the upper levels are L1/L2-hot, where LDG.128 x4 per lane costs nothing extra); the cooperative fetch wins only
+// for DRAM-cold records (tools/fetchbench.cu) and wide nodes pay for their 128-byte per-lane fetch.  Both stay
+// selectable and bit-identical.
+static int choose_trav(const Scene& s, const WfTune& tune)
+{
+    const bool can_wide = s.n_wide != 0 && !s.count_enabled;   // the counted kernel walks the binary LBVH: its counters are the spec's
+    const bool wide = can_wide && (tune.wide >= 0 ? tune.wide != 0 : s.traversal == 2);
+    if (wide) return TRAV_WIDE;
+    return (tune.coop >= 0 ? tune.coop != 0 : s.traversal == 3) ? TRAV_COOP : TRAV_DIRECT;
+}
+
 // Can the wavefront pipeline hold this scene?  Fills the launch layout when it can.
-static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size_t& smem_bytes, bool& smem_scene)
+static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size_t& smem_bytes, bool& smem_scene, int& trav)
 {
     if (s.n_mats > 0xffffu) return false;                 // material id is packed into 16 bits of the path record
-    const uint32_t depth = s.bvh_depth + 1u;              // deferred children never exceed the tree depth
+    uint32_t depth = s.bvh_depth + 1u;                    // deferred children never exceed the tree depth
     if (depth > 255u) return false;
+    trav = TRAV_DIRECT;
+    const bool force_global = (s.traversal == 2 && !s.count_enabled && s.n_wide != 0) || s.traversal == 3;
     const size_t scene_f4 = 4 * (size_t)s.n_nodes + 4 * (size_t)s.n_tris + 3 * (size_t)s.n_mats;
     const size_t fixed = (size_t)kCtlF4 * 16;
     const size_t per_path = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;   // state, candidate word, stack
     // scene copies: 8 if the paths still get >= 512 slots, else 1; larger scenes stay in global memory
     for (int shift = 3; shift >= 0; shift -= 3) {
         const size_t scene_bytes = (scene_f4 * 16) << shift;
-        if (s.n_tris == 0 || scene_bytes + fixed + 512 * per_path > kMaxSmem) continue;
+        if (s.n_tris == 0 || force_global || scene_bytes + fixed + 512 * per_path > kMaxSmem) continue;
         uint32_t P = (uint32_t)((kMaxSmem - fixed - scene_bytes) / (32 * per_path));
         if (P > 32) P = 32;
         if (tune.paths32 >= 1 && (uint32_t)tune.paths32 < P) P = (uint32_t)tune.paths32;
@@ -748,15 +791,24 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
     }
     // global-memory scene: node/triangle records come through L1/L2; the paths take most of the shared memory
     // (batch occupancy needs many more paths than threads) and the rest stays L1
+    trav = choose_trav(s, tune);
+    // a wide step defers up to 3 children per wide level (two binary levels)
+    if (trav == TRAV_WIDE) depth = 3u * ((s.bvh_depth + 1u) / 2u) + 1u;
+    if (depth > 255u) {
+        trav = TRAV_DIRECT;
+        depth = s.bvh_depth + 1u;
+    }
+    const size_t per_path_g = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;
+    const size_t per_warp = trav == TRAV_COOP ? (size_t)kStageF4 * 16 : 0;   // staging buffer of the cooperative fetch
     const size_t budget = (size_t)(tune.smem_kb >= 32 && tune.smem_kb <= 227 ? tune.smem_kb : 200) * 1024;
-    uint32_t P = (uint32_t)((budget - fixed) / (32 * per_path));
+    uint32_t P = (uint32_t)((budget - fixed) / (32 * per_path_g + per_warp));
     if (P > 32) P = 32;
     if (tune.paths32 >= 1 && (uint32_t)tune.paths32 < P) P = (uint32_t)tune.paths32;
     if (P < 4 && tune.paths32 < 1) return false;
     wc.np = 32 * P;
     wc.stack_depth = depth;
     wc.copies_shift = 0;
-    smem_bytes = fixed + wc.np * per_path;
+    smem_bytes = fixed + wc.np * per_path_g + (P < 24u ? P : 24u) * per_warp;
     smem_scene = false;
     return true;
 }
@@ -766,7 +818,8 @@ bool wavefront_supported(const Scene& s)
     WfConst wc;
     size_t b;
     bool ss;
-    return wavefront_plan(s, s.wf, wc, b, ss);
+    int trav;
+    return wavefront_plan(s, s.wf, wc, b, ss, trav);
 }
 
 // PTB_TUNE="node_votes=6,tail_cols=40,..." -- experiment overrides of WfTune, read once per process.
@@ -783,7 +836,8 @@ static WfTune tuned(const WfTune& base)
                                {"full_cols", &WfTune::full_cols},   {"sticky", &WfTune::sticky},
                                {"tail_cols", &WfTune::tail_cols},   {"miss_loop", &WfTune::miss_loop},
                                {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
-                               {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist}};
+                               {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
+                               {"wide", &WfTune::wide},             {"coop", &WfTune::coop}};
     std::string str(env);
     size_t pos = 0;
     while (pos < str.size()) {
@@ -805,7 +859,8 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     WfConst wc = {};
     size_t smem_bytes = 0;
     bool smem_scene = false;
-    if (!wavefront_plan(s, tune, wc, smem_bytes, smem_scene)) return cudaErrorInvalidConfiguration;
+    int trav = TRAV_DIRECT;
+    if (!wavefront_plan(s, tune, wc, smem_bytes, smem_scene, trav)) return cudaErrorInvalidConfiguration;
     wc.node_steps = tune.node_votes;
     wc.node_keep8 = tune.node_keep8;
     wc.full_cols = tune.full_cols;
@@ -819,10 +874,22 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     // cheap, i.e. tiny scenes staged with 8 copies.  The counted kernel always traverses, so that its node / triangle
     // counters stay the ones of the specified traversal (and equal to the oracle's).
     const bool use_short = scene == 3 && s.n_tris <= 64 && tune.shortlist != 0;
+    s.last_wide = 0;
+    if (scene < 0 && trav == TRAV_WIDE) {
+        s.last_wide = 1;
+        return probe ? launch_wavefront<false, true, -1, false, TRAV_WIDE>(s, lc, wc, smem_bytes, stream)
+                     : launch_wavefront<false, false, -1, false, TRAV_WIDE>(s, lc, wc, smem_bytes, stream);
+    }
+    if (scene < 0 && trav == TRAV_COOP) {
+        s.last_wide = 2;
+        if (probe) return launch_wavefront<false, true, -1, false, TRAV_COOP>(s, lc, wc, smem_bytes, stream);
+        if (count) return launch_wavefront<true, false, -1, false, TRAV_COOP>(s, lc, wc, smem_bytes, stream);
+        return launch_wavefront<false, false, -1, false, TRAV_COOP>(s, lc, wc, smem_bytes, stream);
+    }
 #define PTB_WF_DISPATCH(COUNT, PROBE, SHORT)                                                      \
-    (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT>(s, lc, wc, smem_bytes, stream)       \
-     : scene == 0 ? launch_wavefront<COUNT, PROBE, 0, false>(s, lc, wc, smem_bytes, stream)       \
-                  : launch_wavefront<COUNT, PROBE, -1, false>(s, lc, wc, smem_bytes, stream))
+    (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream)   \
+     : scene == 0 ? launch_wavefront<COUNT, PROBE, 0, false, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream)   \
+                  : launch_wavefront<COUNT, PROBE, -1, false, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream))
     if (probe) return use_short ? PTB_WF_DISPATCH(false, true, true) : PTB_WF_DISPATCH(false, true, false);
     if (count) return PTB_WF_DISPATCH(true, false, false);
     return use_short ? PTB_WF_DISPATCH(false, false, true) : PTB_WF_DISPATCH(false, false, false);

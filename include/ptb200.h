@@ -123,6 +123,17 @@ int pt_scene_get_counters(pt_scene* scene, pt_counters* out, int reset);
 int pt_scene_get_sched_stats(pt_scene* scene, uint64_t* out16, int reset);
 /* kernel variant: 0 = auto, 1 = persistent thread-per-path, 2 = CTA-local wavefront */
 int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
+/* How the render kernel walks the acceleration structure:
+ *   0 = auto (= 1, the fastest measured on B200 for every BASELINE scene);
+ *   1 = binary LBVH, every lane fetches its own node (from shared memory when the scene fits);
+ *   2 = wide nodes (two LBVH levels per 128-byte record), scene read from global memory whatever its size;
+ *   3 = binary LBVH with a warp-cooperative node fetch (four lanes per 64-byte node, transposed through shared
+ *       memory), scene read from global memory whatever its size.
+ * The pixels do not depend on it: all variants cull with the LBVH's own boxes and every hit comes from the same
+ * triangle test (OptiX's acceleration structure, PathTracerMain.cpp:311-398, is closed). */
+int pt_scene_set_traversal(pt_scene* scene, int traversal);
+int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 binary LBVH, 1 wide nodes,
+                                                         2 binary LBVH with warp-cooperative node fetch */
 int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes,
                               uint32_t* kernels_launched);
 
@@ -132,6 +143,9 @@ int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* b
  * (leaf order); bounds: lo xyz, hi xyz. */
 int pt_bvh_export(const pt_scene* scene, uint32_t* morton, uint64_t* sorted_keys, uint32_t* sorted_prim,
                   int32_t* parent, void* nodes64, void* tris48, float* bounds6);
+/* Wide-node export; any pointer may be NULL.  wide_index[n_nodes]: exclusive count of wide-node roots among the
+ * binary nodes before i (= the wide node's index where binary node i is a root); wnodes: n_wide x 128 B. */
+int pt_bvh_export_wide(const pt_scene* scene, uint32_t* n_wide, uint32_t* wide_index, void* wnodes128);
 /* Batch ray queries through the device traversal kernels (host arrays in/out). */
 int pt_trace_rays(const pt_scene* scene, const float* org3, const float* dir3, const float* tmin, const float* tmax,
                   uint64_t n, int32_t* prim_out, float* t_out, uint8_t* any_out, uint64_t* counters2);

@@ -458,6 +458,15 @@ def test_full_size_c4_two_million_triangles(api, port):
         bp, bt, ba, _ = osc.trace(org[:96], d[:96], 0.01, 1e16, use_bvh=False, want_any=True)
         assert np.array_equal(gp[:96], bp) and np.array_equal(gt[:96].view(np.uint32), bt.view(np.uint32))
         _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432), pipelines=(0, 1))
+        assert gs.last_launch_info()["traversal"] == "binary"                     # pipeline 1 ran last
+        import torch
+        acc_c, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
+        assert gs.last_launch_info()["traversal"] == "binary"                     # auto
+        for trav, expect in ((3, "binary-coop"), (2, "wide")):
+            gs.set_traversal(trav)
+            acc_t, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
+            assert gs.last_launch_info()["traversal"] == expect
+            assert torch.equal(acc_t.view(torch.int32), acc_c.view(torch.int32))  # every pixel of the 1080p frame
     finally:
         gs.destroy()
 
@@ -638,3 +647,108 @@ def test_random_soups_and_cameras(api, port, seed):
             assert np.array_equal(gr["fb"], orr["fb"]), (seed, view)
     finally:
         gs.destroy()
+
+
+# ---- wide nodes (two LBVH levels per record): structure and pixels ------------------------------------------------
+def _wide_from_binary(nodes, parent):
+    """CPU statement of lbvh.cu wide_mark/wide_emit: binary nodes with an even number of ancestors become wide
+    nodes (numbered in binary-node order); children = grandchildren, or the child itself where it is a leaf."""
+    n = nodes.shape[0]
+    ni = nodes.view(np.int32)
+    depth = np.zeros(n, np.int64)
+    cur = parent.astype(np.int64).copy()
+    while (cur >= 0).any():
+        live = cur >= 0
+        depth[live] += 1
+        cur[live] = parent[cur[live]]
+    flag = (depth % 2 == 0).astype(np.uint32)
+    index = (np.cumsum(flag) - flag).astype(np.uint32)
+    out = np.zeros((int(flag.sum()), 32), np.uint32)
+    empty = np.zeros(8, np.uint32)
+    empty[3] = 0x80000000
+    for i in np.nonzero(flag)[0]:
+        slots = []
+        c = (int(ni[i, 3]), int(ni[i, 7]))
+        for s in range(2):
+            if s == 1 and c[1] == c[0]:
+                break
+            if c[s] < 0:
+                lo, hi = (nodes[i, 0:3], nodes[i, 4:7]) if s == 0 else (nodes[i, 8:11], nodes[i, 12:15])
+                slots.append((lo, hi, c[s]))
+            else:
+                r = c[s]
+                for lo, hi, g in ((nodes[r, 0:3], nodes[r, 4:7], int(ni[r, 3])), (nodes[r, 8:11], nodes[r, 12:15], int(ni[r, 7]))):
+                    slots.append((lo, hi, int(index[g]) if g >= 0 else g))
+        rec = out[index[i]]
+        for k in range(4):
+            if k < len(slots):
+                lo, hi, ch = slots[k]
+                rec[8 * k: 8 * k + 3] = lo
+                rec[8 * k + 3] = np.uint32(ch & 0xFFFFFFFF)
+                rec[8 * k + 4: 8 * k + 7] = hi
+            else:
+                rec[8 * k: 8 * k + 8] = empty
+    return index, out
+
+
+@pytest.mark.parametrize("name", ["cornell", "material", "tess40", "tess300"])
+def test_wide_nodes_bit_exact(api, port, scenes_cache, name):
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    b, w = gs.bvh_export(), gs.bvh_export_wide()
+    index, ref = _wide_from_binary(b["nodes"], b["parent"])
+    assert w["n_wide"] == ref.shape[0]
+    assert np.array_equal(w["wide_index"], index)
+    assert np.array_equal(w["wnodes"], ref)
+    # every leaf is referenced exactly once, every wide node but the root exactly once
+    ch = w["wnodes"].reshape(-1, 4, 8)[:, :, 3].view(np.int32).ravel()
+    ch = ch[ch != np.int32(-0x80000000)]
+    assert np.array_equal(np.sort(~ch[ch < 0]), np.arange(arr.n_tri))
+    assert np.array_equal(np.sort(ch[ch >= 0]), np.arange(1, w["n_wide"]))
+
+
+@pytest.mark.parametrize("name,w,h,spp,md", [("cornell", 160, 90, 6, 16), ("material", 200, 112, 6, 28), ("tess40", 160, 90, 4, 8),
+                                             ("tess300", 128, 72, 3, 8)])
+def test_wide_traversal_same_pixels(api, port, scenes_cache, name, w, h, spp, md):
+    """pt_scene_set_traversal: wide nodes and the warp-cooperative node fetch (both forced to global memory, also for
+    scenes that would be staged in shared memory), the per-lane binary LBVH and the oracle give the same primary hits
+    and the same pixels, bit for bit."""
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    p = api.make_params(w, h, spp, md, frame=1, nee=True, importance=True, scene=gs)
+    prev = np.random.default_rng(3).random((h, w, 4), dtype=np.float32)
+    o = osc.render(p, accum=prev.copy(), math_mode=1, use_bvh=True, probes=True)
+    try:
+        for trav, expect in ((2, "wide"), (3, "binary-coop"), (1, "binary")):
+            gs.set_traversal(trav)
+            g = gs.launch_host(p, accum=prev.copy())
+            assert gs.last_launch_info()["traversal"] == expect
+            assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), trav
+            assert np.array_equal(g["fb"], o["fb"]), trav
+            d = gs.debug_primary(p)
+            assert np.array_equal(d["prim"], o["prim"]) and np.array_equal(d["t"].view(np.uint32), o["t"].view(np.uint32))
+    finally:
+        gs.set_traversal(0)
+
+
+def test_wide_traversal_single_triangle_and_soups(api, port):
+    rng = np.random.default_rng(77)
+    for n_tri in (1, 2, 3, 5, 70, 333):
+        arr = _random_soup(rng, n_tri)
+        gs, osc = api.Scene(arr), O.OracleScene(port, arr)
+        try:
+            p = api.make_params(64, 40, 4, 6, frame=0, nee=True, scene=gs)
+            o = osc.render(p, math_mode=1, use_bvh=True)
+            for trav, expect in ((2, "wide"), (3, "binary-coop")):
+                gs.set_traversal(trav)
+                g = gs.launch_host(p)
+                assert gs.last_launch_info()["traversal"] == expect
+                assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (n_tri, trav)
+            # counted launches with the cooperative fetch report the binary traversal's work counters
+            gs.set_traversal(3)
+            gs.enable_counters(True)
+            gs.counters(reset=True)
+            g = gs.launch_host(p)
+            assert gs.last_launch_info()["traversal"] == "binary-coop"
+            assert gs.counters(reset=True) == o["counters"]
+            gs.enable_counters(False)
+        finally:
+            gs.destroy()
