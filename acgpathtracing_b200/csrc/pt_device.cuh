@@ -78,10 +78,25 @@ struct BvhView {
 //                    (e << SHIFT) + k and lane l reads copy l & (copies - 1).  With 8 copies the 8 lanes of every
 //                    quarter-warp hit 8 different 16-byte bank groups whatever elements they ask for, so a
 //                    divergent LDS.128 costs exactly its 4 data wavefronts.
+// 256-bit read-only load (LDG.E.256, sm_100+): one whole 32-byte sector per lane and instruction.  A divergent fetch of
+// 64-byte records costs half the L1 requests of LDG.128 x4 (tools/fetchbench.cu: +45-50 % records/s from L2, +22 % from
+// DRAM, never slower).  `p` must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
+{
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 struct FetchGlobal {
     const float4 *nodes, *tris, *shade, *mats;
     const float4* wnodes;   // wide nodes (8 float4 each), or null
-    __device__ __forceinline__ float4 wnode(int i, int q) const { return __ldg(wnodes + 8 * (size_t)i + q); }
+    __device__ __forceinline__ void node4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
+    {
+        ldg256(nodes + 4 * (size_t)i, q0, q1);
+        ldg256(nodes + 4 * (size_t)i + 2, q2, q3);
+    }
+    __device__ __forceinline__ void wnode2(int i, int k, float4& lo, float4& hi) const { ldg256(wnodes + 8 * (size_t)i + 2 * k, lo, hi); }
     __device__ __forceinline__ void prefetch_wide_child(int c) const
     {
         if (c >= 0) {
@@ -106,6 +121,10 @@ struct FetchGlobal {
 struct FetchShared {
     const float4 *nodes, *tris, *shade, *mats;
     __device__ __forceinline__ void prefetch_child(int) const {}
+    __device__ __forceinline__ void node4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
+    {
+        q0 = node(i, 0), q1 = node(i, 1), q2 = node(i, 2), q3 = node(i, 3);
+    }
     __device__ __forceinline__ float4 node(int i, int q) const { return nodes[4 * i + q]; }
     __device__ __forceinline__ float4 tri(int i, int q) const { return tris[3 * i + q]; }
     __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim]; }
@@ -115,6 +134,10 @@ template <int SHIFT>
 struct FetchSharedBanked {
     const float4 *nodes, *tris, *shade, *mats;   // each already offset by this lane's copy index
     __device__ __forceinline__ void prefetch_child(int) const {}
+    __device__ __forceinline__ void node4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
+    {
+        q0 = node(i, 0), q1 = node(i, 1), q2 = node(i, 2), q3 = node(i, 3);
+    }
     __device__ __forceinline__ float4 node(int i, int q) const { return nodes[((4 * i) << SHIFT) + (q << SHIFT)]; }
     __device__ __forceinline__ float4 tri(int i, int q) const { return tris[((3 * i) << SHIFT) + (q << SHIFT)]; }
     __device__ __forceinline__ float4 tri_shade(uint32_t prim) const { return shade[prim << SHIFT]; }
@@ -256,10 +279,8 @@ __device__ __forceinline__ void trav_node_apply(Trav& t, const STK& stack, const
 template <class FETCH, class STK>
 __device__ __forceinline__ void trav_node_step(Trav& t, const STK& stack, const FETCH& f, float tmin)
 {
-    const float4 q0 = f.node(t.cur, 0);
-    const float4 q1 = f.node(t.cur, 1);
-    const float4 q2 = f.node(t.cur, 2);
-    const float4 q3 = f.node(t.cur, 3);
+    float4 q0, q1, q2, q3;
+    f.node4(t.cur, q0, q1, q2, q3);
     trav_node_apply(t, stack, f, tmin, q0, q1, q2, q3);
 }
 
@@ -300,7 +321,8 @@ __device__ __forceinline__ void trav_wide_step(Trav& t, const STK& stack, const 
     int c[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float4 lo = f.wnode(t.cur, 2 * k), hi = f.wnode(t.cur, 2 * k + 1);
+        float4 lo, hi;
+        f.wnode2(t.cur, k, lo, hi);
         c[k] = __float_as_int(lo.w);
         float tk;
         const bool h = ray_box(t.r, f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), tmin, t.tfar, tk) && c[k] != kTravDone;
