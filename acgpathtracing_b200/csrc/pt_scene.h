@@ -28,9 +28,11 @@ struct WfTune {
     int miss_loop = 16;      // samples of an all-miss pixel finished per END visit
     int paths32 = 0;         // paths per CTA / 32 (0 = as many as fit)
     int block = 0;           // threads per CTA (0 = derived from the paths)
-    int smem_kb = 200;       // shared-memory budget for the paths when the scene is read from global memory
+    int smem_kb = 196;       // shared-memory budget for the paths when the scene is read from global memory: the largest
+                             // carve-out step (..., 164, 196, 228 KB) that still leaves 60 KB of L1 (one step more costs C3 8 %)
     int shortlist = 1;       // per-pixel candidate lists for camera rays (tiny scenes)
     int wide = -1;           // -1: follow Scene::traversal; 0 / 1: binary / wide nodes for scenes in global memory
+    int idle_ns = 64;        // sleep of a warp that found every queue empty
     int coop = -1;           // -1 / 1: warp-cooperative fetch of the binary nodes of a scene in global memory; 0: per lane
 };
 

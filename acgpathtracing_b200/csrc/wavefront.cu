@@ -64,6 +64,7 @@ struct WfConst {
     int tail_cols;           // tail mode when the non-empty columns of all four queues add up to at most this
     int miss_loop;           // samples of an all-miss pixel finished per END visit
     int block_override;      // host only: threads per CTA when set by PTB_TUNE
+    int idle_ns;             // sleep of a warp that found every queue empty
 };
 
 struct ThreadCounters {
@@ -281,7 +282,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 }
                 if (COUNT) st_idle++;
                 stage = -1;
-                __nanosleep(64);
+                __nanosleep((unsigned)wc.idle_ns);
                 continue;
             }
             idle_polls = 0;
@@ -837,7 +838,8 @@ static WfTune tuned(const WfTune& base)
                                {"tail_cols", &WfTune::tail_cols},   {"miss_loop", &WfTune::miss_loop},
                                {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
                                {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
-                               {"wide", &WfTune::wide},             {"coop", &WfTune::coop}};
+                               {"wide", &WfTune::wide},             {"coop", &WfTune::coop},
+                               {"idle_ns", &WfTune::idle_ns}};
     std::string str(env);
     size_t pos = 0;
     while (pos < str.size()) {
@@ -868,6 +870,7 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     wc.tail_cols = tune.tail_cols;
     wc.miss_loop = tune.miss_loop;
     wc.block_override = tune.block;
+    wc.idle_ns = tune.idle_ns;
     const bool count = s.count_enabled;
     const int scene = smem_scene ? (int)wc.copies_shift : -1;
     // Per-pixel candidate lists for camera rays: only where building one (a loop over all triangles per pixel) is
