@@ -53,6 +53,10 @@ def _load():
         "pt_scene_get_sched_stats": (i32, [vp, C.POINTER(u64), i32]),
         "pt_scene_set_pipeline": (i32, [vp, i32]),
         "pt_scene_set_traversal": (i32, [vp, i32]),
+        "pt_scene_set_tree": (i32, [vp, i32]),
+        "pt_scene_tree_in_use": (i32, [vp]),
+        "pt_bvh_export_sah": (i32, [vp, vp, C.POINTER(u32)]),
+        "pt_sah_build_host": (i32, [vp, vp, u32, vp, C.POINTER(u32)]),
         "pt_scene_last_traversal": (i32, [vp]),
         "pt_bvh_export_wide": (i32, [vp, C.POINTER(u32), vp, vp]),
         "pt_scene_last_launch_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
@@ -91,6 +95,19 @@ def _check(rc):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def sah_build_host(tri_lo, tri_hi, sorted_prim):
+    """The library's host SAH builder (sah.cu) on its own: per-primitive boxes (n, 3) + leaf order -> (nodes (n-1, 16) u32, depth)."""
+    n = len(sorted_prim)
+    boxes = np.zeros((n, 8), np.float32)
+    boxes[:, 0:3] = tri_lo
+    boxes[:, 4:7] = tri_hi
+    prim = np.ascontiguousarray(sorted_prim, np.uint32)
+    nodes = np.zeros((n - 1, 16), np.uint32)
+    d = C.c_uint32()
+    _check(lib.pt_sah_build_host(_ptr(boxes), _ptr(prim), n, _ptr(nodes), C.byref(d)))
+    return nodes, d.value
 
 
 def camera_uvw_frame(eye, lookat, up, fov_y_deg, aspect):
@@ -215,6 +232,20 @@ class Scene:
 
     def set_pipeline(self, pipeline):
         _check(lib.pt_scene_set_pipeline(self._h, pipeline))
+
+    def set_tree(self, tree):
+        """0 auto (SAH for scenes of 2..8192 triangles), 1 LBVH, 2 SAH (pt_scene_set_tree)."""
+        _check(lib.pt_scene_set_tree(self._h, tree))
+
+    def tree_in_use(self):
+        return {1: "lbvh", 2: "sah"}.get(lib.pt_scene_tree_in_use(self._h), "?")
+
+    def bvh_export_sah(self):
+        """dict(nodes (n_nodes, 16) u32, depth) of the sweep-SAH tree."""
+        nodes = np.zeros((self.info()["n_nodes"], 16), np.uint32)
+        d = C.c_uint32()
+        _check(lib.pt_bvh_export_sah(self._h, _ptr(nodes), C.byref(d)))
+        return dict(nodes=nodes, depth=d.value)
 
     def set_traversal(self, traversal):
         """0 auto, 1 binary LBVH, 2 wide nodes (pt_scene_set_traversal)."""

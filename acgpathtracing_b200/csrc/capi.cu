@@ -72,7 +72,7 @@ static void scene_free(Scene* s)
     void* ptrs[] = {s->d_verts, s->d_indices, s->d_mat_ids, s->d_mats, s->d_tri_in, s->d_tri_bb, s->d_tri_shade,
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
-                    s->d_node_hi, s->d_nodes, s->d_tris, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
+                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_tris, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
                     s->d_tile_order};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -216,6 +216,18 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    // small scenes: sweep-SAH tree over the LBVH's leaves, built on the host (sah.cu); not part of build_ms (GPU time)
+    if (e == cudaSuccess && n >= 2 && n <= kSahMaxTris) {
+        std::vector<float4> bb(2 * n), nodes;
+        std::vector<uint32_t> prim(n);
+        A(cudaMemcpy(bb.data(), s->d_tri_bb, sizeof(float4) * 2 * n, cudaMemcpyDeviceToHost));
+        A(cudaMemcpy(prim.data(), s->d_vals[s->sorted_buf], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        if (e == cudaSuccess) {
+            sah_build_host(bb.data(), prim.data(), (uint32_t)n, nodes, s->sah_depth);
+            A(dev_alloc(&s->d_nodes_sah, nodes.size()));
+            A(cudaMemcpy(s->d_nodes_sah, nodes.data(), sizeof(float4) * nodes.size(), cudaMemcpyHostToDevice));
+        }
+    }
     if (e != cudaSuccess) {
         scene_free(s);
         return cuda_fail(e, "scene upload / LBVH build");
@@ -423,6 +435,44 @@ int pt_scene_set_traversal(pt_scene* scene, int traversal)
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
     if (traversal < 0 || traversal > 3) return fail(PT_ERR_INVALID, "traversal must be 0, 1, 2 or 3");
     s->traversal = traversal;
+    return PT_OK;
+}
+
+int pt_scene_set_tree(pt_scene* scene, int tree)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    if (tree < 0 || tree > 2) return fail(PT_ERR_INVALID, "tree must be 0, 1 or 2");
+    if (tree == 2 && !s->d_nodes_sah && s->n_tris >= 2) return fail(PT_ERR_INVALID, "no SAH tree for this scene (more than 8192 triangles)");
+    s->tree = tree;
+    return PT_OK;
+}
+
+int pt_scene_tree_in_use(const pt_scene* scene)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    return s ? (scene_uses_sah(*s) ? 2 : 1) : -1;
+}
+
+int pt_bvh_export_sah(const pt_scene* scene, void* nodes64, uint32_t* depth)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    if (!s->d_nodes_sah) return fail(PT_ERR_INVALID, "no SAH tree for this scene");
+    DeviceGuard g(s->device);
+    if (depth) *depth = s->sah_depth;
+    if (nodes64) PT_CUDA(cudaMemcpy(nodes64, s->d_nodes_sah, 64 * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
+    return PT_OK;
+}
+
+int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth)
+{
+    if (!tri_boxes8 || !sorted_prim || !nodes64 || n_tris < 2) return fail(PT_ERR_INVALID, "pt_sah_build_host: bad argument");
+    std::vector<float4> nodes;
+    uint32_t d = 0;
+    sah_build_host(reinterpret_cast<const float4*>(tri_boxes8), sorted_prim, n_tris, nodes, d);
+    memcpy(nodes64, nodes.data(), sizeof(float4) * nodes.size());
+    if (depth) *depth = d;
     return PT_OK;
 }
 

@@ -74,6 +74,10 @@ struct Scene {
     float4* d_node_hi = nullptr;
     float4* d_nodes = nullptr;        // 4 per node
     float4* d_tris = nullptr;         // 3 per leaf (leaf order)
+    // sweep-SAH tree over the same leaves (sah.cu), built on the host for scenes of 2 .. kSahMaxTris triangles
+    float4* d_nodes_sah = nullptr;    // 4 per node, same record as d_nodes; null when not built
+    uint32_t sah_depth = 0;
+    int tree = 0;                     // pt_scene_set_tree: 0 auto (SAH when built and no deeper than kSahMaxDepth), 1 LBVH, 2 SAH
     uint32_t* d_wide_index = nullptr; // per binary node: index of the wide node rooted there (lbvh.cu wide_count)
     float4* d_wnodes = nullptr;       // wide nodes, 8 per node (two binary levels per record)
     uint32_t n_wide = 0;
@@ -98,6 +102,21 @@ struct Scene {
     // last launch
     uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_wide = 0;   // last_wide: 0 binary per lane, 1 wide nodes, 2 binary cooperative
 };
+
+constexpr uint32_t kSahMaxTris = 8192;    // the host build is O(n log^2 n); larger scenes keep the GPU-built LBVH
+constexpr uint32_t kSahMaxDepth = 64;
+
+// which tree the render / trace kernels walk
+inline bool scene_uses_sah(const Scene& s)
+{
+    if (!s.d_nodes_sah || s.tree == 1) return false;
+    return s.tree == 2 || s.sah_depth <= kSahMaxDepth;
+}
+inline const float4* scene_nodes(const Scene& s) { return scene_uses_sah(s) ? s.d_nodes_sah : s.d_nodes; }
+inline uint32_t scene_depth(const Scene& s) { return scene_uses_sah(s) ? s.sah_depth : s.bvh_depth; }
+
+// sah.cu
+void sah_build_host(const float4* tri_bb, const uint32_t* sorted_prim, uint32_t n, std::vector<float4>& nodes, uint32_t& depth);
 
 // lbvh.cu
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream);

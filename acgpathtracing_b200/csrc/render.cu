@@ -331,7 +331,7 @@ cudaError_t trace_rays_device(Scene& s, const float* d_org, const float* d_dir, 
                               cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;
-    BvhView bvh{s.d_nodes, s.d_tris, s.n_tris};
+    BvhView bvh{scene_nodes(s), s.d_tris, s.n_tris};
     const unsigned grid = (unsigned)((n + 255) / 256);
     trace_rays_kernel<<<grid, 256, 0, stream>>>(bvh, d_org, d_dir, d_tmin, d_tmax, n, d_prim, d_t, d_any, d_counters2);
     return cudaGetLastError();
@@ -579,7 +579,7 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.background = make_float3(s.background[0], s.background[1], s.background[2]);
     lc.accum = (float4*)params.accumulationBuffer;
     lc.frame_buffer = raw_mean ? nullptr : (uchar4*)params.frameBuffer;
-    lc.bvh = BvhView{s.d_nodes, s.d_tris, s.n_tris};
+    lc.bvh = BvhView{scene_nodes(s), s.d_tris, s.n_tris};
     lc.wnodes = s.d_wnodes;
     lc.n_nodes = s.n_nodes;
     lc.n_mats = s.n_mats;

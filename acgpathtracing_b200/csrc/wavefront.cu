@@ -769,7 +769,7 @@ static int choose_trav(const Scene& s, const WfTune& tune)
 static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size_t& smem_bytes, bool& smem_scene, int& trav)
 {
     if (s.n_mats > 0xffffu) return false;                 // material id is packed into 16 bits of the path record
-    uint32_t depth = s.bvh_depth + 1u;                    // deferred children never exceed the tree depth
+    uint32_t depth = scene_depth(s) + 1u;                 // deferred children never exceed the tree depth
     if (depth > 255u) return false;
     trav = TRAV_DIRECT;
     const bool force_global = (s.traversal == 2 && !s.count_enabled && s.n_wide != 0) || s.traversal == 3;
@@ -797,7 +797,7 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
     if (trav == TRAV_WIDE) depth = 3u * ((s.bvh_depth + 1u) / 2u) + 1u;
     if (depth > 255u) {
         trav = TRAV_DIRECT;
-        depth = s.bvh_depth + 1u;
+        depth = scene_depth(s) + 1u;
     }
     const size_t per_path_g = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;
     const size_t per_warp = trav == TRAV_COOP ? (size_t)kStageF4 * 16 : 0;   // staging buffer of the cooperative fetch

@@ -197,6 +197,8 @@ def run_b200(args):
     scene = api.Scene(arr)
     if args.pipeline:
         scene.set_pipeline(args.pipeline)
+    if args.tree:
+        scene.set_tree(args.tree)
     info = scene.info()
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -427,9 +429,9 @@ def run_b200(args):
             "hbm": {"achieved": (w * h * 36) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
                     "unit": "GB/s", "note": "image traffic only: 16 B read + 16 B write + 4 B framebuffer per pixel per launch"},
             "algorithmic_flops_per_launch": flops / args.steps, "algorithmic_bytes_per_launch": tbytes / args.steps,
-            "algorithmic_note": "work of the SPECIFIED traversal (every ray through the LBVH), counted by the instrumented kernel and "
-                                "equal to the oracle's counts; the timed kernel resolves camera rays of tiny scenes from per-pixel "
-                                "candidate lists instead, which lowers the work done, not the work credited",
+            "algorithmic_note": "work of the SPECIFIED traversal (every ray through the tree named in config.pipeline.tree), counted by "
+                                "the instrumented kernel and equal to the oracle's counts; the timed kernel resolves camera rays of "
+                                "tiny scenes from per-pixel candidate lists instead, which lowers the work done, not the work credited",
             "per_gpu": world > 1,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -445,7 +447,7 @@ def run_b200(args):
                        "spp_per_step": spp, "max_depth": md, "direct_lighting": nee, "importance_sampling": imp,
                        "frames": f"0..{args.steps - 1}",
                        "parallelism": f"pixel-tiles x{world}" + (f" (EMULATED rank 0 of {args.emulate_ranks}: not a bench value)" if args.emulate_ranks > 1 else ""),
-                       "l2": "flushed between timed steps (256 MiB fill)", "pipeline": scene.last_launch_info(),
+                       "l2": "flushed between timed steps (256 MiB fill)", "pipeline": dict(scene.last_launch_info(), tree=scene.tree_in_use()),
                        "exchange": "none (1 GPU)" if world == 1 else (
                            f"frames dealt to ranks ({fp.rounds} whole frame(s) per rank, {len(fp.leftover)} tile-partitioned); one "
                            f"all-gather of per-frame means + ordered fold per image, {fp.bytes_received()} B received per rank, "
@@ -472,6 +474,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per launch")
     ap.add_argument("--pipeline", type=int, default=0, help="0 auto, 1 persistent state machine, 2 CTA-local wavefront")
+    ap.add_argument("--tree", type=int, default=0, help="0 auto (sweep-SAH tree for scenes of 2..8192 triangles), 1 LBVH, 2 SAH")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partition", default="auto", choices=["auto", "tiles"],
                     help="N > 1: auto = whole frames per rank + tile-partitioned leftovers; tiles = every launch tile-partitioned")

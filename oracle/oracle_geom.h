@@ -146,6 +146,12 @@ struct Lbvh {
     std::vector<BvhNode> nodes;         // max(n_tri - 1, 1) two-child nodes (empty when n_tri == 0)
     std::vector<TriRec> tris;           // leaf order
     std::vector<TriRec> tris_input;     // input (primitive) order, for brute force
+    std::vector<float> leaf_lo, leaf_hi; // 3 per leaf slot: the triangle's box (leaf order)
+    // sweep-SAH tree over the same leaves (sah_build below); `use_sah` selects which tree the traversals walk
+    std::vector<BvhNode> sah_nodes;
+    uint32_t sah_depth = 0;
+    bool use_sah = false;
+    const std::vector<BvhNode>& walk() const { return use_sah ? sah_nodes : nodes; }
 };
 
 static inline int delta64(const std::vector<uint64_t>& k, int i, int j)
@@ -212,6 +218,13 @@ static inline Lbvh lbvh_build(const float* verts_xyzw, uint32_t /*n_verts*/, con
         b.sorted_prim[i] = (uint32_t)(b.sorted_keys[i] & 0xffffffffu);
         b.tris[i] = b.tris_input[b.sorted_prim[i]];
     }
+    b.leaf_lo.resize(3 * (size_t)n_tri);
+    b.leaf_hi.resize(3 * (size_t)n_tri);
+    for (uint32_t i = 0; i < n_tri; ++i)
+        for (int a = 0; a < 3; ++a) {
+            b.leaf_lo[3 * (size_t)i + a] = bbmin[3 * (size_t)b.sorted_prim[i] + a];
+            b.leaf_hi[3 * (size_t)i + a] = bbmax[3 * (size_t)b.sorted_prim[i] + a];
+        }
 
     const int N = (int)n_tri;
     const int n_internal = N > 1 ? N - 1 : 1;
@@ -299,6 +312,118 @@ static inline Lbvh lbvh_build(const float* verts_xyzw, uint32_t /*n_verts*/, con
     return b;
 }
 
+// ---- sweep-SAH tree over the LBVH's leaf slots ----------------------------------------------------
+// Our specification (csrc/sah.cu states it; OptiX's builder is closed): a subtree over m >= 2 slots tries, for the
+// axes x, y, z in turn, the order by (lo + hi in float, slot) and every split "first k | rest", cost = A(first k) * k +
+// A(rest) * (m - k) with A = ex*ey + ey*ez + ez*ex in double; the first strict minimum wins; nodes in preorder.
+// Written recursively here (the library walks an explicit job stack) -- same tree, bit for bit, or the tests fail.
+struct SahBuilder {
+    const Lbvh& b;
+    std::vector<BvhNode>& out;
+    uint32_t depth = 0;
+    SahBuilder(const Lbvh& bb, std::vector<BvhNode>& o) : b(bb), out(o) {}
+
+    struct Aabb {
+        float lo[3], hi[3];
+    };
+    Aabb slot_box(uint32_t s) const
+    {
+        Aabb x;
+        for (int a = 0; a < 3; ++a) {
+            x.lo[a] = b.leaf_lo[3 * (size_t)s + a];
+            x.hi[a] = b.leaf_hi[3 * (size_t)s + a];
+        }
+        return x;
+    }
+    static Aabb join(Aabb x, const Aabb& y)
+    {
+        for (int a = 0; a < 3; ++a) {
+            x.lo[a] = fminf(x.lo[a], y.lo[a]);
+            x.hi[a] = fmaxf(x.hi[a], y.hi[a]);
+        }
+        return x;
+    }
+    static double area(const Aabb& x)
+    {
+        double e[3];
+        for (int a = 0; a < 3; ++a) e[a] = (double)x.hi[a] - (double)x.lo[a];
+        return e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+    }
+
+    // returns the child reference of the subtree over `slots`
+    int32_t build(std::vector<uint32_t> slots, uint32_t level)
+    {
+        if (slots.size() == 1) return ~(int32_t)slots[0];
+        if (level > depth) depth = level;
+        const size_t m = slots.size();
+        const int32_t me = (int32_t)out.size();
+        out.emplace_back();
+        bool found = false;
+        double best = 0.0;
+        size_t best_k = 0;
+        std::vector<uint32_t> best_sorted;
+        Aabb best_left{}, best_right{};
+        for (int a = 0; a < 3; ++a) {
+            std::vector<uint32_t> sorted = slots;
+            std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t x, uint32_t y) {
+                const float kx = b.leaf_lo[3 * (size_t)x + a] + b.leaf_hi[3 * (size_t)x + a];
+                const float ky = b.leaf_lo[3 * (size_t)y + a] + b.leaf_hi[3 * (size_t)y + a];
+                if (kx != ky) return kx < ky;
+                return x < y;
+            });
+            std::vector<Aabb> left(m), right(m);      // left[i] = boxes 0..i, right[i] = boxes i..m-1
+            left[0] = slot_box(sorted[0]);
+            for (size_t i = 1; i < m; ++i) left[i] = join(left[i - 1], slot_box(sorted[i]));
+            right[m - 1] = slot_box(sorted[m - 1]);
+            for (size_t i = m - 1; i-- > 0;) right[i] = join(right[i + 1], slot_box(sorted[i]));
+            bool took = false;
+            for (size_t k = 1; k < m; ++k) {
+                const double c = area(left[k - 1]) * (double)k + area(right[k]) * (double)(m - k);
+                if (!found || c < best) {
+                    found = true;
+                    took = true;
+                    best = c;
+                    best_k = k;
+                    best_left = left[k - 1];
+                    best_right = right[k];
+                }
+            }
+            if (took) best_sorted = sorted;
+        }
+        const int32_t l = build(std::vector<uint32_t>(best_sorted.begin(), best_sorted.begin() + best_k), level + 1);
+        const int32_t r = build(std::vector<uint32_t>(best_sorted.begin() + best_k, best_sorted.end()), level + 1);
+        BvhNode& nd = out[me];
+        for (int a = 0; a < 3; ++a) {
+            nd.lo0[a] = best_left.lo[a];
+            nd.hi0[a] = best_left.hi[a];
+            nd.lo1[a] = best_right.lo[a];
+            nd.hi1[a] = best_right.hi[a];
+        }
+        nd.c0 = l;
+        nd.c1 = r;
+        nd.pad0 = nd.pad1 = 0;
+        return me;
+    }
+};
+
+constexpr uint32_t kSahMaxTris = 8192, kSahMaxDepth = 64;   // the library's limits (csrc/pt_scene.h)
+
+// Builds b.sah_nodes for scenes of 2 .. kSahMaxTris triangles and applies the library's "auto" rule to b.use_sah.
+static inline void sah_build(Lbvh& b)
+{
+    b.sah_nodes.clear();
+    b.sah_depth = 0;
+    b.use_sah = false;
+    if (b.n_tri < 2 || b.n_tri > kSahMaxTris) return;
+    b.sah_nodes.reserve(b.n_tri - 1);
+    SahBuilder sb(b, b.sah_nodes);
+    std::vector<uint32_t> all(b.n_tri);
+    for (uint32_t i = 0; i < b.n_tri; ++i) all[i] = i;
+    sb.build(all, 1);
+    b.sah_depth = sb.depth;
+    b.use_sah = b.sah_depth <= kSahMaxDepth;
+}
+
 // ---- traversal -----------------------------------------------------------------------------
 // Logical sequence (mirrored by the device kernels): start at node 0; at an internal node test
 // both child boxes against [tmin, best_t]; visit the nearer hit child first (child 1 only when
@@ -314,7 +439,7 @@ static inline Hit bvh_closest(const Lbvh& b, const float o[3], const float d[3],
     int32_t cur = 0;
     for (;;) {
         if (cur >= 0) {
-            const BvhNode& nd = b.nodes[cur];
+            const BvhNode& nd = b.walk()[cur];
             if (ctr) ctr->n_node++;
             float tn0, tn1;
             bool h0 = ray_box(r, nd.lo0, nd.hi0, tmin, h.t, tn0);
@@ -361,7 +486,7 @@ static inline bool bvh_any(const Lbvh& b, const float o[3], const float d[3], fl
     int32_t cur = 0;
     for (;;) {
         if (cur >= 0) {
-            const BvhNode& nd = b.nodes[cur];
+            const BvhNode& nd = b.walk()[cur];
             if (ctr) ctr->n_node++;
             float tn0, tn1;
             bool h0 = ray_box(r, nd.lo0, nd.hi0, tmin, tmax, tn0);

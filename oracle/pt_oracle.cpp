@@ -648,6 +648,7 @@ void* ptor_scene_create(const float* verts_xyzw, uint32_t nV, const uint32_t* in
     sc->mat_ids.assign(matIds, matIds + nT);
     sc->mats.assign(mats, mats + nM);
     sc->bvh = lbvh_build(sc->verts.data(), nV, sc->indices.data(), nT, sc->mat_ids.data());
+    sah_build(sc->bvh);
     return sc;
 }
 void ptor_scene_destroy(void* s) { delete (OrScene*)s; }
@@ -658,6 +659,21 @@ void ptor_scene_set_background(void* s, float r, float g, float b)
 }
 
 void ptor_scene_set_jitter_order(void* s, int order) { ((OrScene*)s)->jitter_order = order; }
+
+// which tree the traversals walk: 0 auto (the library's rule), 1 LBVH, 2 SAH; returns the tree in use (1 / 2)
+int ptor_scene_set_tree(void* s, int tree)
+{
+    Lbvh& b = ((OrScene*)s)->bvh;
+    const bool have = !b.sah_nodes.empty();
+    b.use_sah = have && (tree == 2 || (tree == 0 && b.sah_depth <= kSahMaxDepth));
+    return b.use_sah ? 2 : 1;
+}
+uint32_t ptor_bvh_export_sah(void* s, void* nodes64)
+{
+    const Lbvh& b = ((OrScene*)s)->bvh;
+    if (nodes64) std::memcpy(nodes64, b.sah_nodes.data(), b.sah_nodes.size() * sizeof(BvhNode));
+    return b.sah_depth;
+}
 
 // LBVH export: sizes via NULL pointers
 uint32_t ptor_bvh_num_nodes(void* s) { return (uint32_t)((OrScene*)s)->bvh.nodes.size(); }

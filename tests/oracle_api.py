@@ -55,6 +55,10 @@ def load_port():
     lib.ptor_bvh_num_nodes.restype = C.c_uint32
     lib.ptor_bvh_num_nodes.argtypes = [_vp]
     lib.ptor_bvh_export.argtypes = [_vp] * 8
+    lib.ptor_scene_set_tree.argtypes = [_vp, C.c_int]
+    lib.ptor_scene_set_tree.restype = C.c_int
+    lib.ptor_bvh_export_sah.argtypes = [_vp, _vp]
+    lib.ptor_bvh_export_sah.restype = C.c_uint32
     lib.ptor_trace.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp]
     lib.ptor_render.restype = C.c_int
     lib.ptor_render.argtypes = [_vp, C.POINTER(PathTraceParams), C.c_int, C.c_int, C.c_int, _vp, _vp,
@@ -129,6 +133,15 @@ class OracleScene:
         self.lib.ptor_bvh_export(self.h, _ptr(out["morton"]), _ptr(out["sorted_keys"]), _ptr(out["sorted_prim"]),
                                  _ptr(out["parent"]), _ptr(out["nodes"]), _ptr(out["tris"]), _ptr(out["bounds"]))
         return out
+
+    def set_tree(self, tree):
+        """0 auto (the library's rule), 1 LBVH, 2 SAH; returns "lbvh" / "sah" (the tree the traversals walk)."""
+        return {1: "lbvh", 2: "sah"}[self.lib.ptor_scene_set_tree(self.h, tree)]
+
+    def bvh_sah(self):
+        nodes = np.zeros((self.lib.ptor_bvh_num_nodes(self.h), 16), np.uint32)
+        depth = self.lib.ptor_bvh_export_sah(self.h, _ptr(nodes))
+        return dict(nodes=nodes, depth=depth)
 
     def trace(self, org, dirs, tmin, tmax, use_bvh=True, want_any=False):
         org = np.ascontiguousarray(org, np.float32)

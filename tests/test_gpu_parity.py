@@ -752,3 +752,57 @@ def test_wide_traversal_single_triangle_and_soups(api, port):
             gs.enable_counters(False)
         finally:
             gs.destroy()
+
+
+# ---- sweep-SAH tree (pt_scene_set_tree): same leaves, better topology, same pixels ------------------------------------
+@pytest.mark.parametrize("name", ["cornell", "material", "tess40"])
+def test_sah_tree_bit_exact_and_selectable(api, port, scenes_cache, name):
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    g, o = gs.bvh_export_sah(), osc.bvh_sah()
+    gn, on = g["nodes"].copy(), o["nodes"].copy()
+    gn[:, [11, 15]] = 0
+    on[:, [11, 15]] = 0
+    assert g["depth"] == o["depth"] and np.array_equal(gn, on)
+    assert gs.tree_in_use() == "sah" == osc.set_tree(0)                     # auto: 2..8192 triangles
+    org, d = _rays(arr, 100_000, 17)
+    w, h = 160, 90
+    p = api.make_params(w, h, 4, 12, frame=2, nee=True, importance=True, scene=gs)
+    prev = np.random.default_rng(4).random((h, w, 4), dtype=np.float32)
+    results = {}
+    try:
+        for tree in (2, 1):
+            gs.set_tree(tree)
+            name_t = osc.set_tree(tree)
+            assert gs.tree_in_use() == name_t
+            gp, gt, ga, gc = gs.trace(org, d, 0.01, 1e16, want_any=True)
+            op, ot, oa, oc = osc.trace(org, d, 0.01, 1e16, use_bvh=True, want_any=True)
+            assert np.array_equal(gp, op) and np.array_equal(gt.view(np.uint32), ot.view(np.uint32)) and np.array_equal(ga, oa)
+            assert gc.tolist() == oc.tolist()                                   # work counters of THAT tree
+            gs.enable_counters(True)
+            gs.counters(reset=True)
+            gr = gs.launch_host(p, accum=prev.copy())
+            orr = osc.render(p, accum=prev.copy(), math_mode=1, use_bvh=True)
+            assert gs.counters(reset=True) == orr["counters"]
+            gs.enable_counters(False)
+            assert np.array_equal(gr["accum"].view(np.uint32), orr["accum"].view(np.uint32))
+            un = gs.launch_host(p, accum=prev.copy())                           # the uncounted (timed) kernel
+            assert np.array_equal(un["accum"].view(np.uint32), orr["accum"].view(np.uint32)) and np.array_equal(un["fb"], orr["fb"])
+            results[tree] = (gr["accum"], gc.tolist())
+        assert np.array_equal(results[1][0].view(np.uint32), results[2][0].view(np.uint32))
+        assert results[2][1][0] < results[1][1][0]                              # fewer node visits with SAH
+    finally:
+        gs.enable_counters(False)
+        gs.set_tree(0)
+        osc.set_tree(0)
+
+
+def test_sah_tree_limits(api, port):
+    """No SAH tree above 8192 triangles (LBVH stays in use, asking for SAH is an error); one triangle: LBVH."""
+    big = S.tessellated_scene(70)
+    gs = api.Scene(big)
+    try:
+        assert gs.tree_in_use() == "lbvh"
+        with pytest.raises(api.PtError):
+            gs.set_tree(2)
+    finally:
+        gs.destroy()
