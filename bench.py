@@ -422,8 +422,8 @@ def run_b200(args):
             "peak_source": "measured live by pt_bench_fp32_peak (dependent-free FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
             "peak_nominal": fp32_nominal,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this
-            # command on C2 (profiles/r1_v3f_wavefront_ncu_summary.txt: 415,744 + 548,096 B); other workloads: not captured
-            "traffic": 963840 if (args.workload == "c2" and args.pipeline != 1 and not args.spp) else None,
+            # command on C2 (profiles/r1_v3g_sah_wavefront_ncu_summary.txt: 682,496 + 522,752 B); other workloads: not captured
+            "traffic": 1205248 if (args.workload == "c2" and args.pipeline != 1 and not args.spp and not args.tree) else None,
             "l2": {"achieved": ach_gbs, "peak": l2_meas, "unit": "GB/s", "frac": ach_gbs / l2_meas,
                    "note": "node/triangle record bytes; served from shared memory when the scene is staged there"},
             "hbm": {"achieved": (w * h * 36) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
