@@ -26,6 +26,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+_emit = print          # replaced in __main__: the JSON line goes to the real stdout, everything else to stderr
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
@@ -165,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    _emit(json.dumps(out))
 
 
 # ================================================================================================================
@@ -460,7 +461,7 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "image_mean_radiance": checksum,
         }
-        print(json.dumps(out), flush=True)
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -488,4 +489,9 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one line, the JSON: anything a library prints there while we run (NCCL's version banner)
+    # goes to stderr instead
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    _emit = lambda line: os.write(_json_fd, (line + "\n").encode())
     main()
