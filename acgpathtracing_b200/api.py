@@ -56,6 +56,7 @@ def _load():
         "pt_scene_set_tree": (i32, [vp, i32]),
         "pt_scene_tree_in_use": (i32, [vp]),
         "pt_bvh_export_sah": (i32, [vp, vp, C.POINTER(u32)]),
+        "pt_bvh_export_ploc": (i32, [vp, vp, C.POINTER(u32), C.POINTER(C.c_float)]),
         "pt_sah_build_host": (i32, [vp, vp, u32, vp, C.POINTER(u32)]),
         "pt_scene_last_traversal": (i32, [vp]),
         "pt_bvh_export_wide": (i32, [vp, C.POINTER(u32), vp, vp]),
@@ -234,11 +235,18 @@ class Scene:
         _check(lib.pt_scene_set_pipeline(self._h, pipeline))
 
     def set_tree(self, tree):
-        """0 auto (SAH for scenes of 2..8192 triangles), 1 LBVH, 2 SAH (pt_scene_set_tree)."""
+        """0 auto (SAH for scenes of 2..8192 triangles, PLOC above), 1 LBVH, 2 SAH, 3 PLOC (pt_scene_set_tree)."""
         _check(lib.pt_scene_set_tree(self._h, tree))
 
     def tree_in_use(self):
-        return {1: "lbvh", 2: "sah"}.get(lib.pt_scene_tree_in_use(self._h), "?")
+        return {1: "lbvh", 2: "sah", 3: "ploc"}.get(lib.pt_scene_tree_in_use(self._h), "?")
+
+    def bvh_export_ploc(self):
+        """dict(nodes (n_nodes, 16) u32, depth, build_ms) of the GPU-built PLOC tree."""
+        nodes = np.zeros((self.info()["n_nodes"], 16), np.uint32)
+        d, ms = C.c_uint32(), C.c_float()
+        _check(lib.pt_bvh_export_ploc(self._h, _ptr(nodes), C.byref(d), C.byref(ms)))
+        return dict(nodes=nodes, depth=d.value, build_ms=ms.value)
 
     def bvh_export_sah(self):
         """dict(nodes (n_nodes, 16) u32, depth) of the sweep-SAH tree."""

@@ -72,7 +72,7 @@ static void scene_free(Scene* s)
     void* ptrs[] = {s->d_verts, s->d_indices, s->d_mat_ids, s->d_mats, s->d_tri_in, s->d_tri_bb, s->d_tri_shade,
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
-                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_tris, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
+                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
                     s->d_tile_order};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -213,6 +213,15 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
         }
         if (e == cudaSuccess && n) A(cudaMemcpy(&s->bvh_depth, s->d_work_counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (e == cudaSuccess && n) A(cudaMemcpy(s->h_bounds, s->d_bounds, 6 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    // PLOC tree over the same leaves (GPU; the tree the kernels walk when the scene is too large for the host SAH sweep)
+    if (e == cudaSuccess && n >= 2) {
+        A(cudaEventRecord(e0, stream));
+        A(ploc_build(*s, stream));
+        A(cudaEventRecord(e1, stream));
+        A(cudaStreamSynchronize(stream));
+        if (e == cudaSuccess) cudaEventElapsedTime(&s->ploc_ms, e0, e1);
+        s->build_ms += s->ploc_ms;
     }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
@@ -442,8 +451,9 @@ int pt_scene_set_tree(pt_scene* scene, int tree)
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
-    if (tree < 0 || tree > 2) return fail(PT_ERR_INVALID, "tree must be 0, 1 or 2");
+    if (tree < 0 || tree > 3) return fail(PT_ERR_INVALID, "tree must be 0, 1, 2 or 3");
     if (tree == 2 && !s->d_nodes_sah && s->n_tris >= 2) return fail(PT_ERR_INVALID, "no SAH tree for this scene (more than 8192 triangles)");
+    if (tree == 3 && !s->d_nodes_ploc && s->n_tris >= 2) return fail(PT_ERR_INVALID, "no PLOC tree for this scene");
     s->tree = tree;
     return PT_OK;
 }
@@ -451,7 +461,7 @@ int pt_scene_set_tree(pt_scene* scene, int tree)
 int pt_scene_tree_in_use(const pt_scene* scene)
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
-    return s ? (scene_uses_sah(*s) ? 2 : 1) : -1;
+    return s ? scene_tree(*s) : -1;
 }
 
 int pt_bvh_export_sah(const pt_scene* scene, void* nodes64, uint32_t* depth)
@@ -462,6 +472,18 @@ int pt_bvh_export_sah(const pt_scene* scene, void* nodes64, uint32_t* depth)
     DeviceGuard g(s->device);
     if (depth) *depth = s->sah_depth;
     if (nodes64) PT_CUDA(cudaMemcpy(nodes64, s->d_nodes_sah, 64 * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
+    return PT_OK;
+}
+
+int pt_bvh_export_ploc(const pt_scene* scene, void* nodes64, uint32_t* depth, float* build_ms)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    if (!s->d_nodes_ploc) return fail(PT_ERR_INVALID, "no PLOC tree for this scene");
+    DeviceGuard g(s->device);
+    if (depth) *depth = s->ploc_depth;
+    if (build_ms) *build_ms = s->ploc_ms;
+    if (nodes64) PT_CUDA(cudaMemcpy(nodes64, s->d_nodes_ploc, 64 * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
     return PT_OK;
 }
 

@@ -77,7 +77,11 @@ struct Scene {
     // sweep-SAH tree over the same leaves (sah.cu), built on the host for scenes of 2 .. kSahMaxTris triangles
     float4* d_nodes_sah = nullptr;    // 4 per node, same record as d_nodes; null when not built
     uint32_t sah_depth = 0;
-    int tree = 0;                     // pt_scene_set_tree: 0 auto (SAH when built and no deeper than kSahMaxDepth), 1 LBVH, 2 SAH
+    // PLOC tree over the same leaves (lbvh.cu ploc_build), built on the GPU for every scene of >= 2 triangles
+    float4* d_nodes_ploc = nullptr;   // 4 per node, same record; null when not built
+    uint32_t ploc_depth = 0;
+    float ploc_ms = 0.f;
+    int tree = 0;                     // pt_scene_set_tree: 0 auto, 1 LBVH, 2 SAH, 3 PLOC
     uint32_t* d_wide_index = nullptr; // per binary node: index of the wide node rooted there (lbvh.cu wide_count)
     float4* d_wnodes = nullptr;       // wide nodes, 8 per node (two binary levels per record)
     uint32_t n_wide = 0;
@@ -106,14 +110,27 @@ struct Scene {
 constexpr uint32_t kSahMaxTris = 8192;    // the host build is O(n log^2 n); larger scenes keep the GPU-built LBVH
 constexpr uint32_t kSahMaxDepth = 64;
 
-// which tree the render / trace kernels walk
-inline bool scene_uses_sah(const Scene& s)
+// which tree the render / trace kernels walk: 1 LBVH, 2 SAH, 3 PLOC.  auto: the host-built SAH tree where there is one
+// (2..kSahMaxTris triangles), else the GPU-built PLOC tree, else the LBVH; a tree deeper than kSahMaxDepth is passed over.
+inline int scene_tree(const Scene& s)
 {
-    if (!s.d_nodes_sah || s.tree == 1) return false;
-    return s.tree == 2 || s.sah_depth <= kSahMaxDepth;
+    if (s.tree == 2 && s.d_nodes_sah) return 2;
+    if (s.tree == 3 && s.d_nodes_ploc) return 3;
+    if (s.tree != 0) return 1;
+    if (s.d_nodes_sah && s.sah_depth <= kSahMaxDepth) return 2;
+    if (s.d_nodes_ploc && s.ploc_depth <= kSahMaxDepth) return 3;
+    return 1;
 }
-inline const float4* scene_nodes(const Scene& s) { return scene_uses_sah(s) ? s.d_nodes_sah : s.d_nodes; }
-inline uint32_t scene_depth(const Scene& s) { return scene_uses_sah(s) ? s.sah_depth : s.bvh_depth; }
+inline const float4* scene_nodes(const Scene& s)
+{
+    const int t = scene_tree(s);
+    return t == 2 ? s.d_nodes_sah : (t == 3 ? s.d_nodes_ploc : s.d_nodes);
+}
+inline uint32_t scene_depth(const Scene& s)
+{
+    const int t = scene_tree(s);
+    return t == 2 ? s.sah_depth : (t == 3 ? s.ploc_depth : s.bvh_depth);
+}
 
 // sah.cu
 void sah_build_host(const float4* tri_bb, const uint32_t* sorted_prim, uint32_t n, std::vector<float4>& nodes, uint32_t& depth);
@@ -122,6 +139,7 @@ void sah_build_host(const float4* tri_bb, const uint32_t* sorted_prim, uint32_t 
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
 cudaError_t wide_count(Scene& s, cudaStream_t stream);
 cudaError_t wide_emit(Scene& s, cudaStream_t stream);
+cudaError_t ploc_build(Scene& s, cudaStream_t stream);
 
 // render.cu
 constexpr uint32_t kMaxFoldFrames = 64;

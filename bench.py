@@ -475,7 +475,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel per launch")
     ap.add_argument("--pipeline", type=int, default=0, help="0 auto, 1 persistent state machine, 2 CTA-local wavefront")
-    ap.add_argument("--tree", type=int, default=0, help="0 auto (sweep-SAH tree for scenes of 2..8192 triangles), 1 LBVH, 2 SAH")
+    ap.add_argument("--tree", type=int, default=0, help="0 auto (sweep-SAH tree for scenes of 2..8192 triangles, PLOC above), 1 LBVH, 2 SAH, 3 PLOC")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--partition", default="auto", choices=["auto", "tiles"],
                     help="N > 1: auto = whole frames per rank + tile-partitioned leftovers; tiles = every launch tile-partitioned")

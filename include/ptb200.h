@@ -123,17 +123,23 @@ int pt_scene_get_counters(pt_scene* scene, pt_counters* out, int reset);
 int pt_scene_get_sched_stats(pt_scene* scene, uint64_t* out16, int reset);
 /* kernel variant: 0 = auto, 1 = persistent thread-per-path, 2 = CTA-local wavefront */
 int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
-/* Which binary tree the render and trace kernels walk: 0 = auto (the sweep-SAH tree when the scene has 2..8192 triangles
- * and that tree is at most 64 levels deep, else the LBVH), 1 = the Morton-order LBVH built on the GPU, 2 = the
- * sweep-SAH tree over the same leaves, built on the host at pt_scene_create (PT_ERR_INVALID when there is none).
- * Both are trees of the same 64-byte two-child nodes over the same leaf records, so the pixels, primary hits and
- * any-hit answers do not depend on the choice; the work counters do (18-27 % fewer node visits with SAH).
- * Replaces the build flags of optixAccelBuild (PathTracerMain.cpp:334-339). */
+/* Which binary tree the render and trace kernels walk.  Three trees over the same leaf records, all made of the same
+ * 64-byte two-child nodes, so the pixels, primary hits and any-hit answers do not depend on the choice (the work
+ * counters do):
+ *   1 = the Morton-order LBVH, built on the GPU (always built; pt_bvh_export);
+ *   2 = a sweep-SAH tree, built on the host at pt_scene_create for scenes of 2..8192 triangles (18-27 % fewer node
+ *       visits than the LBVH);
+ *   3 = a PLOC tree (parallel locally-ordered clustering, radius 8), built on the GPU for every scene of >= 2
+ *       triangles (22-27 % fewer node visits on the 2 M-triangle scene);
+ *   0 = auto: 2 where it exists, else 3, else 1 (a tree more than 64 levels deep is passed over).
+ * Asking for a tree the scene does not have is PT_ERR_INVALID.  Replaces the build flags of optixAccelBuild
+ * (PathTracerMain.cpp:334-339). */
 int pt_scene_set_tree(pt_scene* scene, int tree);
-int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH */
+int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH, 3 PLOC */
 /* SAH tree export (tests): nodes: n_nodes x 64 B (same record as pt_bvh_export's); depth: internal nodes on the
  * longest root-to-leaf chain. */
 int pt_bvh_export_sah(const pt_scene* scene, void* nodes64, uint32_t* depth);
+int pt_bvh_export_ploc(const pt_scene* scene, void* nodes64, uint32_t* depth, float* build_ms);
 /* The host builder on its own (no device needed): tri_boxes8 = per PRIMITIVE (lo.xyz, -, hi.xyz, -), sorted_prim =
  * leaf slot -> primitive (pt_bvh_export), n_tris >= 2; writes (n_tris - 1) x 64 B. */
 int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth);

@@ -151,7 +151,11 @@ struct Lbvh {
     std::vector<BvhNode> sah_nodes;
     uint32_t sah_depth = 0;
     bool use_sah = false;
-    const std::vector<BvhNode>& walk() const { return use_sah ? sah_nodes : nodes; }
+    // PLOC tree over the same leaves (ploc_build below)
+    std::vector<BvhNode> ploc_nodes;
+    uint32_t ploc_depth = 0;
+    bool use_ploc = false;
+    const std::vector<BvhNode>& walk() const { return use_sah ? sah_nodes : (use_ploc ? ploc_nodes : nodes); }
 };
 
 static inline int delta64(const std::vector<uint64_t>& k, int i, int j)
@@ -406,6 +410,89 @@ struct SahBuilder {
     }
 };
 
+// ---- PLOC tree over the LBVH's leaf slots (csrc/lbvh.cu ploc_* kernels state the rounds; serial here) ----------------
+// Clusters start as the leaves in Morton order.  Round: cluster i chooses, among j in [i - 8, i + 8], j != i, the one
+// whose union box has the smallest ex*ey + ey*ez + ez*ex (float; first strict minimum for ascending j; default i - 1, or
+// i + 1 for i = 0); mutual choices merge into a node at the lower index, survivors keep their order.  Node ids count
+// down from n - 2 in creation order (round by round, ascending position), so the last node -- the root -- is node 0.
+static inline void ploc_build(Lbvh& b)
+{
+    b.ploc_nodes.clear();
+    b.ploc_depth = 0;
+    b.use_ploc = false;
+    const int n = (int)b.n_tri;
+    if (n < 2) return;
+    struct Cluster {
+        float lo[3], hi[3];
+        int32_t ref;
+    };
+    std::vector<Cluster> cur(n), next;
+    for (int i = 0; i < n; ++i) {
+        for (int a = 0; a < 3; ++a) {
+            cur[i].lo[a] = b.leaf_lo[3 * (size_t)i + a];
+            cur[i].hi[a] = b.leaf_hi[3 * (size_t)i + a];
+        }
+        cur[i].ref = ~i;
+    }
+    b.ploc_nodes.resize(n - 1);
+    std::vector<uint32_t> node_level(n - 1, 0);          // height of the subtree under a node, in internal nodes
+    int next_id = n - 2;
+    std::vector<int> nn;
+    while (cur.size() > 1) {
+        const int c = (int)cur.size();
+        nn.assign(c, 0);
+        for (int i = 0; i < c; ++i) {
+            int best_j = i > 0 ? i - 1 : i + 1;
+            float best = INFINITY;
+            const int first = std::max(0, i - 8), last = std::min(c - 1, i + 8);
+            for (int j = first; j <= last; ++j) {
+                if (j == i) continue;
+                float e[3];
+                for (int a = 0; a < 3; ++a) e[a] = fmaxf(cur[i].hi[a], cur[j].hi[a]) - fminf(cur[i].lo[a], cur[j].lo[a]);
+                const float area = e[0] * e[1] + e[1] * e[2] + e[2] * e[0];
+                if (area < best) {
+                    best = area;
+                    best_j = j;
+                }
+            }
+            nn[i] = best_j;
+        }
+        next.clear();
+        int made = 0;
+        for (int i = 0; i < c; ++i) {
+            const int j = nn[i];
+            const bool mutual = nn[j] == i;
+            if (mutual && i > j) continue;
+            if (!mutual) {
+                next.push_back(cur[i]);
+                continue;
+            }
+            const int id = next_id - made;
+            ++made;
+            BvhNode& nd = b.ploc_nodes[id];
+            Cluster m;
+            for (int a = 0; a < 3; ++a) {
+                nd.lo0[a] = cur[i].lo[a];
+                nd.hi0[a] = cur[i].hi[a];
+                nd.lo1[a] = cur[j].lo[a];
+                nd.hi1[a] = cur[j].hi[a];
+                m.lo[a] = fminf(cur[i].lo[a], cur[j].lo[a]);
+                m.hi[a] = fmaxf(cur[i].hi[a], cur[j].hi[a]);
+            }
+            nd.c0 = cur[i].ref;
+            nd.c1 = cur[j].ref;
+            nd.pad0 = nd.pad1 = 0;
+            const uint32_t l0 = cur[i].ref >= 0 ? node_level[cur[i].ref] : 0u, l1 = cur[j].ref >= 0 ? node_level[cur[j].ref] : 0u;
+            node_level[id] = 1u + std::max(l0, l1);
+            m.ref = id;
+            next.push_back(m);
+        }
+        next_id -= made;
+        cur.swap(next);
+    }
+    b.ploc_depth = node_level[0];
+}
+
 constexpr uint32_t kSahMaxTris = 8192, kSahMaxDepth = 64;   // the library's limits (csrc/pt_scene.h)
 
 // Builds b.sah_nodes for scenes of 2 .. kSahMaxTris triangles and applies the library's "auto" rule to b.use_sah.
@@ -422,6 +509,23 @@ static inline void sah_build(Lbvh& b)
     sb.build(all, 1);
     b.sah_depth = sb.depth;
     b.use_sah = b.sah_depth <= kSahMaxDepth;
+}
+
+// The library's rule (csrc/pt_scene.h scene_tree): tree = 0 auto (SAH where there is one, else PLOC, else LBVH; a tree
+// deeper than 64 is passed over), 1 LBVH, 2 SAH, 3 PLOC.  Returns the tree in use (1 / 2 / 3).
+static inline int select_tree(Lbvh& b, int tree)
+{
+    const bool have_sah = !b.sah_nodes.empty(), have_ploc = !b.ploc_nodes.empty();
+    int t = 1;
+    if (tree == 2 && have_sah) t = 2;
+    else if (tree == 3 && have_ploc) t = 3;
+    else if (tree == 0) {
+        if (have_sah && b.sah_depth <= kSahMaxDepth) t = 2;
+        else if (have_ploc && b.ploc_depth <= kSahMaxDepth) t = 3;
+    }
+    b.use_sah = t == 2;
+    b.use_ploc = t == 3;
+    return t;
 }
 
 // ---- traversal -----------------------------------------------------------------------------

@@ -649,6 +649,8 @@ void* ptor_scene_create(const float* verts_xyzw, uint32_t nV, const uint32_t* in
     sc->mats.assign(mats, mats + nM);
     sc->bvh = lbvh_build(sc->verts.data(), nV, sc->indices.data(), nT, sc->mat_ids.data());
     sah_build(sc->bvh);
+    ploc_build(sc->bvh);
+    select_tree(sc->bvh, 0);
     return sc;
 }
 void ptor_scene_destroy(void* s) { delete (OrScene*)s; }
@@ -660,13 +662,13 @@ void ptor_scene_set_background(void* s, float r, float g, float b)
 
 void ptor_scene_set_jitter_order(void* s, int order) { ((OrScene*)s)->jitter_order = order; }
 
-// which tree the traversals walk: 0 auto (the library's rule), 1 LBVH, 2 SAH; returns the tree in use (1 / 2)
-int ptor_scene_set_tree(void* s, int tree)
+// which tree the traversals walk: 0 auto (the library's rule), 1 LBVH, 2 SAH, 3 PLOC; returns the tree in use
+int ptor_scene_set_tree(void* s, int tree) { return select_tree(((OrScene*)s)->bvh, tree); }
+uint32_t ptor_bvh_export_ploc(void* s, void* nodes64)
 {
-    Lbvh& b = ((OrScene*)s)->bvh;
-    const bool have = !b.sah_nodes.empty();
-    b.use_sah = have && (tree == 2 || (tree == 0 && b.sah_depth <= kSahMaxDepth));
-    return b.use_sah ? 2 : 1;
+    const Lbvh& b = ((OrScene*)s)->bvh;
+    if (nodes64) std::memcpy(nodes64, b.ploc_nodes.data(), b.ploc_nodes.size() * sizeof(BvhNode));
+    return b.ploc_depth;
 }
 uint32_t ptor_bvh_export_sah(void* s, void* nodes64)
 {

@@ -171,6 +171,8 @@ int ptref_render(const void* params168, const float* verts_xyzw, uint32_t nV, co
     scene.miss.backgroundColor = make_float4(bg4[0], bg4[1], bg4[2], bg4[3]);
     scene.bvh = ora::lbvh_build(verts_xyzw, nV, indices, nT, matIds);
     ora::sah_build(scene.bvh);   // same tree choice as the port and the library (work counters are compared)
+    ora::ploc_build(scene.bvh);
+    ora::select_tree(scene.bvh, 0);
     scene.use_bvh = use_bvh != 0;
     g_scene = &scene;
 

@@ -59,6 +59,8 @@ def load_port():
     lib.ptor_scene_set_tree.restype = C.c_int
     lib.ptor_bvh_export_sah.argtypes = [_vp, _vp]
     lib.ptor_bvh_export_sah.restype = C.c_uint32
+    lib.ptor_bvh_export_ploc.argtypes = [_vp, _vp]
+    lib.ptor_bvh_export_ploc.restype = C.c_uint32
     lib.ptor_trace.argtypes = [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp, _vp]
     lib.ptor_render.restype = C.c_int
     lib.ptor_render.argtypes = [_vp, C.POINTER(PathTraceParams), C.c_int, C.c_int, C.c_int, _vp, _vp,
@@ -135,8 +137,13 @@ class OracleScene:
         return out
 
     def set_tree(self, tree):
-        """0 auto (the library's rule), 1 LBVH, 2 SAH; returns "lbvh" / "sah" (the tree the traversals walk)."""
-        return {1: "lbvh", 2: "sah"}[self.lib.ptor_scene_set_tree(self.h, tree)]
+        """0 auto (the library's rule), 1 LBVH, 2 SAH, 3 PLOC; returns the tree the traversals walk."""
+        return {1: "lbvh", 2: "sah", 3: "ploc"}[self.lib.ptor_scene_set_tree(self.h, tree)]
+
+    def bvh_ploc(self):
+        nodes = np.zeros((self.lib.ptor_bvh_num_nodes(self.h), 16), np.uint32)
+        depth = self.lib.ptor_bvh_export_ploc(self.h, _ptr(nodes))
+        return dict(nodes=nodes, depth=depth)
 
     def bvh_sah(self):
         nodes = np.zeros((self.lib.ptor_bvh_num_nodes(self.h), 16), np.uint32)

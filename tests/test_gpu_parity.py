@@ -450,6 +450,12 @@ def test_full_size_c4_two_million_triangles(api, port):
         gn[:, [11, 15]] = 0
         on[:, [11, 15]] = 0
         assert np.array_equal(gn, on)
+        gpl, opl = gs.bvh_export_ploc(), osc.bvh_ploc()                           # the tree both sides walk by default
+        gn, on = gpl["nodes"].copy(), opl["nodes"].copy()
+        gn[:, [11, 15]] = 0
+        on[:, [11, 15]] = 0
+        assert gpl["depth"] == opl["depth"] and np.array_equal(gn, on)
+        assert gs.tree_in_use() == osc.set_tree(0) == "ploc"
         org, d = _rays(arr, 4096, 23)
         gp, gt, ga, gc = gs.trace(org, d, 0.01, 1e16, want_any=True)
         op, ot, oa, oc = osc.trace(org, d, 0.01, 1e16, use_bvh=True, want_any=True)
@@ -770,7 +776,7 @@ def test_sah_tree_bit_exact_and_selectable(api, port, scenes_cache, name):
     prev = np.random.default_rng(4).random((h, w, 4), dtype=np.float32)
     results = {}
     try:
-        for tree in (2, 1):
+        for tree in (2, 3, 1):
             gs.set_tree(tree)
             name_t = osc.set_tree(tree)
             assert gs.tree_in_use() == name_t
@@ -789,7 +795,8 @@ def test_sah_tree_bit_exact_and_selectable(api, port, scenes_cache, name):
             assert np.array_equal(un["accum"].view(np.uint32), orr["accum"].view(np.uint32)) and np.array_equal(un["fb"], orr["fb"])
             results[tree] = (gr["accum"], gc.tolist())
         assert np.array_equal(results[1][0].view(np.uint32), results[2][0].view(np.uint32))
-        assert results[2][1][0] < results[1][1][0]                              # fewer node visits with SAH
+        assert np.array_equal(results[1][0].view(np.uint32), results[3][0].view(np.uint32))
+        assert results[2][1][0] < results[1][1][0] and results[3][1][0] < results[1][1][0]   # fewer node visits than the LBVH
     finally:
         gs.enable_counters(False)
         gs.set_tree(0)
@@ -797,12 +804,25 @@ def test_sah_tree_bit_exact_and_selectable(api, port, scenes_cache, name):
 
 
 def test_sah_tree_limits(api, port):
-    """No SAH tree above 8192 triangles (LBVH stays in use, asking for SAH is an error); one triangle: LBVH."""
+    """No SAH tree above 8192 triangles (the PLOC tree is in use there; asking for SAH is an error)."""
     big = S.tessellated_scene(70)
     gs = api.Scene(big)
     try:
-        assert gs.tree_in_use() == "lbvh"
+        assert gs.tree_in_use() == "ploc"
         with pytest.raises(api.PtError):
             gs.set_tree(2)
     finally:
         gs.destroy()
+
+
+@pytest.mark.parametrize("name", ["cornell", "material", "tess40", "tess300"])
+def test_ploc_tree_bit_exact(api, port, scenes_cache, name):
+    """The GPU-built PLOC tree (lbvh.cu ploc_* kernels) equals the oracle's serial restatement, word for word."""
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    g, o = gs.bvh_export_ploc(), osc.bvh_ploc()
+    gn, on = g["nodes"].copy(), o["nodes"].copy()
+    gn[:, [11, 15]] = 0
+    on[:, [11, 15]] = 0
+    assert g["depth"] == o["depth"]
+    assert np.array_equal(gn, on)
+    assert gs.tree_in_use() == osc.set_tree(0) == ("sah" if arr.n_tri <= 8192 else "ploc")

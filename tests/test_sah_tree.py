@@ -92,10 +92,46 @@ def test_sah_tree_answers_like_brute_force(port, name):
 
 
 def test_auto_rule(port):
-    """auto = SAH for 2..8192 triangles (and at most 64 levels), LBVH otherwise."""
+    """auto = SAH for 2..8192 triangles, PLOC above (each at most 64 levels deep), LBVH for a single triangle."""
     assert O.OracleScene(port, S.cornell32()).set_tree(0) == "sah"
     one = _soup(np.random.default_rng(1), 1)
     assert O.OracleScene(port, one).set_tree(0) == "lbvh"
     big = S.tessellated_scene(70)                         # 9812 triangles
     assert big.n_tri > 8192
-    assert O.OracleScene(port, big).set_tree(0) == "lbvh"
+    osc = O.OracleScene(port, big)
+    assert osc.set_tree(0) == "ploc" and osc.set_tree(2) == "lbvh" and osc.set_tree(3) == "ploc"
+
+
+@pytest.mark.parametrize("name,arr", _cases() + [("tess70", S.tessellated_scene(70))], ids=lambda x: x if isinstance(x, str) else "")
+def test_ploc_tree_structure_and_answers(port, name, arr):
+    """The oracle's PLOC tree (the GPU build is compared with it word for word in tests/test_gpu_parity.py): n - 1 nodes,
+    root 0, every leaf and every other node referenced once, child boxes = exact unions, and the same answers as the
+    LBVH and as brute force."""
+    osc = O.OracleScene(port, arr)
+    p = osc.bvh_ploc()
+    nodes = p["nodes"]
+    ch = nodes[:, [3, 7]].view(np.int32)
+    assert np.array_equal(np.sort(~ch[ch < 0]), np.arange(arr.n_tri))
+    assert np.array_equal(np.sort(ch[ch >= 0]), np.arange(1, arr.n_tri - 1))
+    assert np.all(ch[ch >= 0] > np.repeat(np.arange(arr.n_tri - 1), 2).reshape(-1, 2)[ch >= 0])   # children were created earlier
+    b = osc.bvh()
+    lo, hi = _boxes(arr)
+    slot_lo, slot_hi = lo[b["sorted_prim"]], hi[b["sorted_prim"]]
+    f = nodes.view(np.float32)
+    box_lo, box_hi = np.zeros((arr.n_tri - 1, 3), np.float32), np.zeros((arr.n_tri - 1, 3), np.float32)
+    for i in range(arr.n_tri - 2, -1, -1):               # children have larger ids: bottom-up in one sweep
+        for side, (l, h) in enumerate(((f[i, 0:3], f[i, 4:7]), (f[i, 8:11], f[i, 12:15]))):
+            c = int(ch[i, side])
+            el, eh = (slot_lo[~c], slot_hi[~c]) if c < 0 else (box_lo[c], box_hi[c])
+            assert np.array_equal(l, el) and np.array_equal(h, eh)
+        box_lo[i] = np.minimum(f[i, 0:3], f[i, 8:11])
+        box_hi[i] = np.maximum(f[i, 4:7], f[i, 12:15])
+    rng = np.random.default_rng(13)
+    n = 4000
+    org = rng.uniform(arr.verts[:, :3].min(0) - 30, arr.verts[:, :3].max(0) + 30, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    assert osc.set_tree(3) == "ploc"
+    pp, pt, pa, _ = osc.trace(org, d, 0.01, 1e16, use_bvh=True, want_any=True)
+    bp, bt, ba, _ = osc.trace(org, d, 0.01, 1e16, use_bvh=False, want_any=True)
+    assert np.array_equal(pp, bp) and np.array_equal(pt.view(np.uint32), bt.view(np.uint32)) and np.array_equal(pa, ba)
