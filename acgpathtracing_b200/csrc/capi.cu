@@ -71,7 +71,7 @@ static void scene_free(Scene* s)
 {
     void* ptrs[] = {s->d_verts, s->d_indices, s->d_mat_ids, s->d_mats, s->d_tri_in, s->d_tri_bb, s->d_tri_shade,
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
-                    s->d_block_hist, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
+                    s->d_block_hist, s->d_scan_scratch, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
                     s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
                     s->d_tile_order};
     for (void* p : ptrs)
@@ -152,6 +152,7 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
         A(dev_alloc(&s->d_vals[b], n));
     }
     A(dev_alloc(&s->d_block_hist, 256 * n_blocks));
+    A(dev_alloc(&s->d_scan_scratch, lbvh_scan_scratch_entries(n)));
     A(dev_alloc(&s->d_left, n));
     A(dev_alloc(&s->d_right, n));
     A(dev_alloc(&s->d_node_parent, n));

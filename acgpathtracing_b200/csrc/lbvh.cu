@@ -183,6 +183,82 @@ __global__ void __launch_bounds__(1024) scan_kernel(uint32_t* __restrict__ data,
     }
 }
 
+// ---- multi-block exclusive scan ------------------------------------------------------------------------------------
+// scan_kernel above walks the whole array with one CTA: fine for a few thousand entries, 2 ms for the 2 M flags of a
+// PLOC round.  For larger arrays: every CTA scans a tile of 4096 entries in place and writes the tile's total, the
+// totals are scanned (recursively), and a third kernel adds each tile's offset.  Integer sums: deterministic.
+constexpr uint32_t kScanTile = 4096;   // 1024 threads x 4 entries
+
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(uint32_t* __restrict__ data, uint32_t count, uint32_t* __restrict__ tile_sums)
+{
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * 4u;
+    uint32_t v[4], sum = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = base + k < count ? data[base + k] : 0u;
+        sum += v[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, t, off);
+            if (lane >= off) t += y;
+        }
+        warp_sums[lane] = t;   // inclusive
+    }
+    __syncthreads();
+    uint32_t run = x - sum + (warp > 0 ? warp_sums[warp - 1] : 0u);   // exclusive prefix of this thread's four entries
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < count) data[base + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 1023) tile_sums[blockIdx.x] = warp_sums[31];
+}
+
+__global__ void __launch_bounds__(1024) scan_add_kernel(uint32_t* __restrict__ data, uint32_t count, const uint32_t* __restrict__ tile_offsets)
+{
+    const uint32_t off = tile_offsets[blockIdx.x];
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * 4u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < count) data[base + k] += off;
+}
+
+// scratch: at least scan_scratch_entries(count) entries
+static inline size_t scan_scratch_entries(size_t count)
+{
+    size_t total = 0;
+    while (count > kScanTile) {
+        count = (count + kScanTile - 1) / kScanTile;
+        total += count;
+    }
+    return total + 1;
+}
+
+static void scan_exclusive(uint32_t* data, uint32_t count, uint32_t* scratch, cudaStream_t stream)
+{
+    if (count <= kScanTile) {
+        scan_kernel<<<1, 1024, 0, stream>>>(data, count);
+        return;
+    }
+    const uint32_t tiles = (count + kScanTile - 1) / kScanTile;
+    scan_tiles_kernel<<<tiles, 1024, 0, stream>>>(data, count, scratch);
+    scan_exclusive(scratch, tiles, scratch + tiles, stream);
+    scan_add_kernel<<<tiles, 1024, 0, stream>>>(data, count, scratch);
+}
+
 // Ranked, stable scatter.  Warp w of a block owns the contiguous chunk [w*256, (w+1)*256) of the block's
 // tile and walks it in rounds of 32 consecutive keys, so (block, warp, round, lane) is the input order.
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const uint32_t* __restrict__ keys_in,
@@ -556,6 +632,12 @@ __global__ void __launch_bounds__(256) ploc_emit_kernel(int c, const int* __rest
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 // Builds every device array of `s` from the uploaded inputs.  All work is enqueued on `stream`.
+size_t lbvh_scan_scratch_entries(size_t n_tris)
+{
+    const size_t n_blocks = (n_tris + kSortTile - 1) / kSortTile;
+    return scan_scratch_entries(std::max<size_t>(256 * n_blocks, n_tris + 1));
+}
+
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream)
 {
     const uint32_t n = s.n_tris;
@@ -571,7 +653,7 @@ cudaError_t lbvh_build(Scene& s, cudaStream_t stream)
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
         sort_hist_kernel<<<n_blocks, kSortThreads, 0, stream>>>(s.d_keys[src], n, shift, s.d_block_hist, n_blocks);
-        scan_kernel<<<1, 1024, 0, stream>>>(s.d_block_hist, 256u * n_blocks);
+        scan_exclusive(s.d_block_hist, 256u * n_blocks, s.d_scan_scratch, stream);
         sort_scatter_kernel<<<n_blocks, kSortThreads, 0, stream>>>(s.d_keys[src], s.d_vals[src], s.d_keys[src ^ 1],
                                                                   s.d_vals[src ^ 1], n, shift, s.d_block_hist, n_blocks);
         src ^= 1;
@@ -606,7 +688,7 @@ cudaError_t wide_count(Scene& s, cudaStream_t stream)
     if (n == 0) return cudaSuccess;
     const int n_internal = (int)s.n_nodes;
     wide_mark_kernel<<<div_up(n_internal + 1, 256), 256, 0, stream>>>(n_internal, s.d_node_parent, s.d_visit, s.d_wide_index);
-    scan_kernel<<<1, 1024, 0, stream>>>(s.d_wide_index, (uint32_t)n_internal + 1u);
+    scan_exclusive(s.d_wide_index, (uint32_t)n_internal + 1u, s.d_scan_scratch, stream);
     return cudaGetLastError();
 }
 
@@ -654,8 +736,8 @@ cudaError_t ploc_build(Scene& s, cudaStream_t stream)
             }
             ploc_nearest_kernel<<<div_up(c, 256), 256, 0, stream>>>(c, lo[cur], hi[cur], nn);
             ploc_flags_kernel<<<div_up(c + 1, 256), 256, 0, stream>>>(c, nn, keep, make);
-            scan_kernel<<<1, 1024, 0, stream>>>(keep, (uint32_t)c + 1u);
-            scan_kernel<<<1, 1024, 0, stream>>>(make, (uint32_t)c + 1u);
+            scan_exclusive(keep, (uint32_t)c + 1u, s.d_scan_scratch, stream);
+            scan_exclusive(make, (uint32_t)c + 1u, s.d_scan_scratch, stream);
             ploc_emit_kernel<<<div_up(c, 256), 256, 0, stream>>>(c, nn, keep, make, next_id, lo[cur], hi[cur], ref[cur], lo[cur ^ 1],
                                                                 hi[cur ^ 1], ref[cur ^ 1], nodes, node_parent, leaf_parent);
             uint32_t kept = 0, made = 0;

@@ -65,6 +65,7 @@ struct Scene {
     uint32_t* d_vals[2] = {nullptr, nullptr};
     int sorted_buf = 0;
     uint32_t* d_block_hist = nullptr;
+    uint32_t* d_scan_scratch = nullptr;   // tile totals of the multi-block scan (lbvh.cu scan_exclusive)
     int* d_left = nullptr;
     int* d_right = nullptr;
     int* d_node_parent = nullptr;
@@ -136,6 +137,7 @@ inline uint32_t scene_depth(const Scene& s)
 void sah_build_host(const float4* tri_bb, const uint32_t* sorted_prim, uint32_t n, std::vector<float4>& nodes, uint32_t& depth);
 
 // lbvh.cu
+size_t lbvh_scan_scratch_entries(size_t n_tris);
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
 cudaError_t wide_count(Scene& s, cudaStream_t stream);
 cudaError_t wide_emit(Scene& s, cudaStream_t stream);
