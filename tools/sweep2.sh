@@ -1,14 +1,20 @@
 cd /root/repo
-timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "lbvh or ploc or wide_nodes or sah or c4 or traversal_bit" > gpurun_out/pytest_scan.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_scan.log
-tail -5 gpurun_out/pytest_scan.log
 python - <<'PY'
-import sys, time
-sys.path.insert(0, '/root/repo')
-from acgpathtracing_b200 import api, scenes
-for name, arr in (("cornell", scenes.cornell32()), ("material", scenes.material_scene(3)), ("tess300", scenes.tessellated_scene(300)), ("tess1000", scenes.tessellated_scene(1000))):
-    for rep in range(2):
-        t0 = time.time(); gs = api.Scene(arr); dt = time.time() - t0
-        info = gs.info(); p = gs.bvh_export_ploc()
-        print(f"BUILD {name} tris {info['n_tris']} gpu build_ms {info['build_ms']:.3f} (ploc {p['build_ms']:.3f}, depth {p['depth']}) wall create {dt*1e3:.1f} ms tree {gs.tree_in_use()}")
-        gs.destroy()
+import ctypes
+rt = ctypes.CDLL("libcudart.so.12")
+v = ctypes.c_int()
+for name, a in (("MaxPersistingL2CacheSize", 108), ("MaxAccessPolicyWindowSize", 109), ("L2CacheSize", 38)):
+    rt.cudaDeviceGetAttribute(ctypes.byref(v), a, 0); print("ATTR", name, v.value)
 PY
+run() { echo "== $1 PTB_TUNE=$2"; PTB_TUNE=$2 timeout 300 python bench.py --workload $1 --steps $3 --warmup 2 --no-cpu-baseline 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('RESULT', round(d['value'],1), round(d['ms_per_step'],2), round(d['e2e']['value'],1), d['config']['pipeline'])
+    else: print(l.rstrip()[-300:])
+"; }
+run c4 l2_mb=0 2
+run c4 l2_mb=16 2
+run c4 l2_mb=32 2
+run c4 l2_mb=64 2
+run c4 l2_mb=96 2
