@@ -157,6 +157,24 @@ struct StackStrided {    // level-major words, `stride` paths apart (shared memo
     __device__ __forceinline__ int get(int i) const { return base[i * stride]; }
 };
 
+// The first `cap` levels in shared memory as above, deeper levels in a global-memory array (level-major, `ostride`
+// paths apart).  For scenes read from global memory: a traversal rarely defers more than a dozen children, but the
+// stack has to be sized for the tree's depth (36 for the 2 M-triangle PLOC tree) -- kept whole in shared memory it takes
+// half of a path's record and with it a third of the paths a CTA can hold.
+struct StackSpill {
+    int* base;
+    int stride;
+    int cap;
+    int* over;
+    int ostride;
+    __device__ __forceinline__ void put(int i, int v) const
+    {
+        if (i < cap) base[i * stride] = v;
+        else over[(size_t)(i - cap) * ostride] = v;
+    }
+    __device__ __forceinline__ int get(int i) const { return i < cap ? base[i * stride] : over[(size_t)(i - cap) * ostride]; }
+};
+
 struct Ray {
     float3 o, d;
     float3 inv, ood;   // 1/d (|d| clamped away from 0) and o*inv

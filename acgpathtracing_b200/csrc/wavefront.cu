@@ -55,7 +55,9 @@ enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3, MOD
 
 struct WfConst {
     uint32_t np;             // paths per CTA
-    uint32_t stack_depth;    // words per path
+    uint32_t stack_depth;    // words per path in shared memory
+    uint32_t stack_total;    // words per path the tree can need; levels >= stack_depth live in `stack_over`
+    int* stack_over;         // [stack_total - stack_depth][grid * np], or null
     uint32_t copies_shift;   // staged scene copies = 1 << copies_shift
     int node_steps;          // K: slab-test steps per NODE batch
     int node_keep8;          // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
@@ -134,6 +136,20 @@ __device__ __forceinline__ void wf_push(uint32_t* mask, int stage, int lane, int
 // SCENE = -1: scene records in global memory; SCENE = s >= 0: 1 << s interleaved copies staged in shared memory
 template <int SCENE> struct WfFetch { typedef FetchSharedBanked<SCENE> type; };
 template <> struct WfFetch<-1> { typedef FetchGlobal type; };
+
+// traversal stack of a path: whole in shared memory when the scene is staged there (shallow trees), else the first
+// wc.stack_depth levels in shared memory and the rest in global memory
+template <int SCENE> struct WfStack {
+    typedef StackStrided type;
+    static __device__ __forceinline__ type make(int* stack_mem, int pid, uint32_t np, const WfConst&) { return type{stack_mem + pid, (int)np}; }
+};
+template <> struct WfStack<-1> {
+    typedef StackSpill type;
+    static __device__ __forceinline__ type make(int* stack_mem, int pid, uint32_t np, const WfConst& wc)
+    {
+        return type{stack_mem + pid, (int)np, (int)wc.stack_depth, wc.stack_over + (size_t)blockIdx.x * np + pid, (int)(gridDim.x * np)};
+    }
+};
 
 __device__ __forceinline__ float4 pack(float3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
 __device__ __forceinline__ float3 xyz(float4 v) { return make_float3(v.x, v.y, v.z); }
@@ -348,7 +364,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 t.sp = spm & 0xff;
                 mode = spm >> 8;
             }
-            const StackStrided stack{stack_mem + pid, (int)NP};
+            const typename WfStack<SCENE>::type stack = WfStack<SCENE>::make(stack_mem, pid, NP, wc);
             for (;;) {
                 const bool at_node = t.cur >= 0;
                 const bool at_leaf = t.cur < 0 && t.cur != kTravDone;
@@ -393,7 +409,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 t.sp = spm & 0xff;
                 mode = spm >> 8;
             }
-            const StackStrided stack{stack_mem + pid, (int)NP};
+            const typename WfStack<SCENE>::type stack = WfStack<SCENE>::make(stack_mem, pid, NP, wc);
             const int n0 = __popc(__ballot_sync(kFull, active));
             if (COUNT) st_batches[ST_NODE]++, st_lanes[ST_NODE] += n0;
             for (int step = 0; step < wc.node_steps; ++step) {
@@ -450,7 +466,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 const int spm = __float_as_int(ts.w);
                 t.sp = spm & 0xff;
                 const int mode = spm >> 8;
-                const StackStrided stack{stack_mem + pid, (int)NP};
+                const typename WfStack<SCENE>::type stack = WfStack<SCENE>::make(stack_mem, pid, NP, wc);
                 if (COUNT) ctr.n_tri++;
                 trav_leaf_step(t, stack, f, mode == MODE_SHADOW, 0.01f, 1e16f);
                 TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(t.cur), __int_as_float(t.sp | (mode << 8)));
@@ -785,6 +801,7 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
         if (tune.paths32 >= 1 && (uint32_t)tune.paths32 < P) P = (uint32_t)tune.paths32;
         wc.np = 32 * P;
         wc.stack_depth = depth;
+        wc.stack_total = depth;
         wc.copies_shift = (uint32_t)shift;
         smem_bytes = fixed + wc.np * per_path + scene_bytes;
         smem_scene = true;
@@ -799,7 +816,9 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
         trav = TRAV_DIRECT;
         depth = scene_depth(s) + 1u;
     }
-    const size_t per_path_g = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;
+    // shared-memory part of the stack: tune.stack_smem levels (deeper ones spill to global memory, StackSpill)
+    const uint32_t smem_levels = (tune.stack_smem >= 2 && (uint32_t)tune.stack_smem < depth) ? (uint32_t)tune.stack_smem : depth;
+    const size_t per_path_g = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)smem_levels;
     const size_t per_warp = trav == TRAV_COOP ? (size_t)kStageF4 * 16 : 0;   // staging buffer of the cooperative fetch
     const size_t budget = (size_t)(tune.smem_kb >= 32 && tune.smem_kb <= 227 ? tune.smem_kb : 200) * 1024;
     uint32_t P = (uint32_t)((budget - fixed) / (32 * per_path_g + per_warp));
@@ -807,7 +826,8 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
     if (tune.paths32 >= 1 && (uint32_t)tune.paths32 < P) P = (uint32_t)tune.paths32;
     if (P < 4 && tune.paths32 < 1) return false;
     wc.np = 32 * P;
-    wc.stack_depth = depth;
+    wc.stack_depth = smem_levels;
+    wc.stack_total = depth;
     wc.copies_shift = 0;
     smem_bytes = fixed + wc.np * per_path_g + (P < 24u ? P : 24u) * per_warp;
     smem_scene = false;
@@ -839,7 +859,8 @@ static WfTune tuned(const WfTune& base)
                                {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
                                {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
                                {"wide", &WfTune::wide},             {"coop", &WfTune::coop},
-                               {"idle_ns", &WfTune::idle_ns}};
+                               {"idle_ns", &WfTune::idle_ns},
+                               {"stack_smem", &WfTune::stack_smem}};
     std::string str(env);
     size_t pos = 0;
     while (pos < str.size()) {
@@ -871,6 +892,21 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     wc.miss_loop = tune.miss_loop;
     wc.block_override = tune.block;
     wc.idle_ns = tune.idle_ns;
+    wc.stack_over = nullptr;
+    if (!smem_scene && wc.stack_total > wc.stack_depth) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t need = (size_t)(wc.stack_total - wc.stack_depth) * wc.np * (size_t)sms;
+        if (s.stack_over_capacity < need) {
+            if (s.d_stack_over) cudaFree(s.d_stack_over);
+            s.d_stack_over = nullptr;
+            s.stack_over_capacity = 0;
+            if (cudaMalloc((void**)&s.d_stack_over, need * sizeof(int)) != cudaSuccess) return cudaErrorMemoryAllocation;
+            s.stack_over_capacity = need;
+        }
+        wc.stack_over = s.d_stack_over;
+    }
     const bool count = s.count_enabled;
     const int scene = smem_scene ? (int)wc.copies_shift : -1;
     // Per-pixel candidate lists for camera rays: only where building one (a loop over all triangles per pixel) is

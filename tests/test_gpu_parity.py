@@ -826,3 +826,27 @@ def test_ploc_tree_bit_exact(api, port, scenes_cache, name):
     assert g["depth"] == o["depth"]
     assert np.array_equal(gn, on)
     assert gs.tree_in_use() == osc.set_tree(0) == ("sah" if arr.n_tri <= 8192 else "ploc")
+
+
+@pytest.mark.parametrize("name,w,h,spp,md", [("material", 160, 90, 6, 28), ("tess40", 160, 90, 4, 8), ("tess300", 128, 72, 3, 8)])
+@pytest.mark.parametrize("levels", [2, 5, 0])
+def test_stack_spill_same_pixels(api, port, scenes_cache, monkeypatch, name, w, h, spp, md, levels):
+    """Scenes read from global memory keep only the first levels of a path's traversal stack in shared memory (12 by
+    default) and spill deeper ones to global memory; forced down to 2 and 5 levels (and with no spill at all) the pixels
+    and the work counters are still the oracle's."""
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    p = api.make_params(w, h, spp, md, frame=1, nee=True, importance=True, scene=gs)
+    o = osc.render(p, math_mode=1, use_bvh=True)
+    monkeypatch.setenv("PTB_TUNE", f"stack_smem={levels}")
+    try:
+        gs.set_traversal(3 if name == "material" else 0)          # material (672 triangles) would be staged in shared memory
+        g = gs.launch_host(p)
+        assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32))
+        gs.enable_counters(True)
+        gs.counters(reset=True)
+        g = gs.launch_host(p)
+        assert gs.counters(reset=True) == o["counters"]
+        assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32))
+    finally:
+        gs.enable_counters(False)
+        gs.set_traversal(0)
