@@ -748,6 +748,18 @@ def test_wide_traversal_single_triangle_and_soups(api, port):
                 g = gs.launch_host(p)
                 assert gs.last_launch_info()["traversal"] == expect
                 assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (n_tri, trav)
+            if n_tri >= 2:                                   # the three trees of a tiny scene: same pixels, PLOC == oracle's
+                gp, op = gs.bvh_export_ploc(), osc.bvh_ploc()
+                a, b = gp["nodes"].copy(), op["nodes"].copy()
+                a[:, [11, 15]] = 0
+                b[:, [11, 15]] = 0
+                assert gp["depth"] == op["depth"] and np.array_equal(a, b), n_tri
+                gs.set_traversal(0)
+                for tree in (1, 2, 3):
+                    gs.set_tree(tree)
+                    g = gs.launch_host(p)
+                    assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (n_tri, tree)
+                gs.set_tree(0)
             # counted launches with the cooperative fetch report the binary traversal's work counters
             gs.set_traversal(3)
             gs.enable_counters(True)
