@@ -550,11 +550,18 @@ __global__ void __launch_bounds__(256) ploc_init_kernel(uint32_t n, const float4
     ref[i] = ~(int)i;
 }
 
-__global__ void __launch_bounds__(256) ploc_nearest_kernel(int c, const float4* __restrict__ lo, const float4* __restrict__ hi,
-                                                           int* __restrict__ nn)
+// The round kernels take the cluster count c and the next node id from device memory (state[0], state[1]): the host
+// enqueues several rounds back to back with grids sized for the last count it knows and reads the state only every
+// kPlocRoundsPerSync rounds -- a read-back per round made the build time hostage to the host's sync latency (10 ms on one
+// box, 300 ms on another).  Rounds enqueued after the last merge find c == 1 and do nothing.
+constexpr int kPlocRoundsPerSync = 8;
+
+__global__ void __launch_bounds__(256) ploc_nearest_kernel(const int* __restrict__ state, const float4* __restrict__ lo,
+                                                           const float4* __restrict__ hi, int* __restrict__ nn)
 {
+    const int c = state[0];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c) return;
+    if (c <= 1 || i >= c) return;
     const float4 lo_i = lo[i], hi_i = hi[i];
     const int first = max(0, i - kPlocRadius), last = min(c - 1, i + kPlocRadius);
     int best_j = i > 0 ? i - 1 : i + 1;                  // never left undecided, whatever the boxes hold
@@ -571,32 +578,46 @@ __global__ void __launch_bounds__(256) ploc_nearest_kernel(int c, const float4* 
 }
 
 // keep[i]: cluster i survives the round (at its compacted position); make[i]: i is the lower index of a merging pair
-__global__ void __launch_bounds__(256) ploc_flags_kernel(int c, const int* __restrict__ nn, uint32_t* __restrict__ keep,
-                                                         uint32_t* __restrict__ make)
+__global__ void __launch_bounds__(256) ploc_flags_kernel(const int* __restrict__ state, int c_upper, const int* __restrict__ nn,
+                                                         uint32_t* __restrict__ keep, uint32_t* __restrict__ make)
 {
+    const int c = state[0];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > c) return;
+    if (i > c_upper) return;
     uint32_t k = 0u, m = 0u;
-    if (i < c) {
+    if (c > 1 && i < c) {
         const int j = nn[i];
         const bool mutual = nn[j] == i;
         k = (mutual && i > j) ? 0u : 1u;
         m = (mutual && i < j) ? 1u : 0u;
     }
-    keep[i] = k;      // entry c stays 0: after the exclusive scans it holds the totals
+    keep[i] = k;      // entries c .. c_upper stay 0: after the exclusive scans entry c holds the totals
     make[i] = m;
 }
 
-__global__ void __launch_bounds__(256) ploc_emit_kernel(int c, const int* __restrict__ nn, const uint32_t* __restrict__ pos,
-                                                        const uint32_t* __restrict__ rank, int next_id,
+// one thread: next round's cluster count and node id
+__global__ void ploc_advance_kernel(int* __restrict__ state, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ make)
+{
+    const int c = state[0];
+    if (c <= 1) return;
+    const uint32_t kept = keep[c], made = make[c];
+    if (made == 0u || kept + made != (uint32_t)c) state[3] = 1;      // cannot happen: every round merges at least one pair
+    state[0] = made == 0u ? 1 : (int)kept;
+    state[1] -= (int)made;
+    state[2] += 1;
+}
+
+__global__ void __launch_bounds__(256) ploc_emit_kernel(const int* __restrict__ state, const int* __restrict__ nn,
+                                                        const uint32_t* __restrict__ pos, const uint32_t* __restrict__ rank,
                                                         const float4* __restrict__ lo_in, const float4* __restrict__ hi_in,
                                                         const int* __restrict__ ref_in, float4* __restrict__ lo_out,
                                                         float4* __restrict__ hi_out, int* __restrict__ ref_out,
                                                         float4* __restrict__ nodes, int* __restrict__ node_parent,
                                                         int* __restrict__ leaf_parent)
 {
+    const int c = state[0], next_id = state[1];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c) return;
+    if (c <= 1 || i >= c) return;
     const int j = nn[i];
     const bool mutual = nn[j] == i;
     if (mutual && i > j) return;                         // absorbed by cluster j
@@ -709,49 +730,62 @@ cudaError_t ploc_build(Scene& s, cudaStream_t stream)
     float4 *lo[2] = {nullptr, nullptr}, *hi[2] = {nullptr, nullptr}, *nodes = nullptr;
     int *ref[2] = {nullptr, nullptr}, *nn = nullptr, *node_parent = nullptr, *leaf_parent = nullptr;
     uint32_t *keep = nullptr, *make = nullptr;
+    int* state = nullptr;                                // [0] clusters left  [1] next node id  [2] rounds done  [3] error
     cudaError_t e = cudaSuccess;
     auto A = [&](cudaError_t r) {
         if (e == cudaSuccess) e = r;
     };
-    for (int b = 0; b < 2; ++b) {
-        A(cudaMalloc((void**)&lo[b], sizeof(float4) * n));
-        A(cudaMalloc((void**)&hi[b], sizeof(float4) * n));
-        A(cudaMalloc((void**)&ref[b], sizeof(int) * n));
-    }
-    A(cudaMalloc((void**)&nn, sizeof(int) * n));
-    A(cudaMalloc((void**)&keep, sizeof(uint32_t) * ((size_t)n + 1)));
-    A(cudaMalloc((void**)&make, sizeof(uint32_t) * ((size_t)n + 1)));
-    A(cudaMalloc((void**)&node_parent, sizeof(int) * n));
-    A(cudaMalloc((void**)&leaf_parent, sizeof(int) * n));
+    // one arena for the scratch arrays (a dozen separate cudaMalloc / cudaFree pairs cost more than the build)
+    char* arena = nullptr;
+    size_t arena_bytes = 0;
+    auto carve = [&](size_t bytes) {
+        const size_t off = arena_bytes;
+        arena_bytes += (bytes + 255) & ~(size_t)255;
+        return off;
+    };
+    const size_t o_lo0 = carve(sizeof(float4) * n), o_lo1 = carve(sizeof(float4) * n), o_hi0 = carve(sizeof(float4) * n),
+                 o_hi1 = carve(sizeof(float4) * n), o_ref0 = carve(sizeof(int) * n), o_ref1 = carve(sizeof(int) * n),
+                 o_nn = carve(sizeof(int) * n), o_state = carve(sizeof(int) * 4), o_keep = carve(sizeof(uint32_t) * ((size_t)n + 1)),
+                 o_make = carve(sizeof(uint32_t) * ((size_t)n + 1)), o_np = carve(sizeof(int) * n), o_lp = carve(sizeof(int) * n);
+    A(cudaMalloc((void**)&arena, arena_bytes));
     A(cudaMalloc((void**)&nodes, sizeof(float4) * 4 * ((size_t)n - 1)));
+    if (e == cudaSuccess) {
+        lo[0] = (float4*)(arena + o_lo0), lo[1] = (float4*)(arena + o_lo1), hi[0] = (float4*)(arena + o_hi0), hi[1] = (float4*)(arena + o_hi1);
+        ref[0] = (int*)(arena + o_ref0), ref[1] = (int*)(arena + o_ref1), nn = (int*)(arena + o_nn), state = (int*)(arena + o_state);
+        keep = (uint32_t*)(arena + o_keep), make = (uint32_t*)(arena + o_make);
+        node_parent = (int*)(arena + o_np), leaf_parent = (int*)(arena + o_lp);
+    }
     bool ok = e == cudaSuccess;
     uint32_t depth = 0;
     if (ok) {
         ploc_init_kernel<<<div_up(n, 256), 256, 0, stream>>>(n, s.d_tri_bb, s.d_vals[s.sorted_buf], lo[0], hi[0], ref[0]);
-        int c = (int)n, next_id = (int)n - 2, cur = 0;
-        for (int round = 0; c > 1 && ok; ++round) {
-            if (round > 100000) {                        // cannot happen (every round merges at least one pair)
+        int h_state[4] = {(int)n, (int)n - 2, 0, 0};
+        A(cudaMemcpyAsync(state, h_state, sizeof(h_state), cudaMemcpyHostToDevice, stream));
+        int c_upper = (int)n, cur = 0;
+        for (int batch = 0; c_upper > 1 && ok; ++batch) {
+            if (batch > 100000) {
                 ok = false;
                 break;
             }
-            ploc_nearest_kernel<<<div_up(c, 256), 256, 0, stream>>>(c, lo[cur], hi[cur], nn);
-            ploc_flags_kernel<<<div_up(c + 1, 256), 256, 0, stream>>>(c, nn, keep, make);
-            scan_exclusive(keep, (uint32_t)c + 1u, s.d_scan_scratch, stream);
-            scan_exclusive(make, (uint32_t)c + 1u, s.d_scan_scratch, stream);
-            ploc_emit_kernel<<<div_up(c, 256), 256, 0, stream>>>(c, nn, keep, make, next_id, lo[cur], hi[cur], ref[cur], lo[cur ^ 1],
-                                                                hi[cur ^ 1], ref[cur ^ 1], nodes, node_parent, leaf_parent);
-            uint32_t kept = 0, made = 0;
-            A(cudaMemcpyAsync(&kept, keep + c, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            A(cudaMemcpyAsync(&made, make + c, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            for (int r = 0; r < kPlocRoundsPerSync; ++r) {
+                ploc_nearest_kernel<<<div_up(c_upper, 256), 256, 0, stream>>>(state, lo[cur], hi[cur], nn);
+                ploc_flags_kernel<<<div_up(c_upper + 1, 256), 256, 0, stream>>>(state, c_upper, nn, keep, make);
+                scan_exclusive(keep, (uint32_t)c_upper + 1u, s.d_scan_scratch, stream);
+                scan_exclusive(make, (uint32_t)c_upper + 1u, s.d_scan_scratch, stream);
+                ploc_emit_kernel<<<div_up(c_upper, 256), 256, 0, stream>>>(state, nn, keep, make, lo[cur], hi[cur], ref[cur], lo[cur ^ 1],
+                                                                          hi[cur ^ 1], ref[cur ^ 1], nodes, node_parent, leaf_parent);
+                ploc_advance_kernel<<<1, 1, 0, stream>>>(state, keep, make);
+                cur ^= 1;
+            }
+            A(cudaMemcpyAsync(h_state, state, sizeof(h_state), cudaMemcpyDeviceToHost, stream));
             A(cudaStreamSynchronize(stream));
-            if (e != cudaSuccess || made == 0 || kept + made != (uint32_t)c) {
+            if (e != cudaSuccess || h_state[3] != 0) {
                 ok = false;
                 break;
             }
-            next_id -= (int)made;
-            c = (int)kept;
-            cur ^= 1;
+            c_upper = h_state[0];
         }
+        const int next_id = h_state[1];
         if (ok && next_id != -1) ok = false;
         if (ok) {
             const int root_parent = -1;
@@ -764,9 +798,7 @@ cudaError_t ploc_build(Scene& s, cudaStream_t stream)
             ok = e == cudaSuccess;
         }
     }
-    void* scratch[] = {lo[0], lo[1], hi[0], hi[1], ref[0], ref[1], nn, keep, make, node_parent, leaf_parent};
-    for (void* p : scratch)
-        if (p) cudaFree(p);
+    if (arena) cudaFree(arena);
     if (ok) {
         s.d_nodes_ploc = nodes;
         s.ploc_depth = depth;
