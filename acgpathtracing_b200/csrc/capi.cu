@@ -455,6 +455,8 @@ int pt_scene_set_tree(pt_scene* scene, int tree)
     if (tree < 0 || tree > 3) return fail(PT_ERR_INVALID, "tree must be 0, 1, 2 or 3");
     if (tree == 2 && !s->d_nodes_sah && s->n_tris >= 2) return fail(PT_ERR_INVALID, "no SAH tree for this scene (more than 8192 triangles)");
     if (tree == 3 && !s->d_nodes_ploc && s->n_tris >= 2) return fail(PT_ERR_INVALID, "no PLOC tree for this scene");
+    if ((tree == 2 && s->d_nodes_sah && s->sah_depth > kSahMaxDepth) || (tree == 3 && s->d_nodes_ploc && s->ploc_depth > kSahMaxDepth))
+        return fail(PT_ERR_INVALID, "that tree is more than 64 levels deep for this scene (degenerate input); the LBVH stays in use");
     s->tree = tree;
     return PT_OK;
 }

@@ -120,8 +120,10 @@ constexpr uint32_t kSahMaxDepth = 64;
 // (2..kSahMaxTris triangles), else the GPU-built PLOC tree, else the LBVH; a tree deeper than kSahMaxDepth is passed over.
 inline int scene_tree(const Scene& s)
 {
-    if (s.tree == 2 && s.d_nodes_sah) return 2;
-    if (s.tree == 3 && s.d_nodes_ploc) return 3;
+    // (pt_scene_set_tree refuses a tree deeper than kSahMaxDepth: the traversal stacks of the fallback and trace
+    // kernels hold 64 entries, which bounds the LBVH -- 62-bit keys -- but not a SAH or PLOC tree of degenerate input)
+    if (s.tree == 2 && s.d_nodes_sah && s.sah_depth <= kSahMaxDepth) return 2;
+    if (s.tree == 3 && s.d_nodes_ploc && s.ploc_depth <= kSahMaxDepth) return 3;
     if (s.tree != 0) return 1;
     if (s.d_nodes_sah && s.sah_depth <= kSahMaxDepth) return 2;
     if (s.d_nodes_ploc && s.ploc_depth <= kSahMaxDepth) return 3;

@@ -132,7 +132,7 @@ int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
  *   3 = a PLOC tree (parallel locally-ordered clustering, radius 8), built on the GPU for every scene of >= 2
  *       triangles (22-27 % fewer node visits on the 2 M-triangle scene);
  *   0 = auto: 2 where it exists, else 3, else 1 (a tree more than 64 levels deep is passed over).
- * Asking for a tree the scene does not have is PT_ERR_INVALID.  Replaces the build flags of optixAccelBuild
+ * Asking for a tree the scene does not have, or one deeper than 64 levels, is PT_ERR_INVALID.  Replaces the build flags of optixAccelBuild
  * (PathTracerMain.cpp:334-339). */
 int pt_scene_set_tree(pt_scene* scene, int tree);
 int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH, 3 PLOC */

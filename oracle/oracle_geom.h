@@ -512,13 +512,13 @@ static inline void sah_build(Lbvh& b)
 }
 
 // The library's rule (csrc/pt_scene.h scene_tree): tree = 0 auto (SAH where there is one, else PLOC, else LBVH; a tree
-// deeper than 64 is passed over), 1 LBVH, 2 SAH, 3 PLOC.  Returns the tree in use (1 / 2 / 3).
+// deeper than 64 is passed over, also when asked for by name), 1 LBVH, 2 SAH, 3 PLOC.  Returns the tree in use (1 / 2 / 3).
 static inline int select_tree(Lbvh& b, int tree)
 {
     const bool have_sah = !b.sah_nodes.empty(), have_ploc = !b.ploc_nodes.empty();
     int t = 1;
-    if (tree == 2 && have_sah) t = 2;
-    else if (tree == 3 && have_ploc) t = 3;
+    if (tree == 2 && have_sah && b.sah_depth <= kSahMaxDepth) t = 2;
+    else if (tree == 3 && have_ploc && b.ploc_depth <= kSahMaxDepth) t = 3;
     else if (tree == 0) {
         if (have_sah && b.sah_depth <= kSahMaxDepth) t = 2;
         else if (have_ploc && b.ploc_depth <= kSahMaxDepth) t = 3;

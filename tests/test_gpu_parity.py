@@ -862,3 +862,50 @@ def test_stack_spill_same_pixels(api, port, scenes_cache, monkeypatch, name, w, 
     finally:
         gs.enable_counters(False)
         gs.set_traversal(0)
+
+
+def _degenerate_scene(kind):
+    """Inputs that stress tie-breaking in the tree builders: equal Morton keys, equal SAH costs, equal PLOC areas."""
+    rng = np.random.default_rng(3)
+    tri = np.array([[100, 100, 300], [450, 120, 320], [280, 480, 340]], np.float32)
+    if kind == "copies":                      # 300 copies of one triangle
+        v = np.tile(tri, (300, 1))
+    elif kind == "stack":                     # 200 parallel copies, shifted along z by multiples of an ulp-sized step
+        v = np.concatenate([tri + np.array([0, 0, 0.5 * k], np.float32) for k in range(200)])
+    else:                                     # zero-area triangles (points, segments) mixed with real ones
+        v = rng.uniform(50, 500, (450, 3)).astype(np.float32)
+        v[0:90] = v[0]                        # 30 triangles collapsed to one point
+        v[91::3][:40] = v[90::3][:40]         # segments
+    v4 = np.ones((v.shape[0], 4), np.float32)
+    v4[:, :3] = v
+    n = v.shape[0] // 3
+    mats = [dict(name="white", Kd=(0.8, 0.8, 0.8), Ke=(0, 0, 0)), dict(name="RefractiveThing", Kd=(1, 1, 1), Ke=(0, 0, 0), Ni=1.5)]
+    return S.SceneArrays(verts=v4, indices=np.arange(3 * n, dtype=np.uint32).reshape(n, 3),
+                         mat_ids=(np.arange(n) % 2).astype(np.uint32), materials=mats, name=kind)
+
+
+@pytest.mark.parametrize("kind", ["copies", "stack", "flat"])
+def test_degenerate_scenes_all_trees(api, port, kind):
+    arr = _degenerate_scene(kind)
+    gs, osc = api.Scene(arr), O.OracleScene(port, arr)
+    try:
+        for exp_g, exp_o in ((gs.bvh_export_sah(), osc.bvh_sah()), (gs.bvh_export_ploc(), osc.bvh_ploc())):
+            a, b = exp_g["nodes"].copy(), exp_o["nodes"].copy()
+            a[:, [11, 15]] = 0
+            b[:, [11, 15]] = 0
+            assert exp_g["depth"] == exp_o["depth"] and np.array_equal(a, b)
+        p = api.make_params(96, 54, 3, 12, frame=0, nee=True, scene=gs)
+        for tree in (0, 1, 2, 3):
+            for trav in (0, 3):
+                used = osc.set_tree(tree)
+                try:
+                    gs.set_tree(tree)
+                except api.PtError:                  # a tree deeper than 64 levels (300 copies of one triangle) is refused
+                    assert used == "lbvh" and tree in (2, 3)
+                    gs.set_tree(1)
+                gs.set_traversal(trav)
+                assert gs.tree_in_use() == used
+                g, o = gs.launch_host(p), osc.render(p, math_mode=1, use_bvh=True)
+                assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (kind, tree, trav)
+    finally:
+        gs.destroy()
