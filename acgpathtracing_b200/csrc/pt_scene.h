@@ -21,8 +21,11 @@ constexpr uint64_t kSceneMagic = 0x5054423230305343ull;   // "PTB200SC"
 // PTB_TUNE="key=value,..." overrides them per process for experiments (wavefront.cu wavefront_launch).
 struct WfTune {
     int node_votes = 6;      // votes (of two slab-test steps each) per NODE batch
+    int node_votes_g = 3;    // ... for scenes read from global memory: shorter batches regroup more often, which keeps more lanes
+                             // (and more loads) in flight where a step is a cache miss (C4: 1396 -> 1519 with full_cols_g = 28)
     int node_keep8 = 2;      // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
     int full_cols = 32;      // a downstream stage is taken as soon as this many columns have a waiting path
+    int full_cols_g = 28;    // ... for scenes read from global memory
     int sticky = 4;          // repeats of the same stage without a full vote while it fills the whole warp
     int tail_cols = 24;      // tail mode when the non-empty columns of all queues add up to at most this
     int miss_loop = 16;      // samples of an all-miss pixel finished per END visit

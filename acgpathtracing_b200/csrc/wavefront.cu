@@ -853,7 +853,8 @@ static WfTune tuned(const WfTune& base)
         const char* name;
         int WfTune::*field;
     };
-    static const Key keys[] = {{"node_votes", &WfTune::node_votes}, {"node_keep8", &WfTune::node_keep8},
+    static const Key keys[] = {{"node_votes_g", &WfTune::node_votes_g}, {"full_cols_g", &WfTune::full_cols_g},
+                               {"node_votes", &WfTune::node_votes}, {"node_keep8", &WfTune::node_keep8},
                                {"full_cols", &WfTune::full_cols},   {"sticky", &WfTune::sticky},
                                {"tail_cols", &WfTune::tail_cols},   {"miss_loop", &WfTune::miss_loop},
                                {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
@@ -873,6 +874,9 @@ static WfTune tuned(const WfTune& base)
                 if (item.compare(0, eq, k.name) == 0 && eq == strlen(k.name)) t.*(k.field) = atoi(item.c_str() + eq + 1);
         pos = end + 1;
     }
+    // "node_votes=" / "full_cols=" without their "_g" twins apply to every scene (sweeps)
+    if (str.find("node_votes=") != std::string::npos && str.find("node_votes_g=") == std::string::npos) t.node_votes_g = t.node_votes;
+    if (str.find("full_cols=") != std::string::npos && str.find("full_cols_g=") == std::string::npos) t.full_cols_g = t.full_cols;
     return t;
 }
 
@@ -884,9 +888,9 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     bool smem_scene = false;
     int trav = TRAV_DIRECT;
     if (!wavefront_plan(s, tune, wc, smem_bytes, smem_scene, trav)) return cudaErrorInvalidConfiguration;
-    wc.node_steps = tune.node_votes;
+    wc.node_steps = smem_scene ? tune.node_votes : tune.node_votes_g;
     wc.node_keep8 = tune.node_keep8;
-    wc.full_cols = tune.full_cols;
+    wc.full_cols = smem_scene ? tune.full_cols : tune.full_cols_g;
     wc.sticky = tune.sticky;
     wc.tail_cols = tune.tail_cols;
     wc.miss_loop = tune.miss_loop;
