@@ -263,7 +263,7 @@ class Scene:
         g, b, s, k = (C.c_uint32() for _ in range(4))
         _check(lib.pt_scene_last_launch_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(k)))
         return dict(grid=g.value, block=b.value, smem_bytes=s.value, kernels=k.value,
-                    traversal={0: "binary", 1: "wide", 2: "binary-coop"}.get(lib.pt_scene_last_traversal(self._h), "?"))
+                    traversal={0: "binary", 1: "wide", 2: "binary-coop", 3: "binary-quant"}.get(lib.pt_scene_last_traversal(self._h), "?"))
 
     def bvh_export_wide(self):
         """Wide nodes (two LBVH levels per 128-byte record): dict(n_wide, wide_index[n_nodes], wnodes[n_wide, 32] u32)."""

@@ -72,7 +72,7 @@ static void scene_free(Scene* s)
     void* ptrs[] = {s->d_verts, s->d_indices, s->d_mat_ids, s->d_mats, s->d_tri_in, s->d_tri_bb, s->d_tri_shade,
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_scan_scratch, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
-                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
+                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_qnodes, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
                     s->d_tile_order, s->d_stack_over};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -443,7 +443,7 @@ int pt_scene_set_traversal(pt_scene* scene, int traversal)
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
-    if (traversal < 0 || traversal > 3) return fail(PT_ERR_INVALID, "traversal must be 0, 1, 2 or 3");
+    if (traversal < 0 || traversal > 4) return fail(PT_ERR_INVALID, "traversal must be 0 .. 4");
     s->traversal = traversal;
     return PT_OK;
 }

@@ -12,6 +12,7 @@
 //   refit       bottom-up AABB union with per-node arrival counters (fmin/fmax are order-independent)
 //   pack        64-byte two-child nodes + 48-byte triangle records in leaf order
 #include <cuda_runtime.h>
+#include <math.h>
 #include <float.h>
 #include <stdint.h>
 
@@ -644,6 +645,50 @@ __global__ void __launch_bounds__(256) ploc_emit_kernel(const int* __restrict__ 
     ref_out[p] = id;
 }
 
+// ---- quantised nodes: 32 bytes per node for scenes that are read from global memory ------------------------------------
+// Twelve 16-bit plane positions on the grid  lo + q * step  of the scene's bounding box and the two child references (layout:
+// pt_device.cuh FetchGlobal::qnode4).  lo planes are rounded down, hi planes up, and the rounding is CHECKED with the very
+// expression the traversal evaluates (one fused multiply-add), so a quantised box always contains the exact one: the
+// traversal reaches a superset of the leaves and the hits -- which come from the exact triangle records -- cannot change.
+__device__ __forceinline__ uint32_t quant_down(float x, float lo, float step)
+{
+    float t = floorf((x - lo) / step);
+    t = fminf(fmaxf(t, 0.0f), 65535.0f);
+    uint32_t q = (uint32_t)t;
+    while (q > 0u && __fmaf_rn((float)q, step, lo) > x) --q;
+    return q;
+}
+__device__ __forceinline__ uint32_t quant_up(float x, float lo, float step)
+{
+    float t = ceilf((x - lo) / step);
+    t = fminf(fmaxf(t, 0.0f), 65535.0f);
+    uint32_t q = (uint32_t)t;
+    while (q < 65535u && __fmaf_rn((float)q, step, lo) < x) ++q;
+    return q;
+}
+
+__global__ void __launch_bounds__(256) quantize_nodes_kernel(int n_internal, const float4* __restrict__ nodes, float3 lo, float3 step,
+                                                             uint4* __restrict__ qnodes, uint32_t* __restrict__ bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_internal) return;
+    const float4 q0 = nodes[4 * (size_t)i + 0], q1 = nodes[4 * (size_t)i + 1], q2 = nodes[4 * (size_t)i + 2], q3 = nodes[4 * (size_t)i + 3];
+    const uint32_t l0x = quant_down(q0.x, lo.x, step.x), l0y = quant_down(q0.y, lo.y, step.y), l0z = quant_down(q0.z, lo.z, step.z);
+    const uint32_t h0x = quant_up(q1.x, lo.x, step.x), h0y = quant_up(q1.y, lo.y, step.y), h0z = quant_up(q1.z, lo.z, step.z);
+    const uint32_t l1x = quant_down(q2.x, lo.x, step.x), l1y = quant_down(q2.y, lo.y, step.y), l1z = quant_down(q2.z, lo.z, step.z);
+    const uint32_t h1x = quant_up(q3.x, lo.x, step.x), h1y = quant_up(q3.y, lo.y, step.y), h1z = quant_up(q3.z, lo.z, step.z);
+    // the guarantee, re-checked: quantised lo <= exact lo and quantised hi >= exact hi on every plane
+    const bool ok = __fmaf_rn((float)l0x, step.x, lo.x) <= q0.x && __fmaf_rn((float)l0y, step.y, lo.y) <= q0.y &&
+                    __fmaf_rn((float)l0z, step.z, lo.z) <= q0.z && __fmaf_rn((float)h0x, step.x, lo.x) >= q1.x &&
+                    __fmaf_rn((float)h0y, step.y, lo.y) >= q1.y && __fmaf_rn((float)h0z, step.z, lo.z) >= q1.z &&
+                    __fmaf_rn((float)l1x, step.x, lo.x) <= q2.x && __fmaf_rn((float)l1y, step.y, lo.y) <= q2.y &&
+                    __fmaf_rn((float)l1z, step.z, lo.z) <= q2.z && __fmaf_rn((float)h1x, step.x, lo.x) >= q3.x &&
+                    __fmaf_rn((float)h1y, step.y, lo.y) >= q3.y && __fmaf_rn((float)h1z, step.z, lo.z) >= q3.z;
+    if (!ok) atomicAdd(bad, 1u);
+    qnodes[2 * (size_t)i + 0] = make_uint4(l0x | (l0y << 16), l0z | (h0x << 16), h0y | (h0z << 16), l1x | (l1y << 16));
+    qnodes[2 * (size_t)i + 1] = make_uint4(l1z | (h1x << 16), h1y | (h1z << 16), __float_as_uint(q0.w), __float_as_uint(q1.w));
+}
+
 #define PTB_CUDA_TRY(expr)                  \
     do {                                    \
         cudaError_t e__ = (expr);           \
@@ -806,6 +851,34 @@ cudaError_t ploc_build(Scene& s, cudaStream_t stream)
         cudaFree(nodes);
     }
     return e;
+}
+
+// Quantised copy of the tree the kernels walk (scene_nodes), rebuilt when that choice changes.  Leaves s.d_qnodes null
+// when a box cannot be contained (never expected: the grid spans the scene's bounding box).
+cudaError_t quantize_nodes(Scene& s, cudaStream_t stream)
+{
+    const int tree = scene_tree(s);
+    if (s.n_tris < 2) return cudaSuccess;
+    if (s.d_qnodes && s.qnodes_tree == tree) return cudaSuccess;
+    if (!s.d_qnodes) PTB_CUDA_TRY(cudaMalloc((void**)&s.d_qnodes, sizeof(uint4) * 2 * (size_t)s.n_nodes));
+    s.qnodes_tree = 0;
+    for (int a = 0; a < 3; ++a) {
+        const float lo = s.h_bounds[a], hi = s.h_bounds[3 + a];
+        float step = (hi - lo) / 65535.0f;
+        if (!(step > 1e-30f)) step = 1e-30f;
+        for (int it = 0; it < 64 && fmaf(65535.0f, step, lo) < hi; ++it) step = nextafterf(step, INFINITY);   // the grid must reach hi
+        s.q_lo[a] = lo;
+        s.q_step[a] = step;
+    }
+    PTB_CUDA_TRY(cudaMemsetAsync(s.d_work_counter + 3, 0, sizeof(uint32_t), stream));
+    quantize_nodes_kernel<<<div_up(s.n_nodes, 256), 256, 0, stream>>>((int)s.n_nodes, scene_nodes(s), make_float3(s.q_lo[0], s.q_lo[1], s.q_lo[2]),
+                                                                      make_float3(s.q_step[0], s.q_step[1], s.q_step[2]),
+                                                                      reinterpret_cast<uint4*>(s.d_qnodes), s.d_work_counter + 3);
+    uint32_t bad = 0;
+    PTB_CUDA_TRY(cudaMemcpyAsync(&bad, s.d_work_counter + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    PTB_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (bad == 0) s.qnodes_tree = tree;
+    return cudaGetLastError();
 }
 
 }  // namespace ptb

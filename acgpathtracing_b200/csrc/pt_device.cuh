@@ -91,6 +91,32 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
 struct FetchGlobal {
     const float4 *nodes, *tris, *shade, *mats;
     const float4* wnodes;   // wide nodes (8 float4 each), or null
+    // quantised nodes (lbvh.cu quantize_nodes_kernel), 32 bytes = one LDG.E.256 per node: twelve 16-bit plane positions on
+    // the scene's bounding-box grid (w0 = lo0.x | lo0.y << 16, w1 = lo0.z | hi0.x << 16, w2 = hi0.y | hi0.z << 16, w3..w5 the
+    // same for child 1) and the two child references (w6, w7).  A plane is q * step + lo in ONE fused multiply-add, the same
+    // expression the build checks its rounding with: lo planes never above, hi planes never below the exact box.
+    const float4* qnodes;
+    float3 q_lo, q_step;
+    __device__ __forceinline__ void qnode4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
+    {
+        float4 a, b;
+        ldg256(qnodes + 2 * (size_t)i, a, b);
+        const uint32_t w0 = __float_as_uint(a.x), w1 = __float_as_uint(a.y), w2 = __float_as_uint(a.z), w3 = __float_as_uint(a.w);
+        const uint32_t w4 = __float_as_uint(b.x), w5 = __float_as_uint(b.y);
+        q0 = make_float4(__fmaf_rn((float)(w0 & 0xffffu), q_step.x, q_lo.x), __fmaf_rn((float)(w0 >> 16), q_step.y, q_lo.y),
+                         __fmaf_rn((float)(w1 & 0xffffu), q_step.z, q_lo.z), b.z);
+        q1 = make_float4(__fmaf_rn((float)(w1 >> 16), q_step.x, q_lo.x), __fmaf_rn((float)(w2 & 0xffffu), q_step.y, q_lo.y),
+                         __fmaf_rn((float)(w2 >> 16), q_step.z, q_lo.z), b.w);
+        q2 = make_float4(__fmaf_rn((float)(w3 & 0xffffu), q_step.x, q_lo.x), __fmaf_rn((float)(w3 >> 16), q_step.y, q_lo.y),
+                         __fmaf_rn((float)(w4 & 0xffffu), q_step.z, q_lo.z), 0.0f);
+        q3 = make_float4(__fmaf_rn((float)(w4 >> 16), q_step.x, q_lo.x), __fmaf_rn((float)(w5 & 0xffffu), q_step.y, q_lo.y),
+                         __fmaf_rn((float)(w5 >> 16), q_step.z, q_lo.z), 0.0f);
+    }
+    __device__ __forceinline__ void prefetch_qchild(int c) const
+    {
+        const void* p = c >= 0 ? (const void*)(qnodes + 2 * (size_t)c) : (const void*)(tris + 3 * (~c));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
     __device__ __forceinline__ void node4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
     {
         ldg256(nodes + 4 * (size_t)i, q0, q1);
@@ -269,7 +295,7 @@ __device__ __forceinline__ void trav_pop(Trav& t, const STK& stack)
 
 // Internal-node step.  Logical visiting order (mirrored by the oracle, which matters only for the work counters):
 // nearer hit child first, child 1 only when strictly nearer.  Uses r.inv / r.ood only.
-template <class FETCH, class STK>
+template <bool QUANT = false, class FETCH, class STK>
 __device__ __forceinline__ void trav_node_apply(Trav& t, const STK& stack, const FETCH& f, float tmin, float4 q0, float4 q1,
                                                 float4 q2, float4 q3)
 {
@@ -288,10 +314,20 @@ __device__ __forceinline__ void trav_node_apply(Trav& t, const STK& stack, const
     const int top = stack.get(can_pop ? t.sp - 1 : 0);
     if (both) {
         stack.put(t.sp, far_child);
-        f.prefetch_child(far_child);
+        if constexpr (QUANT) f.prefetch_qchild(far_child);
+        else f.prefetch_child(far_child);
     }
     t.cur = none ? (can_pop ? top : kTravDone) : near_child;
     t.sp += both ? 1 : ((none && can_pop) ? -1 : 0);
+}
+
+// Node step on the quantised node array (scenes in global memory): one 32-byte fetch per node instead of 64 bytes.
+template <class FETCH, class STK>
+__device__ __forceinline__ void trav_qnode_step(Trav& t, const STK& stack, const FETCH& f, float tmin)
+{
+    float4 q0, q1, q2, q3;
+    f.qnode4(t.cur, q0, q1, q2, q3);
+    trav_node_apply<true>(t, stack, f, tmin, q0, q1, q2, q3);
 }
 
 template <class FETCH, class STK>

@@ -38,6 +38,7 @@ struct WfTune {
     int idle_ns = 64;        // sleep of a warp that found every queue empty
     int stack_smem = 12;     // scenes in global memory: traversal-stack levels kept in shared memory, deeper ones spill to
                              // global memory (0 = all in shared memory).  C4: 672 -> 992 paths per CTA, +21 %
+    int quant = -1;          // -1: follow Scene::traversal; 0 / 1: exact 64-byte / quantised 32-byte nodes for scenes in global memory
     int coop = -1;           // -1 / 1: warp-cooperative fetch of the binary nodes of a scene in global memory; 0: per lane
 };
 
@@ -88,10 +89,14 @@ struct Scene {
     uint32_t ploc_depth = 0;
     float ploc_ms = 0.f;
     int tree = 0;                     // pt_scene_set_tree: 0 auto, 1 LBVH, 2 SAH, 3 PLOC
+    // quantised 32-byte nodes of the tree in use (lbvh.cu quantize_nodes), built at the first launch that wants them
+    float4* d_qnodes = nullptr;
+    int qnodes_tree = 0;              // which tree (1 LBVH, 2 SAH, 3 PLOC) d_qnodes was made from; 0 = none
+    float q_lo[3] = {0.f, 0.f, 0.f}, q_step[3] = {1.f, 1.f, 1.f};
     uint32_t* d_wide_index = nullptr; // per binary node: index of the wide node rooted there (lbvh.cu wide_count)
     float4* d_wnodes = nullptr;       // wide nodes, 8 per node (two binary levels per record)
     uint32_t n_wide = 0;
-    int traversal = 0;                // pt_scene_set_traversal: 0 auto, 1 binary per lane, 2 wide (global), 3 binary cooperative (global)
+    int traversal = 0;                // pt_scene_set_traversal: 0 auto, 1 binary per lane, 2 wide (global), 3 binary cooperative (global), 4 quantised (global)
 
     // launch-time scratch
     uint32_t* d_work_counter = nullptr;         // [0] pixel fetch counter  [1] LBVH depth (build)
@@ -113,7 +118,7 @@ struct Scene {
     size_t stack_over_capacity = 0;
 
     // last launch
-    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_wide = 0;   // last_wide: 0 binary per lane, 1 wide nodes, 2 binary cooperative
+    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_wide = 0;   // last_wide: 0 binary per lane, 1 wide nodes, 2 binary cooperative, 3 binary quantised
 };
 
 constexpr uint32_t kSahMaxTris = 8192;    // the host build is O(n log^2 n); larger scenes keep the GPU-built LBVH
@@ -152,6 +157,7 @@ cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
 cudaError_t wide_count(Scene& s, cudaStream_t stream);
 cudaError_t wide_emit(Scene& s, cudaStream_t stream);
 cudaError_t ploc_build(Scene& s, cudaStream_t stream);
+cudaError_t quantize_nodes(Scene& s, cudaStream_t stream);
 
 // render.cu
 constexpr uint32_t kMaxFoldFrames = 64;

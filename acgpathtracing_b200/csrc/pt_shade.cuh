@@ -32,6 +32,8 @@ struct LaunchConst {   // everything a launch needs, passed by value as a kernel
     // scene (global memory; kernels may stage it into shared memory)
     BvhView bvh;
     const float4* wnodes;         // wide nodes (lbvh.cu wide_emit_kernel), 8 float4 each
+    const float4* qnodes;         // quantised nodes of the tree in use (lbvh.cu quantize_nodes_kernel), 2 float4 each, or null
+    float3 q_lo, q_step;
     uint32_t n_nodes, n_mats;
     const float4* tri_shade;      // per primitive: (N_0.xyz, material id)
     const DevMaterial* mats;      // 3 x float4 per material

@@ -200,7 +200,9 @@ __device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, cons
 //   TRAV_COOP    the warp reads its 32 nodes cooperatively, four lanes per record, and transposes through a per-warp
 //                staging buffer (pt_device.cuh coop_fetch64): 8 lines per instruction instead of 32
 //   TRAV_WIDE    wide nodes -- four child boxes, two LBVH levels, per 128-byte record (trav_wide_step)
-enum : int { TRAV_DIRECT = 0, TRAV_WIDE = 1, TRAV_COOP = 2 };
+//   TRAV_QUANT   quantised nodes: twelve 16-bit planes + two child references in 32 bytes, ONE LDG.E.256 per lane and node
+//                (lbvh.cu quantize_nodes_kernel): half the L1 requests and half the node bytes of TRAV_DIRECT
+enum : int { TRAV_DIRECT = 0, TRAV_WIDE = 1, TRAV_COOP = 2, TRAV_QUANT = 3 };
 constexpr int kStageF4 = 128;          // float4s of staging per warp (TRAV_COOP)
 
 template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV>
@@ -231,7 +233,12 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     f.tris = lc.bvh.tris;
     f.shade = lc.tri_shade;
     f.mats = reinterpret_cast<const float4*>(lc.mats);
-    if constexpr (SCENE < 0) f.wnodes = lc.wnodes;
+    if constexpr (SCENE < 0) {
+        f.wnodes = lc.wnodes;
+        f.qnodes = lc.qnodes;
+        f.q_lo = lc.q_lo;
+        f.q_step = lc.q_step;
+    }
     if (SCENE >= 0) {
         const uint32_t shift = SCENE >= 0 ? (uint32_t)SCENE : 0u, copies = 1u << shift;
         const uint32_t n_nodes4 = 4 * lc.n_nodes, n_tris4 = 3 * lc.bvh.n_tris, n_sh = lc.bvh.n_tris, n_m4 = 3 * lc.n_mats;
@@ -374,6 +381,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     if (at_node) {
                         if (COUNT) ctr.n_node++;
                         if constexpr (WIDE) trav_wide_step(t, stack, f, 0.01f);
+                        else if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
                         else trav_node_step(t, stack, f, 0.01f);
                     }
                 } else if (at_leaf) {
@@ -435,11 +443,13 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     if (at) {
                         if (COUNT) ctr.n_node++;
                         if constexpr (WIDE) trav_wide_step(t, stack, f, 0.01f);
+                        else if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
                         else trav_node_step(t, stack, f, 0.01f);                 // tmin :754
                     }
                     if (!WIDE && t.cur >= 0) {                                   // second step under the same vote
                         if (COUNT) ctr.n_node++;
-                        trav_node_step(t, stack, f, 0.01f);
+                        if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
+                        else trav_node_step(t, stack, f, 0.01f);
                     }
                 }
             }
@@ -778,6 +788,18 @@ static int choose_trav(const Scene& s, const WfTune& tune)
     const bool can_wide = s.n_wide != 0 && !s.count_enabled;   // the counted kernel walks the binary LBVH: its counters are the spec's
     const bool wide = can_wide && (tune.wide >= 0 ? tune.wide != 0 : s.traversal == 2);
     if (wide) return TRAV_WIDE;
+    // quantised nodes: never for counted launches (their counters are those of the exact boxes)
+    // (auto: only where the node and triangle records do not fit in L2 -- C4 +3 %; a scene that does fit is issue-bound and
+    // pays for the 36 extra instructions per node: C3 -12 %)
+    static int l2_bytes = -1;
+    if (l2_bytes < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev) != cudaSuccess) l2_bytes = 0;
+    }
+    const bool larger_than_l2 = 64 * (size_t)s.n_nodes + 48 * (size_t)s.n_tris > (size_t)l2_bytes;
+    const bool quant = tune.quant >= 0 ? tune.quant != 0 : (s.traversal == 4 || (s.traversal == 0 && larger_than_l2));
+    if (!s.count_enabled && s.n_tris >= 2 && quant) return TRAV_QUANT;
     return (tune.coop >= 0 ? tune.coop != 0 : s.traversal == 3) ? TRAV_COOP : TRAV_DIRECT;
 }
 
@@ -788,7 +810,7 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
     uint32_t depth = scene_depth(s) + 1u;                 // deferred children never exceed the tree depth
     if (depth > 255u) return false;
     trav = TRAV_DIRECT;
-    const bool force_global = (s.traversal == 2 && !s.count_enabled && s.n_wide != 0) || s.traversal == 3;
+    const bool force_global = (s.traversal == 2 && !s.count_enabled && s.n_wide != 0) || s.traversal == 3 || s.traversal == 4;
     const size_t scene_f4 = 4 * (size_t)s.n_nodes + 4 * (size_t)s.n_tris + 3 * (size_t)s.n_mats;
     const size_t fixed = (size_t)kCtlF4 * 16;
     const size_t per_path = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;   // state, candidate word, stack
@@ -859,7 +881,7 @@ static WfTune tuned(const WfTune& base)
                                {"tail_cols", &WfTune::tail_cols},   {"miss_loop", &WfTune::miss_loop},
                                {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
                                {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
-                               {"wide", &WfTune::wide},             {"coop", &WfTune::coop},
+                               {"wide", &WfTune::wide},             {"coop", &WfTune::coop},             {"quant", &WfTune::quant},
                                {"idle_ns", &WfTune::idle_ns},
                                {"stack_smem", &WfTune::stack_smem}};
     std::string str(env);
@@ -922,6 +944,20 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
         s.last_wide = 1;
         return probe ? launch_wavefront<false, true, -1, false, TRAV_WIDE>(s, lc, wc, smem_bytes, stream)
                      : launch_wavefront<false, false, -1, false, TRAV_WIDE>(s, lc, wc, smem_bytes, stream);
+    }
+    if (scene < 0 && trav == TRAV_QUANT) {
+        cudaError_t qe = quantize_nodes(s, stream);
+        if (qe != cudaSuccess) return qe;
+        if (s.d_qnodes && s.qnodes_tree == scene_tree(s)) {
+            LaunchConst lq = lc;
+            lq.qnodes = s.d_qnodes;
+            lq.q_lo = make_float3(s.q_lo[0], s.q_lo[1], s.q_lo[2]);
+            lq.q_step = make_float3(s.q_step[0], s.q_step[1], s.q_step[2]);
+            s.last_wide = 3;
+            return probe ? launch_wavefront<false, true, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream)
+                         : launch_wavefront<false, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
+        }
+        trav = TRAV_DIRECT;                              // a box could not be contained (never expected): exact nodes
     }
     if (scene < 0 && trav == TRAV_COOP) {
         s.last_wide = 2;

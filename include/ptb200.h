@@ -144,16 +144,18 @@ int pt_bvh_export_ploc(const pt_scene* scene, void* nodes64, uint32_t* depth, fl
  * leaf slot -> primitive (pt_bvh_export), n_tris >= 2; writes (n_tris - 1) x 64 B. */
 int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth);
 /* How the render kernel walks the acceleration structure:
- *   0 = auto (= 1, the fastest measured on B200 for every BASELINE scene);
+ *   0 = auto: 1, except 4 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
  *   1 = binary LBVH, every lane fetches its own node (from shared memory when the scene fits);
  *   2 = wide nodes (two LBVH levels per 128-byte record), scene read from global memory whatever its size;
  *   3 = binary LBVH with a warp-cooperative node fetch (four lanes per 64-byte node, transposed through shared
- *       memory), scene read from global memory whatever its size.
+ *       memory), scene read from global memory whatever its size;
+ *   4 = quantised nodes: 32 bytes per node (twelve 16-bit plane positions on the grid of the scene's bounding box,
+ *       rounded outwards and checked, + two child references), one 256-bit load per node; scene read from global memory.
  * The pixels do not depend on it: all variants cull with the LBVH's own boxes and every hit comes from the same
  * triangle test (OptiX's acceleration structure, PathTracerMain.cpp:311-398, is closed). */
 int pt_scene_set_traversal(pt_scene* scene, int traversal);
 int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 binary LBVH, 1 wide nodes,
-                                                         2 binary LBVH with warp-cooperative node fetch */
+                                                         2 binary LBVH with warp-cooperative node fetch, 3 quantised nodes */
 int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes,
                               uint32_t* kernels_launched);
 

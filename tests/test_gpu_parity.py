@@ -467,8 +467,8 @@ def test_full_size_c4_two_million_triangles(api, port):
         assert gs.last_launch_info()["traversal"] == "binary"                     # pipeline 1 ran last
         import torch
         acc_c, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
-        assert gs.last_launch_info()["traversal"] == "binary"                     # auto
-        for trav, expect in ((3, "binary-coop"), (2, "wide")):
+        assert gs.last_launch_info()["traversal"] == "binary-quant"               # auto: the records do not fit in L2
+        for trav, expect in ((3, "binary-coop"), (2, "wide"), (1, "binary")):
             gs.set_traversal(trav)
             acc_t, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
             assert gs.last_launch_info()["traversal"] == expect
@@ -723,7 +723,7 @@ def test_wide_traversal_same_pixels(api, port, scenes_cache, name, w, h, spp, md
     prev = np.random.default_rng(3).random((h, w, 4), dtype=np.float32)
     o = osc.render(p, accum=prev.copy(), math_mode=1, use_bvh=True, probes=True)
     try:
-        for trav, expect in ((2, "wide"), (3, "binary-coop"), (1, "binary")):
+        for trav, expect in ((2, "wide"), (3, "binary-coop"), (4, "binary-quant"), (1, "binary")):
             gs.set_traversal(trav)
             g = gs.launch_host(p, accum=prev.copy())
             assert gs.last_launch_info()["traversal"] == expect
@@ -743,7 +743,9 @@ def test_wide_traversal_single_triangle_and_soups(api, port):
         try:
             p = api.make_params(64, 40, 4, 6, frame=0, nee=True, scene=gs)
             o = osc.render(p, math_mode=1, use_bvh=True)
-            for trav, expect in ((2, "wide"), (3, "binary-coop")):
+            for trav, expect in ((2, "wide"), (3, "binary-coop"), (4, "binary-quant")):
+                if n_tri < 2 and trav == 4:
+                    continue                                  # a single triangle has no quantised node array
                 gs.set_traversal(trav)
                 g = gs.launch_host(p)
                 assert gs.last_launch_info()["traversal"] == expect
@@ -754,12 +756,14 @@ def test_wide_traversal_single_triangle_and_soups(api, port):
                 a[:, [11, 15]] = 0
                 b[:, [11, 15]] = 0
                 assert gp["depth"] == op["depth"] and np.array_equal(a, b), n_tri
-                gs.set_traversal(0)
-                for tree in (1, 2, 3):
-                    gs.set_tree(tree)
-                    g = gs.launch_host(p)
-                    assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (n_tri, tree)
+                for trav in (0, 4):                          # exact and quantised nodes of each tree
+                    gs.set_traversal(trav)
+                    for tree in (1, 2, 3):
+                        gs.set_tree(tree)
+                        g = gs.launch_host(p)
+                        assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (n_tri, tree, trav)
                 gs.set_tree(0)
+                gs.set_traversal(0)
             # counted launches with the cooperative fetch report the binary traversal's work counters
             gs.set_traversal(3)
             gs.enable_counters(True)
@@ -896,7 +900,7 @@ def test_degenerate_scenes_all_trees(api, port, kind):
             assert exp_g["depth"] == exp_o["depth"] and np.array_equal(a, b)
         p = api.make_params(96, 54, 3, 12, frame=0, nee=True, scene=gs)
         for tree in (0, 1, 2, 3):
-            for trav in (0, 3):
+            for trav in (0, 3, 4):
                 used = osc.set_tree(tree)
                 try:
                     gs.set_tree(tree)
