@@ -145,7 +145,7 @@ def cpu_reference_run(workload, steps, warmup, prefer_ref=True, target_step_s=2.
     value = w * h * s_spp * steps / total / 1e6
     kind = "reference" if ref is not None else "port"
     sample = (f"{desc}: full {w}x{h} frame at {s_spp} spp per step ({steps} steps, frames 0..{steps - 1}), "
-              f"{'CPU LBVH' if use_bvh else 'brute-force'} intersection, {cores} threads, glibc libm")
+              f"{'CPU BVH traversal (the tree the GPU walks)' if use_bvh else 'brute-force'} intersection, {cores} threads, glibc libm")
     return dict(value=value, unit="Mpixel-samples/s", cores=cores, kind=kind, sample=sample,
                 ms_per_step=1e3 * total / steps, spp=s_spp)
 
