@@ -57,6 +57,7 @@ def _load():
         "pt_scene_tree_in_use": (i32, [vp]),
         "pt_bvh_export_sah": (i32, [vp, vp, C.POINTER(u32)]),
         "pt_bvh_export_ploc": (i32, [vp, vp, C.POINTER(u32), C.POINTER(C.c_float)]),
+        "pt_bvh_export_quant": (i32, [vp, vp, vp, vp]),
         "pt_sah_build_host": (i32, [vp, vp, u32, vp, C.POINTER(u32)]),
         "pt_scene_last_traversal": (i32, [vp]),
         "pt_bvh_export_wide": (i32, [vp, C.POINTER(u32), vp, vp]),
@@ -254,6 +255,13 @@ class Scene:
         d = C.c_uint32()
         _check(lib.pt_bvh_export_sah(self._h, _ptr(nodes), C.byref(d)))
         return dict(nodes=nodes, depth=d.value)
+
+    def bvh_export_quant(self):
+        """Quantised nodes of the tree in use: dict(q (n_nodes, 8) u32, lo (3,), step (3,))."""
+        q = np.zeros((self.info()["n_nodes"], 8), np.uint32)
+        lo, step = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        _check(lib.pt_bvh_export_quant(self._h, _ptr(q), _ptr(lo), _ptr(step)))
+        return dict(q=q, lo=lo, step=step)
 
     def set_traversal(self, traversal):
         """0 auto, 1 binary LBVH, 2 wide nodes (pt_scene_set_traversal)."""

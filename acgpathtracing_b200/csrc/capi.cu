@@ -490,6 +490,22 @@ int pt_bvh_export_ploc(const pt_scene* scene, void* nodes64, uint32_t* depth, fl
     return PT_OK;
 }
 
+int pt_bvh_export_quant(pt_scene* scene, void* qnodes32, float* lo3, float* step3)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    if (s->n_tris < 2) return fail(PT_ERR_INVALID, "no quantised nodes for a scene of fewer than 2 triangles");
+    DeviceGuard g(s->device);
+    PT_CUDA(quantize_nodes(*s, 0));
+    if (!s->d_qnodes || s->qnodes_tree != scene_tree(*s)) return fail(PT_ERR_CUDA, "quantisation could not contain a box");
+    for (int a = 0; a < 3; ++a) {
+        if (lo3) lo3[a] = s->q_lo[a];
+        if (step3) step3[a] = s->q_step[a];
+    }
+    if (qnodes32) PT_CUDA(cudaMemcpy(qnodes32, s->d_qnodes, 32 * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
+    return PT_OK;
+}
+
 int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth)
 {
     if (!tri_boxes8 || !sorted_prim || !nodes64 || n_tris < 2) return fail(PT_ERR_INVALID, "pt_sah_build_host: bad argument");

@@ -140,6 +140,10 @@ int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH, 3 PLOC */
  * longest root-to-leaf chain. */
 int pt_bvh_export_sah(const pt_scene* scene, void* nodes64, uint32_t* depth);
 int pt_bvh_export_ploc(const pt_scene* scene, void* nodes64, uint32_t* depth, float* build_ms);
+/* Quantised nodes of the tree in use (built on demand): n_nodes x 32 B = six words of two 16-bit plane positions each
+ * (lo0.x|lo0.y<<16, lo0.z|hi0.x<<16, hi0.y|hi0.z<<16, then the same for child 1) + the two child references; a plane is
+ * fma(q, step[axis], lo[axis]). */
+int pt_bvh_export_quant(pt_scene* scene, void* qnodes32, float* lo3, float* step3);
 /* The host builder on its own (no device needed): tri_boxes8 = per PRIMITIVE (lo.xyz, -, hi.xyz, -), sorted_prim =
  * leaf slot -> primitive (pt_bvh_export), n_tris >= 2; writes (n_tris - 1) x 64 B. */
 int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth);

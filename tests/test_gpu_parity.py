@@ -913,3 +913,33 @@ def test_degenerate_scenes_all_trees(api, port, kind):
                 assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (kind, tree, trav)
     finally:
         gs.destroy()
+
+
+@pytest.mark.parametrize("name", ["cornell", "material", "tess40", "tess300"])
+def test_quantised_nodes_contain_the_exact_boxes(api, port, scenes_cache, name):
+    """32-byte nodes (pt_scene_set_traversal 4): every dequantised plane -- fma(q, step, lo), the traversal's expression,
+    evaluated here in float64 and rounded once like a float32 fma -- is on the outside of the exact plane, the child
+    references are the exact node's, and a plane is never more than one grid step away."""
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    try:
+        for tree, export in ((1, gs.bvh_export), (2, gs.bvh_export_sah), (3, gs.bvh_export_ploc)):
+            if tree == 2 and arr.n_tri > 8192:
+                continue
+            gs.set_tree(tree)
+            exact = export()["nodes"]
+            qd = gs.bvh_export_quant()
+            q, lo, step = qd["q"], qd["lo"].astype(np.float64), qd["step"].astype(np.float64)
+            f = exact.view(np.float32)
+            assert np.array_equal(q[:, 6], exact[:, 3]) and np.array_equal(q[:, 7], exact[:, 7])
+            w = q[:, :6]
+            planes = np.stack([w[:, 0] & 0xFFFF, w[:, 0] >> 16, w[:, 1] & 0xFFFF, w[:, 1] >> 16, w[:, 2] & 0xFFFF, w[:, 2] >> 16,
+                               w[:, 3] & 0xFFFF, w[:, 3] >> 16, w[:, 4] & 0xFFFF, w[:, 4] >> 16, w[:, 5] & 0xFFFF, w[:, 5] >> 16], axis=1)
+            axis = np.array([0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2])
+            # q * step is exact in float64 (16 x 24 bits), the sum is rounded once to float32: the value of the fused multiply-add
+            deq = (planes.astype(np.float64) * step[axis] + lo[axis]).astype(np.float32)
+            ex = np.stack([f[:, 0], f[:, 1], f[:, 2], f[:, 4], f[:, 5], f[:, 6], f[:, 8], f[:, 9], f[:, 10], f[:, 12], f[:, 13], f[:, 14]], axis=1)
+            is_lo = np.array([1, 1, 1, 0, 0, 0, 1, 1, 1, 0, 0, 0], bool)
+            assert np.all(deq[:, is_lo] <= ex[:, is_lo]) and np.all(deq[:, ~is_lo] >= ex[:, ~is_lo]), tree
+            assert np.all(np.abs(deq.astype(np.float64) - ex) <= 1.001 * step[axis] + 1e-4), tree
+    finally:
+        gs.set_tree(0)
