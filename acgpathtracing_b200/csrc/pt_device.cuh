@@ -123,6 +123,19 @@ struct FetchGlobal {
         ldg256(nodes + 4 * (size_t)i + 2, q2, q3);
     }
     __device__ __forceinline__ void wnode2(int i, int k, float4& lo, float4& hi) const { ldg256(wnodes + 8 * (size_t)i + 2 * k, lo, hi); }
+    // 48-byte triangle record in two loads instead of three: records start 32-byte aligned in even slots and at 16 mod 32
+    // in odd ones, so one half of the record is always a whole aligned sector pair
+    __device__ __forceinline__ void tri3(int i, float4& t0, float4& t1, float4& t2) const
+    {
+        const float4* p = tris + 3 * (size_t)i;
+        if (i & 1) {
+            t0 = __ldg(p);
+            ldg256(p + 1, t1, t2);
+        } else {
+            ldg256(p, t0, t1);
+            t2 = __ldg(p + 2);
+        }
+    }
     __device__ __forceinline__ void prefetch_wide_child(int c) const
     {
         if (c >= 0) {
@@ -147,6 +160,7 @@ struct FetchGlobal {
 struct FetchShared {
     const float4 *nodes, *tris, *shade, *mats;
     __device__ __forceinline__ void prefetch_child(int) const {}
+    __device__ __forceinline__ void tri3(int i, float4& t0, float4& t1, float4& t2) const { t0 = tri(i, 0), t1 = tri(i, 1), t2 = tri(i, 2); }
     __device__ __forceinline__ void node4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
     {
         q0 = node(i, 0), q1 = node(i, 1), q2 = node(i, 2), q3 = node(i, 3);
@@ -160,6 +174,7 @@ template <int SHIFT>
 struct FetchSharedBanked {
     const float4 *nodes, *tris, *shade, *mats;   // each already offset by this lane's copy index
     __device__ __forceinline__ void prefetch_child(int) const {}
+    __device__ __forceinline__ void tri3(int i, float4& t0, float4& t1, float4& t2) const { t0 = tri(i, 0), t1 = tri(i, 1), t2 = tri(i, 2); }
     __device__ __forceinline__ void node4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
     {
         q0 = node(i, 0), q1 = node(i, 1), q2 = node(i, 2), q3 = node(i, 3);
@@ -421,9 +436,8 @@ __device__ __forceinline__ void trav_leaf_step(Trav& t, const STK& stack, const 
                                                float tmax_closest)
 {
     const int leaf = ~t.cur;
-    const float4 t0 = f.tri(leaf, 0);
-    const float4 t1 = f.tri(leaf, 1);
-    const float4 t2 = f.tri(leaf, 2);
+    float4 t0, t1, t2;
+    f.tri3(leaf, t0, t1, t2);
     float th;
     const bool hit = ray_tri(t.r, f3(t0.x, t0.y, t0.z), f3(t1.x, t1.y, t1.z), f3(t2.x, t2.y, t2.z), tmin,
                              any ? t.tfar : tmax_closest, th);
