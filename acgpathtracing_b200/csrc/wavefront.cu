@@ -66,7 +66,8 @@ struct WfConst {
     int tail_cols;           // tail mode when the non-empty columns of all four queues add up to at most this
     int miss_loop;           // samples of an all-miss pixel finished per END visit
     int block_override;      // host only: threads per CTA when set by PTB_TUNE
-    int idle_ns;             // sleep of a warp that found every queue empty
+    int idle_ns;             // sleep of a warp that found every queue empty ...
+    int idle_shift;          // ... doubled for every further empty poll, at most this many times
 };
 
 struct ThreadCounters {
@@ -305,7 +306,9 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 }
                 if (COUNT) st_idle++;
                 stage = -1;
-                __nanosleep((unsigned)wc.idle_ns);
+                // back off: a warp that keeps finding nothing sleeps longer (up to 16x), so that its polls stop taking issue
+                // slots from the warps that hold the paths
+                __nanosleep((unsigned)wc.idle_ns << min(idle_polls - 1u, (uint32_t)wc.idle_shift));
                 continue;
             }
             idle_polls = 0;
@@ -882,7 +885,7 @@ static WfTune tuned(const WfTune& base)
                                {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
                                {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
                                {"wide", &WfTune::wide},             {"coop", &WfTune::coop},             {"quant", &WfTune::quant},
-                               {"idle_ns", &WfTune::idle_ns},
+                               {"idle_ns", &WfTune::idle_ns},       {"idle_shift", &WfTune::idle_shift},
                                {"stack_smem", &WfTune::stack_smem}};
     std::string str(env);
     size_t pos = 0;
@@ -918,6 +921,7 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     wc.miss_loop = tune.miss_loop;
     wc.block_override = tune.block;
     wc.idle_ns = tune.idle_ns;
+    wc.idle_shift = tune.idle_shift < 0 ? 0 : (tune.idle_shift > 10 ? 10 : tune.idle_shift);
     wc.stack_over = nullptr;
     if (!smem_scene && wc.stack_total > wc.stack_depth) {
         int dev = 0, sms = 0;
