@@ -36,7 +36,8 @@ struct WfTune {
     int shortlist = 1;       // per-pixel candidate lists for camera rays (tiny scenes)
     int wide = -1;           // -1: follow Scene::traversal; 0 / 1: binary / wide nodes for scenes in global memory
     int idle_ns = 64;        // sleep of a warp that found every queue empty ...
-    int idle_shift = 0;      // ... doubled for every further empty poll in a row, at most this many times
+    int idle_shift = 4;      // ... doubled for every further empty poll in a row, at most this many times (C3 +4 %: its idle polls
+                             // were 21 % of the issued instructions; C2 and C4 unchanged)
     int stack_smem = 12;     // scenes in global memory: traversal-stack levels kept in shared memory, deeper ones spill to
                              // global memory (0 = all in shared memory).  C4: 672 -> 992 paths per CTA, +21 %
     int quant = -1;          // -1: follow Scene::traversal; 0 / 1: exact 64-byte / quantised 32-byte nodes for scenes in global memory
