@@ -132,10 +132,32 @@ int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
  *   3 = a PLOC tree (parallel locally-ordered clustering, radius 8), built on the GPU for every scene of >= 2
  *       triangles (22-27 % fewer node visits on the 2 M-triangle scene);
  *   0 = auto: 2 where it exists, else 3, else 1 (a tree more than 64 levels deep is passed over).
- * Asking for a tree the scene does not have, or one deeper than 64 levels, is PT_ERR_INVALID.  Replaces the build flags of optixAccelBuild
- * (PathTracerMain.cpp:334-339). */
+ * Asking for a tree the scene does not have, or one deeper than 64 levels, is PT_ERR_INVALID.  Replaces the build
+ * flags of optixAccelBuild (PathTracerMain.cpp:334-339). */
 int pt_scene_set_tree(pt_scene* scene, int tree);
 int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH, 3 PLOC */
+/* How the render kernel walks the acceleration structure:
+ *   0 = auto: 1, except 4 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
+ *   1 = the binary tree in use, every lane fetches its own 64-byte node (from shared memory when the scene fits);
+ *   2 = wide nodes (two LBVH levels per 128-byte record), scene read from global memory whatever its size;
+ *   3 = the binary tree in use with a warp-cooperative node fetch (four lanes per 64-byte node, transposed through
+ *       shared memory), scene read from global memory whatever its size;
+ *   4 = quantised nodes: 32 bytes per node (twelve 16-bit plane positions on the grid of the scene's bounding box,
+ *       rounded outwards and checked, + two child references), one 256-bit load per node; scene read from global memory.
+ * The pixels do not depend on it: every variant culls with boxes that contain the tree's own and every hit comes from
+ * the same triangle test (OptiX's acceleration structure, PathTracerMain.cpp:311-398, is closed). */
+int pt_scene_set_traversal(pt_scene* scene, int traversal);
+int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 binary tree per lane, 1 wide nodes,
+                                                         2 warp-cooperative node fetch, 3 quantised nodes */
+int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes,
+                              uint32_t* kernels_launched);
+
+/* ---- parity probes (tests only; not on the hot path) --------------------------------------------------- */
+/* LBVH export; any pointer may be NULL.  morton[n_tris] in primitive order; sorted_keys[n_tris] =
+ * morton<<32|prim ascending; sorted_prim[n_tris]; parent[n_nodes]; nodes: n_nodes x 64 B; tris: n_tris x 48 B
+ * (leaf order); bounds: lo xyz, hi xyz. */
+int pt_bvh_export(const pt_scene* scene, uint32_t* morton, uint64_t* sorted_keys, uint32_t* sorted_prim,
+                  int32_t* parent, void* nodes64, void* tris48, float* bounds6);
 /* SAH tree export (tests): nodes: n_nodes x 64 B (same record as pt_bvh_export's); depth: internal nodes on the
  * longest root-to-leaf chain. */
 int pt_bvh_export_sah(const pt_scene* scene, void* nodes64, uint32_t* depth);
@@ -147,28 +169,6 @@ int pt_bvh_export_quant(pt_scene* scene, void* qnodes32, float* lo3, float* step
 /* The host builder on its own (no device needed): tri_boxes8 = per PRIMITIVE (lo.xyz, -, hi.xyz, -), sorted_prim =
  * leaf slot -> primitive (pt_bvh_export), n_tris >= 2; writes (n_tris - 1) x 64 B. */
 int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth);
-/* How the render kernel walks the acceleration structure:
- *   0 = auto: 1, except 4 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
- *   1 = binary LBVH, every lane fetches its own node (from shared memory when the scene fits);
- *   2 = wide nodes (two LBVH levels per 128-byte record), scene read from global memory whatever its size;
- *   3 = binary LBVH with a warp-cooperative node fetch (four lanes per 64-byte node, transposed through shared
- *       memory), scene read from global memory whatever its size;
- *   4 = quantised nodes: 32 bytes per node (twelve 16-bit plane positions on the grid of the scene's bounding box,
- *       rounded outwards and checked, + two child references), one 256-bit load per node; scene read from global memory.
- * The pixels do not depend on it: all variants cull with the LBVH's own boxes and every hit comes from the same
- * triangle test (OptiX's acceleration structure, PathTracerMain.cpp:311-398, is closed). */
-int pt_scene_set_traversal(pt_scene* scene, int traversal);
-int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 binary LBVH, 1 wide nodes,
-                                                         2 binary LBVH with warp-cooperative node fetch, 3 quantised nodes */
-int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes,
-                              uint32_t* kernels_launched);
-
-/* ---- parity probes (tests only; not on the hot path) --------------------------------------------------- */
-/* LBVH export; any pointer may be NULL.  morton[n_tris] in primitive order; sorted_keys[n_tris] =
- * morton<<32|prim ascending; sorted_prim[n_tris]; parent[n_nodes]; nodes: n_nodes x 64 B; tris: n_tris x 48 B
- * (leaf order); bounds: lo xyz, hi xyz. */
-int pt_bvh_export(const pt_scene* scene, uint32_t* morton, uint64_t* sorted_keys, uint32_t* sorted_prim,
-                  int32_t* parent, void* nodes64, void* tris48, float* bounds6);
 /* Wide-node export; any pointer may be NULL.  wide_index[n_nodes]: exclusive count of wide-node roots among the
  * binary nodes before i (= the wide node's index where binary node i is a root); wnodes: n_wide x 128 B. */
 int pt_bvh_export_wide(const pt_scene* scene, uint32_t* n_wide, uint32_t* wide_index, void* wnodes128);
