@@ -53,6 +53,20 @@ def _load():
         "pt_scene_get_sched_stats": (i32, [vp, C.POINTER(u64), i32]),
         "pt_scene_set_pipeline": (i32, [vp, i32]),
         "pt_scene_set_traversal": (i32, [vp, i32]),
+        "pt_scene_set_tune": (i32, [vp, C.c_char_p]),
+        "pt_scene_check_error": (i32, [vp]),
+        "pt_multi_plan": (i32, [u32, u32, vp, u32, C.POINTER(u32)]),
+        "pt_multi_slice": (i32, [u32, u32, u32, u32, C.POINTER(u64), C.POINTER(u64)]),
+        "pt_group_create_local": (i32, [C.POINTER(C.c_int), u32, i32, C.POINTER(vp)]),
+        "pt_group_unique_id": (i32, [vp]),
+        "pt_group_create_rank": (i32, [vp, u32, u32, C.POINTER(vp)]),
+        "pt_group_destroy": (None, [vp]),
+        "pt_group_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(i32)]),
+        "pt_group_scene_create": (i32, [vp, vp, u32, vp, u32, vp, vp, u32, C.POINTER(vp)]),
+        "pt_group_scene": (vp, [vp, u32]),
+        "pt_launch_multi": (i32, [vp, PP, u32, vp]),
+        "pt_launch_multi_host": (i32, [vp, PP, u32, C.POINTER(u64), C.POINTER(u64)]),
+        "pt_group_last_timing": (i32, [vp, u32, C.POINTER(C.c_float), C.POINTER(u32)]),
         "pt_scene_set_tree": (i32, [vp, i32]),
         "pt_scene_tree_in_use": (i32, [vp]),
         "pt_bvh_export_sah": (i32, [vp, vp, C.POINTER(u32)]),
@@ -60,7 +74,6 @@ def _load():
         "pt_bvh_export_quant": (i32, [vp, vp, vp, vp]),
         "pt_sah_build_host": (i32, [vp, vp, u32, vp, C.POINTER(u32)]),
         "pt_scene_last_traversal": (i32, [vp]),
-        "pt_bvh_export_wide": (i32, [vp, C.POINTER(u32), vp, vp]),
         "pt_scene_last_launch_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "pt_bvh_export": (i32, [vp] * 8),
         "pt_trace_rays": (i32, [vp, vp, vp, vp, vp, u64, vp, vp, vp, vp]),
@@ -172,9 +185,13 @@ class ObjFile:
 class Scene:
     """Device scene + LBVH (replaces buildTheAccelarationStructure + createShaderBindingTable)."""
 
-    def __init__(self, arrays=None, obj: ObjFile = None, background=None):
+    def __init__(self, arrays=None, obj: ObjFile = None, background=None, _borrowed=None):
         h = C.c_void_p()
-        if obj is not None:
+        self._owned = _borrowed is None
+        if _borrowed is not None:                     # a replica owned by a Group (pt_group_scene)
+            h = C.c_void_p(_borrowed)
+            self.n_tri = None
+        elif obj is not None:
             _check(lib.pt_scene_create_from_obj(obj._h, C.byref(h)))
             self.n_tri = int(obj.indices.shape[0])
         else:
@@ -195,9 +212,9 @@ class Scene:
         return lib.pt_scene_handle(self._h)
 
     def destroy(self):
-        if self._h:
+        if self._h and self._owned:
             lib.pt_scene_destroy(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
@@ -214,6 +231,7 @@ class Scene:
         return dict(n_tris=nt.value, n_nodes=nn.value, build_ms=ms.value)
 
     def enable_counters(self, on=True):
+        """False / 0 off; True / 1 the specified work (equals the oracle's counts); 2 the executed work of an uncounted launch."""
         _check(lib.pt_scene_enable_counters(self._h, int(on)))
 
     def counters(self, reset=True):
@@ -264,23 +282,22 @@ class Scene:
         return dict(q=q, lo=lo, step=step)
 
     def set_traversal(self, traversal):
-        """0 auto, 1 binary LBVH, 2 wide nodes (pt_scene_set_traversal)."""
+        """0 auto, 1 exact nodes (staged in shared memory when the scene fits), 2 exact nodes from global memory,
+        3 quantised nodes from global memory (pt_scene_set_traversal)."""
         _check(lib.pt_scene_set_traversal(self._h, traversal))
+
+    def set_tune(self, spec=""):
+        """Scheduling constants of the render kernel for this scene, "key=value,..." ("" = defaults)."""
+        _check(lib.pt_scene_set_tune(self._h, spec.encode()))
+
+    def check_error(self):
+        _check(lib.pt_scene_check_error(self._h))
 
     def last_launch_info(self):
         g, b, s, k = (C.c_uint32() for _ in range(4))
         _check(lib.pt_scene_last_launch_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(k)))
         return dict(grid=g.value, block=b.value, smem_bytes=s.value, kernels=k.value,
-                    traversal={0: "binary", 1: "wide", 2: "binary-coop", 3: "binary-quant"}.get(lib.pt_scene_last_traversal(self._h), "?"))
-
-    def bvh_export_wide(self):
-        """Wide nodes (two LBVH levels per 128-byte record): dict(n_wide, wide_index[n_nodes], wnodes[n_wide, 32] u32)."""
-        n = C.c_uint32()
-        _check(lib.pt_bvh_export_wide(self._h, C.byref(n), None, None))
-        idx = np.zeros(self.info()["n_nodes"], np.uint32)
-        wn = np.zeros((n.value, 32), np.uint32)
-        _check(lib.pt_bvh_export_wide(self._h, C.byref(n), _ptr(idx), _ptr(wn)))
-        return dict(n_wide=n.value, wide_index=idx, wnodes=wn)
+                    traversal={0: "binary", 1: "binary-quant"}.get(lib.pt_scene_last_traversal(self._h), "?"))
 
     def bvh_export(self):
         info = self.info()
@@ -375,6 +392,114 @@ def partition_pack(accum_full, frame_full, accum_compact, frame_compact, width, 
 def partition_unpack(accum_compact_all, frame_compact_all, accum_full, frame_full, width, height, n_ranks, stream=None):
     _check(lib.pt_partition_unpack(accum_compact_all, frame_compact_all or None, accum_full, frame_full or None, width,
                                    height, n_ranks, C.c_void_p(stream) if stream else None))
+
+
+# ---- multi-GPU (pt_group / pt_launch_multi) -----------------------------------------------------------------------------
+class MultiJob(C.Structure):
+    _fields_ = [("frame", C.c_uint32), ("rank", C.c_uint32), ("first_class", C.c_uint32), ("n_classes", C.c_uint32)]
+
+
+def multi_plan(n_launches, n_ranks):
+    """pt_multi_plan (host only): [(frame, rank, first_class, n_classes)] in exchange order."""
+    n = C.c_uint32()
+    _check(lib.pt_multi_plan(n_launches, n_ranks, None, 0, C.byref(n)))
+    jobs = (MultiJob * max(n.value, 1))()
+    _check(lib.pt_multi_plan(n_launches, n_ranks, C.cast(jobs, C.c_void_p), n.value, C.byref(n)))
+    return [(j.frame, j.rank, j.first_class, j.n_classes) for j in jobs[:n.value]]
+
+
+def multi_slice(width, height, rank, n_ranks):
+    """pt_multi_slice (host only): (first pixel, pixel count) of the slice `rank` folds."""
+    a, b = C.c_uint64(), C.c_uint64()
+    _check(lib.pt_multi_slice(width, height, rank, n_ranks, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+PT_TRANSPORT_PEER, PT_TRANSPORT_NCCL = 0, 1
+PT_GROUP_ID_BYTES = 128
+
+
+def group_unique_id():
+    buf = C.create_string_buffer(PT_GROUP_ID_BYTES)
+    _check(lib.pt_group_unique_id(buf))
+    return buf.raw
+
+
+class Group:
+    """pt_group: several GPUs rendering one image.  Group.local(devices) = one process drives them all;
+    Group.rank(id_bytes, rank, world) = one process per GPU (collective; NCCL)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.scene = None
+
+    @classmethod
+    def local(cls, devices, transport=PT_TRANSPORT_PEER):
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib.pt_group_create_local(arr, len(devices), transport, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def rank(cls, id_bytes, rank, world):
+        h = C.c_void_p()
+        _check(lib.pt_group_create_rank(C.c_char_p(id_bytes), rank, world, C.byref(h)))
+        return cls(h)
+
+    def info(self):
+        n, nl, fr, tr = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_int()
+        _check(lib.pt_group_info(self._h, C.byref(n), C.byref(nl), C.byref(fr), C.byref(tr)))
+        return dict(n_ranks=n.value, n_local=nl.value, first_rank=fr.value, transport={0: "peer", 1: "nccl"}[tr.value])
+
+    def create_scene(self, arrays):
+        """Replicates the scene on every local device; returns the first replica (its handle goes into the params)."""
+        verts = np.ascontiguousarray(arrays.verts, np.float32)
+        indices = np.ascontiguousarray(arrays.indices, np.uint32)
+        mat_ids = np.ascontiguousarray(arrays.mat_ids, np.uint32)
+        mats = arrays.material_structs() if hasattr(arrays, "material_structs") else arrays.materials
+        h = C.c_void_p()
+        _check(lib.pt_group_scene_create(self._h, _ptr(verts), verts.shape[0], _ptr(indices), indices.shape[0], _ptr(mat_ids),
+                                         C.cast(mats, C.c_void_p), len(mats), C.byref(h)))
+        self.scene = Scene(_borrowed=h.value)
+        self.scene.n_tri = int(indices.shape[0])
+        return self.scene
+
+    def replica(self, local_index):
+        h = lib.pt_group_scene(self._h, local_index)
+        if not h:
+            raise PtError(PT_ERR_INVALID, "no such replica")
+        return Scene(_borrowed=h)
+
+    def launch(self, params: PathTraceParams, n_launches, stream=None):
+        """pt_launch_multi: device buffers, stream-ordered."""
+        _check(lib.pt_launch_multi(self._h, C.byref(params), n_launches, C.c_void_p(stream) if stream else None))
+
+    def launch_host(self, params: PathTraceParams, n_launches):
+        """pt_launch_multi_host: host buffers, synchronous.  Returns (h2d_bytes, d2h_bytes) moved by this process."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(lib.pt_launch_multi_host(self._h, C.byref(params), n_launches, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def last_kernels(self, local_index=0):
+        return self.last_timing(local_index)["kernels"]
+
+    def last_timing(self, local_index=0):
+        ms = (C.c_float * 4)()
+        n = C.c_uint32()
+        _check(lib.pt_group_last_timing(self._h, local_index, ms, C.byref(n)))
+        return dict(render_ms=ms[0], exchange_fold_ms=ms[1], gather_ms=ms[2], total_ms=ms[3], kernels=n.value)
+
+    def destroy(self):
+        if self._h:
+            lib.pt_group_destroy(self._h)
+            self._h = None
+            self.scene = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 def device_info():

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <unordered_set>
@@ -24,12 +25,12 @@ void set_error(const std::string& msg) { g_error = msg; }
 static std::mutex g_scene_mutex;
 static std::unordered_set<const Scene*> g_scenes;
 
-static int fail(int code, const std::string& msg)
+int fail(int code, const std::string& msg)
 {
     set_error(msg);
     return code;
 }
-static int cuda_fail(cudaError_t e, const char* what)
+int cuda_fail(cudaError_t e, const char* what)
 {
     return fail(PT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
@@ -39,7 +40,7 @@ static int cuda_fail(cudaError_t e, const char* what)
         if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
     } while (0)
 
-static Scene* scene_from_handle(uint64_t handle)
+Scene* scene_from_handle(uint64_t handle)
 {
     Scene* s = reinterpret_cast<Scene*>(static_cast<uintptr_t>(handle));
     std::lock_guard<std::mutex> lock(g_scene_mutex);
@@ -72,12 +73,39 @@ static void scene_free(Scene* s)
     void* ptrs[] = {s->d_verts, s->d_indices, s->d_mat_ids, s->d_mats, s->d_tri_in, s->d_tri_bb, s->d_tri_shade,
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_scan_scratch, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
-                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_qnodes, s->d_wide_index, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
-                    s->d_tile_order, s->d_stack_over};
+                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_qnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
+                    s->d_stack_over};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (TileOrder& t : s->tile_orders) {
+        if (t.d) cudaFree(t.d);
+        if (t.h) cudaFreeHost(t.h);
+        if (t.copied) cudaEventDestroy(t.copied);
+    }
     s->magic = 0;
     delete s;
+}
+
+// Builds the PLOC tree of a scene that does not have one yet (synchronous; the time goes into ploc_ms and build_ms).
+cudaError_t ensure_ploc(Scene& s)
+{
+    if (s.d_nodes_ploc || s.ploc_tried || s.n_tris < 2) return cudaSuccess;
+    s.ploc_tried = true;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    cudaStream_t stream = 0;
+    if (e == cudaSuccess) e = cudaEventRecord(e0, stream);
+    if (e == cudaSuccess) e = ploc_build(s, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) {
+        cudaEventElapsedTime(&s.ploc_ms, e0, e1);
+        s.build_ms += s.ploc_ms;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return e;
 }
 
 static int validate_params(const pt_params* p, Scene** out)
@@ -158,7 +186,6 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
     A(dev_alloc(&s->d_node_parent, n));
     A(dev_alloc(&s->d_leaf_parent, n));
     A(dev_alloc(&s->d_visit, n + 1));
-    A(dev_alloc(&s->d_wide_index, n + 1));
     A(dev_alloc(&s->d_node_lo, n));
     A(dev_alloc(&s->d_node_hi, n));
     A(dev_alloc(&s->d_nodes, 4 * (size_t)(s->n_nodes ? s->n_nodes : 1)));
@@ -196,38 +223,17 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
     if (e == cudaSuccess) {
         A(cudaEventRecord(e0, stream));
         A(lbvh_build(*s, stream));
-        A(wide_count(*s, stream));
         A(cudaEventRecord(e1, stream));
         A(cudaStreamSynchronize(stream));
         if (e == cudaSuccess) cudaEventElapsedTime(&s->build_ms, e0, e1);
-        // wide nodes: the count is known only now; one more kernel writes the records
-        if (e == cudaSuccess && n) A(cudaMemcpy(&s->n_wide, s->d_wide_index + s->n_nodes, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        if (e == cudaSuccess && n) {
-            A(dev_alloc(&s->d_wnodes, 8 * (size_t)s->n_wide));
-            A(cudaEventRecord(e0, stream));
-            A(wide_emit(*s, stream));
-            A(cudaEventRecord(e1, stream));
-            A(cudaStreamSynchronize(stream));
-            float ms = 0.f;
-            if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-            s->build_ms += ms;
-        }
         if (e == cudaSuccess && n) A(cudaMemcpy(&s->bvh_depth, s->d_work_counter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         if (e == cudaSuccess && n) A(cudaMemcpy(s->h_bounds, s->d_bounds, 6 * sizeof(float), cudaMemcpyDeviceToHost));
     }
-    // PLOC tree over the same leaves (GPU; the tree the kernels walk when the scene is too large for the host SAH sweep)
-    if (e == cudaSuccess && n >= 2) {
-        A(cudaEventRecord(e0, stream));
-        A(ploc_build(*s, stream));
-        A(cudaEventRecord(e1, stream));
-        A(cudaStreamSynchronize(stream));
-        if (e == cudaSuccess) cudaEventElapsedTime(&s->ploc_ms, e0, e1);
-        s->build_ms += s->ploc_ms;
-    }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    // small scenes: sweep-SAH tree over the LBVH's leaves, built on the host (sah.cu); not part of build_ms (GPU time)
+    // small scenes: sweep-SAH tree over the LBVH's leaves, built on the host (sah.cu); sah_ms is host wall-clock
     if (e == cudaSuccess && n >= 2 && n <= kSahMaxTris) {
+        const auto t0 = std::chrono::steady_clock::now();
         std::vector<float4> bb(2 * n), nodes;
         std::vector<uint32_t> prim(n);
         A(cudaMemcpy(bb.data(), s->d_tri_bb, sizeof(float4) * 2 * n, cudaMemcpyDeviceToHost));
@@ -237,7 +243,11 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
             A(dev_alloc(&s->d_nodes_sah, nodes.size()));
             A(cudaMemcpy(s->d_nodes_sah, nodes.data(), sizeof(float4) * nodes.size(), cudaMemcpyHostToDevice));
         }
+        s->sah_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
+    // PLOC tree over the same leaves (GPU): built now only where it is the tree the kernels will walk (no usable SAH tree);
+    // smaller scenes get it on demand (pt_scene_set_tree(scene, 3), pt_bvh_export_ploc)
+    if (e == cudaSuccess && n >= 2 && !(s->d_nodes_sah && s->sah_depth <= kSahMaxDepth)) A(ensure_ploc(*s));
     if (e != cudaSuccess) {
         scene_free(s);
         return cuda_fail(e, "scene upload / LBVH build");
@@ -393,7 +403,9 @@ int pt_scene_enable_counters(pt_scene* scene, int enable)
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    if (enable < 0 || enable > 2) return fail(PT_ERR_INVALID, "pt_scene_enable_counters: 0, 1 or 2");
     s->count_enabled = enable != 0;
+    s->count_executed = enable == 2;
     return PT_OK;
 }
 
@@ -439,11 +451,33 @@ int pt_scene_set_pipeline(pt_scene* scene, int pipeline)
     return PT_OK;
 }
 
+int pt_scene_set_tune(pt_scene* scene, const char* spec)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    WfTune t = WfTune();                       // every call starts from the defaults: "" resets
+    if (!wf_tune_apply(t, spec)) return fail(PT_ERR_INVALID, std::string("pt_scene_set_tune: unknown key in \"") + (spec ? spec : "") + "\"");
+    s->wf = t;
+    return PT_OK;
+}
+
+int pt_scene_check_error(pt_scene* scene)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    DeviceGuard g(s->device);
+    PT_CUDA(cudaDeviceSynchronize());
+    unsigned long long watchdog = 0;
+    PT_CUDA(cudaMemcpy(&watchdog, s->d_counters + 15, sizeof(watchdog), cudaMemcpyDeviceToHost));
+    if (watchdog) return fail(PT_ERR_CUDA, "render kernel watchdog fired (scheduler made no progress)");
+    return PT_OK;
+}
+
 int pt_scene_set_traversal(pt_scene* scene, int traversal)
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
-    if (traversal < 0 || traversal > 4) return fail(PT_ERR_INVALID, "traversal must be 0 .. 4");
+    if (traversal < 0 || traversal > 3) return fail(PT_ERR_INVALID, "traversal must be 0 .. 3");
     s->traversal = traversal;
     return PT_OK;
 }
@@ -453,6 +487,10 @@ int pt_scene_set_tree(pt_scene* scene, int tree)
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
     if (tree < 0 || tree > 3) return fail(PT_ERR_INVALID, "tree must be 0, 1, 2 or 3");
+    if (tree == 3) {
+        DeviceGuard g(s->device);
+        PT_CUDA(ensure_ploc(*s));
+    }
     if (tree == 2 && !s->d_nodes_sah && s->n_tris >= 2) return fail(PT_ERR_INVALID, "no SAH tree for this scene (more than 8192 triangles)");
     if (tree == 3 && !s->d_nodes_ploc && s->n_tris >= 2) return fail(PT_ERR_INVALID, "no PLOC tree for this scene");
     if ((tree == 2 && s->d_nodes_sah && s->sah_depth > kSahMaxDepth) || (tree == 3 && s->d_nodes_ploc && s->ploc_depth > kSahMaxDepth))
@@ -482,8 +520,9 @@ int pt_bvh_export_ploc(const pt_scene* scene, void* nodes64, uint32_t* depth, fl
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
-    if (!s->d_nodes_ploc) return fail(PT_ERR_INVALID, "no PLOC tree for this scene");
     DeviceGuard g(s->device);
+    PT_CUDA(ensure_ploc(*s));
+    if (!s->d_nodes_ploc) return fail(PT_ERR_INVALID, "no PLOC tree for this scene");
     if (depth) *depth = s->ploc_depth;
     if (build_ms) *build_ms = s->ploc_ms;
     if (nodes64) PT_CUDA(cudaMemcpy(nodes64, s->d_nodes_ploc, 64 * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
@@ -520,18 +559,7 @@ int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint
 int pt_scene_last_traversal(const pt_scene* scene)
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
-    return s ? (int)s->last_wide : -1;
-}
-
-int pt_bvh_export_wide(const pt_scene* scene, uint32_t* n_wide, uint32_t* wide_index, void* wnodes128)
-{
-    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
-    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
-    DeviceGuard g(s->device);
-    if (n_wide) *n_wide = s->n_wide;
-    if (wide_index && s->n_nodes) PT_CUDA(cudaMemcpy(wide_index, s->d_wide_index, sizeof(uint32_t) * s->n_nodes, cudaMemcpyDeviceToHost));
-    if (wnodes128 && s->n_wide) PT_CUDA(cudaMemcpy(wnodes128, s->d_wnodes, 128 * (size_t)s->n_wide, cudaMemcpyDeviceToHost));
-    return PT_OK;
+    return s ? (int)s->last_trav : -1;
 }
 
 int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes, uint32_t* kernels_launched)

@@ -458,68 +458,6 @@ __global__ void __launch_bounds__(256) depth_kernel(int n, const int* __restrict
     if ((threadIdx.x & 31) == 0 && d) atomicMax(depth_out, d);
 }
 
-// ---- wide nodes: two binary levels per node ("wide BVH4 collapse") -----------------------------
-// A pure function of the packed binary LBVH, so it is as deterministic as the tree it comes from.  Binary node i
-// becomes the root of a wide node iff it has an even number of ancestors; the wide node's (up to 4) children are
-// i's grandchildren, or i's child itself where that child is a leaf.  Child boxes are the binary tree's boxes,
-// bit for bit -- the wide tree culls with the same boxes, only two levels per fetch instead of one.
-// Record, 128 B = 8 x float4: slot k = (lo_k.xyz, child_k) (hi_k.xyz, 0); child >= 0 wide node, < 0 leaf ~child,
-// kTravDone = empty slot.  Slots are filled in binary order (left subtree first), empty slots last.
-__global__ void __launch_bounds__(256) wide_mark_kernel(int n_internal, const int* __restrict__ node_parent,
-                                                        uint32_t* __restrict__ flag, uint32_t* __restrict__ index)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n_internal) return;
-    uint32_t f = 0u;
-    if (i < n_internal) {
-        int d = 0;
-        for (int cur = node_parent[i]; cur >= 0; cur = node_parent[cur]) ++d;
-        f = (d & 1) ? 0u : 1u;
-    }
-    flag[i] = f;       // entry n_internal stays 0: after the exclusive scan it holds the number of wide nodes
-    index[i] = f;
-}
-
-__global__ void __launch_bounds__(256) wide_emit_kernel(int n_internal, const float4* __restrict__ nodes,
-                                                        const uint32_t* __restrict__ flag, const uint32_t* __restrict__ index,
-                                                        float4* __restrict__ wnodes)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_internal || !flag[i]) return;
-    float4 lo[4], hi[4];
-    int k = 0;
-    const float4 q0 = nodes[4 * i + 0], q1 = nodes[4 * i + 1], q2 = nodes[4 * i + 2], q3 = nodes[4 * i + 3];
-    const int c[2] = {__float_as_int(q0.w), __float_as_int(q1.w)};
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (s == 1 && c[1] == c[0]) break;                     // single-triangle scene: both children are the same leaf
-        if (c[s] < 0) {
-            lo[k] = s ? q2 : q0;
-            hi[k] = s ? q3 : q1;
-            lo[k].w = __int_as_float(c[s]);
-            ++k;
-        } else {
-            const float4 r0 = nodes[4 * c[s] + 0], r1 = nodes[4 * c[s] + 1], r2 = nodes[4 * c[s] + 2], r3 = nodes[4 * c[s] + 3];
-            const int g0 = __float_as_int(r0.w), g1 = __float_as_int(r1.w);
-            lo[k] = r0;
-            hi[k] = r1;
-            lo[k].w = __int_as_float(g0 >= 0 ? (int)index[g0] : g0);
-            ++k;
-            lo[k] = r2;
-            hi[k] = r3;
-            lo[k].w = __int_as_float(g1 >= 0 ? (int)index[g1] : g1);
-            ++k;
-        }
-    }
-    const uint32_t w = index[i];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const bool used = j < k;
-        wnodes[8 * (size_t)w + 2 * j + 0] = used ? lo[j] : make_float4(0.0f, 0.0f, 0.0f, __int_as_float((int)0x80000000));
-        wnodes[8 * (size_t)w + 2 * j + 1] = used ? make_float4(hi[j].x, hi[j].y, hi[j].z, 0.0f) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
-}
-
 // ---- PLOC: a better tree than Morton order for scenes too large for the host SAH sweep (sah.cu) ------------------------
 // Parallel locally-ordered clustering (Meister & Bittner 2018) over the LBVH's leaves in Morton order.  Round: every
 // cluster i looks at its neighbours j in [i - R, i + R] and picks the one whose union box has the smallest half-area
@@ -743,26 +681,6 @@ cudaError_t lbvh_build(Scene& s, cudaStream_t stream)
         depth_kernel<<<g, 256, 0, stream>>>((int)n, s.d_node_parent, s.d_leaf_parent, s.d_work_counter + 1);
     }
     pack_tris_kernel<<<g, 256, 0, stream>>>(n, prim, s.d_tri_in, s.d_tris);
-    return cudaGetLastError();
-}
-
-// Marks the wide-node roots and numbers them (exclusive scan in binary-node order).  The caller reads the count
-// (entry n_nodes of d_wide_index) and then calls wide_emit with an array of that many 128-byte records.
-cudaError_t wide_count(Scene& s, cudaStream_t stream)
-{
-    const uint32_t n = s.n_tris;
-    if (n == 0) return cudaSuccess;
-    const int n_internal = (int)s.n_nodes;
-    wide_mark_kernel<<<div_up(n_internal + 1, 256), 256, 0, stream>>>(n_internal, s.d_node_parent, s.d_visit, s.d_wide_index);
-    scan_exclusive(s.d_wide_index, (uint32_t)n_internal + 1u, s.d_scan_scratch, stream);
-    return cudaGetLastError();
-}
-
-cudaError_t wide_emit(Scene& s, cudaStream_t stream)
-{
-    if (s.n_tris == 0 || s.n_wide == 0) return cudaSuccess;
-    const int n_internal = (int)s.n_nodes;
-    wide_emit_kernel<<<div_up(n_internal, 256), 256, 0, stream>>>(n_internal, s.d_nodes, s.d_visit, s.d_wide_index, s.d_wnodes);
     return cudaGetLastError();
 }
 

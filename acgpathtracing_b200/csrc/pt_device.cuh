@@ -61,6 +61,12 @@ __device__ __forceinline__ float rnd(uint32_t& prev)                        // r
     return (float)(prev & 0x00ffffffu) * 5.9604644775390625e-8f;
 }
 
+// ---- pixel partition: the k-th tile of a launch that owns classes first .. first + span - 1 of n (tile L has class L % n) ----
+__host__ __device__ __forceinline__ uint32_t owned_tile(uint32_t k, uint32_t first, uint32_t span, uint32_t n)
+{
+    return span == 1u ? first + k * n : (k / span) * n + first + k % span;
+}
+
 // ---- acceleration-structure records (DESIGN.md "LBVH spec") ---------------------------------------------------
 // Node, 64 B = 4 x float4:  q0 = (lo0.xyz, child0)  q1 = (hi0.xyz, child1)  q2 = (lo1.xyz, 0)  q3 = (hi1.xyz, 0)
 //   child >= 0: internal node index; child < 0: leaf, ~child = slot in the leaf-ordered triangle array.
@@ -90,7 +96,6 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
 
 struct FetchGlobal {
     const float4 *nodes, *tris, *shade, *mats;
-    const float4* wnodes;   // wide nodes (8 float4 each), or null
     // quantised nodes (lbvh.cu quantize_nodes_kernel), 32 bytes = one LDG.E.256 per node: twelve 16-bit plane positions on
     // the scene's bounding-box grid (w0 = lo0.x | lo0.y << 16, w1 = lo0.z | hi0.x << 16, w2 = hi0.y | hi0.z << 16, w3..w5 the
     // same for child 1) and the two child references (w6, w7).  A plane is q * step + lo in ONE fused multiply-add, the same
@@ -122,7 +127,6 @@ struct FetchGlobal {
         ldg256(nodes + 4 * (size_t)i, q0, q1);
         ldg256(nodes + 4 * (size_t)i + 2, q2, q3);
     }
-    __device__ __forceinline__ void wnode2(int i, int k, float4& lo, float4& hi) const { ldg256(wnodes + 8 * (size_t)i + 2 * k, lo, hi); }
     // 48-byte triangle record in two loads instead of three: records start 32-byte aligned in even slots and at 16 mod 32
     // in odd ones, so one half of the record is always a whole aligned sector pair
     __device__ __forceinline__ void tri3(int i, float4& t0, float4& t1, float4& t2) const
@@ -134,16 +138,6 @@ struct FetchGlobal {
         } else {
             ldg256(p, t0, t1);
             t2 = __ldg(p + 2);
-        }
-    }
-    __device__ __forceinline__ void prefetch_wide_child(int c) const
-    {
-        if (c >= 0) {
-            const char* p = (const char*)(wnodes + 8 * (size_t)c);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 64));
-        } else {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"((const void*)(tris + 3 * (~c))));
         }
     }
     // a deferred child will be fetched after the subtree of its sibling: start pulling its record towards L2/L1 now
@@ -351,82 +345,6 @@ __device__ __forceinline__ void trav_node_step(Trav& t, const STK& stack, const 
     float4 q0, q1, q2, q3;
     f.node4(t.cur, q0, q1, q2, q3);
     trav_node_apply(t, stack, f, tmin, q0, q1, q2, q3);
-}
-
-// Warp-cooperative fetch of 32 different 64-byte records (one per lane; idx < 0 = this lane wants none): four
-// adjacent lanes read one record, 16 bytes each, so that an instruction touches 8 lines instead of 32 and every
-// request to L2 is a whole record; the warp then transposes through a 2 KB staging buffer in shared memory
-// (swizzled: stores and loads are conflict-free).  tools/fetchbench.cu: 2.3x the records/s of per-lane LDG.128 x4 when
-// the records come from DRAM, 1.25-1.4x from L2.  Must be called by all 32 lanes.
-__device__ __forceinline__ void coop_fetch64(const float4* __restrict__ recs, int idx, float4* stage, int lane, float4& q0,
-                                             float4& q1, float4& q2, float4& q3)
-{
-    const int sub = lane & 3, grp = lane >> 2;
-    float4 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int ridx = __shfl_sync(0xffffffffu, idx, 8 * k + grp);
-        v[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (ridx >= 0) v[k] = __ldg(recs + 4 * (size_t)ridx + sub);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) stage[sub * 32 + ((8 * k + grp + 2 * sub) & 31)] = v[k];
-    __syncwarp();
-    q0 = stage[0 * 32 + ((lane + 0) & 31)];
-    q1 = stage[1 * 32 + ((lane + 2) & 31)];
-    q2 = stage[2 * 32 + ((lane + 4) & 31)];
-    q3 = stage[3 * 32 + ((lane + 6) & 31)];
-    __syncwarp();
-}
-
-// Wide-node step: the four child boxes of a 128-byte record (two binary levels, lbvh.cu wide_emit_kernel) against
-// the ray, hit children visited nearest first, the others deferred farthest first.  Same boxes and the same slab
-// test as trav_node_step, so the set of leaves reached is a superset of what survives the shrinking tfar either
-// way and the closest hit under (t, primIdx) is the same.
-template <class FETCH, class STK>
-__device__ __forceinline__ void trav_wide_step(Trav& t, const STK& stack, const FETCH& f, float tmin)
-{
-    float tn[4];
-    int c[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float4 lo, hi;
-        f.wnode2(t.cur, k, lo, hi);
-        c[k] = __float_as_int(lo.w);
-        float tk;
-        const bool h = ray_box(t.r, f3(lo.x, lo.y, lo.z), f3(hi.x, hi.y, hi.z), tmin, t.tfar, tk) && c[k] != kTravDone;
-        tn[k] = h ? tk : __int_as_float(0x7f800000);
-    }
-    // sorting network on (tn, child): misses (+inf) end up last
-#define PTB_CSWAP(a, b)                         \
-    {                                           \
-        const bool s_ = tn[b] < tn[a];          \
-        const float lo_ = fminf(tn[a], tn[b]);  \
-        const float hi_ = fmaxf(tn[a], tn[b]);  \
-        const int ca_ = s_ ? c[b] : c[a];       \
-        const int cb_ = s_ ? c[a] : c[b];       \
-        tn[a] = lo_, tn[b] = hi_;               \
-        c[a] = ca_, c[b] = cb_;                 \
-    }
-    PTB_CSWAP(0, 1)
-    PTB_CSWAP(2, 3)
-    PTB_CSWAP(0, 2)
-    PTB_CSWAP(1, 3)
-    PTB_CSWAP(1, 2)
-#undef PTB_CSWAP
-    const float inf = __int_as_float(0x7f800000);
-    const int nhit = (tn[0] < inf ? 1 : 0) + (tn[1] < inf ? 1 : 0) + (tn[2] < inf ? 1 : 0) + (tn[3] < inf ? 1 : 0);
-    const bool can_pop = t.sp > 0;
-    const int top = stack.get(can_pop ? t.sp - 1 : 0);
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-        if (k < nhit) {
-            stack.put(t.sp + nhit - 1 - k, c[k]);      // farthest deepest: the nearest deferred child is popped first
-            f.prefetch_wide_child(c[k]);
-        }
-    }
-    t.cur = nhit > 0 ? c[0] : (can_pop ? top : kTravDone);
-    t.sp += nhit > 0 ? nhit - 1 : (can_pop ? -1 : 0);
 }
 
 // Leaf step.  any = false: closest hit in (tmin, tmax_closest) under (t, primIdx); any = true: the first hit in

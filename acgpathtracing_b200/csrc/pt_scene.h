@@ -34,14 +34,24 @@ struct WfTune {
     int smem_kb = 196;       // shared-memory budget for the paths when the scene is read from global memory: the largest
                              // carve-out step (..., 164, 196, 228 KB) that still leaves 60 KB of L1 (one step more costs C3 8 %)
     int shortlist = 1;       // per-pixel candidate lists for camera rays (tiny scenes)
-    int wide = -1;           // -1: follow Scene::traversal; 0 / 1: binary / wide nodes for scenes in global memory
     int idle_ns = 64;        // sleep of a warp that found every queue empty ...
     int idle_shift = 4;      // ... doubled for every further empty poll in a row, at most this many times (C3 +4 %: its idle polls
                              // were 21 % of the issued instructions; C2 and C4 unchanged)
     int stack_smem = 12;     // scenes in global memory: traversal-stack levels kept in shared memory, deeper ones spill to
                              // global memory (0 = all in shared memory).  C4: 672 -> 992 paths per CTA, +21 %
     int quant = -1;          // -1: follow Scene::traversal; 0 / 1: exact 64-byte / quantised 32-byte nodes for scenes in global memory
-    int coop = -1;           // -1 / 1: warp-cooperative fetch of the binary nodes of a scene in global memory; 0: per lane
+    int team = 1;            // sample teams: idle path slots take samples of a pixel another slot of their column is working on
+    int team_min = 2;        // ... when that pixel has at least this many samples left to hand out
+};
+
+struct TileOrder {           // one cached work order (render.cu tile_order_update)
+    uint32_t* d = nullptr;
+    uint32_t* h = nullptr;       // pinned staging copy
+    cudaEvent_t copied = nullptr;
+    size_t capacity = 0;
+    uint32_t count = 0;
+    float key[17] = {-1.f};
+    uint64_t stamp = 0;
 };
 
 struct Scene {
@@ -54,6 +64,7 @@ struct Scene {
     int pipeline = 0;              // 0 auto (wavefront when it can hold the scene), 1 persistent lane-per-path, 2 CTA-local wavefront
     WfTune wf;                     // scheduling constants of the wavefront kernel (measured defaults)
     bool count_enabled = false;
+    bool count_executed = false;   // counted launches run the kernel configuration of uncounted ones (candidate lists, quantised nodes)
     int sched[5] = {1, 1, 1, 1, 20};   // render-kernel stage weights (NODE, LEAF, SHADE, END) and NODE fast-path lane count
 
     // inputs (device copies of the TinyObjWrapper arrays)
@@ -90,15 +101,15 @@ struct Scene {
     float4* d_nodes_ploc = nullptr;   // 4 per node, same record; null when not built
     uint32_t ploc_depth = 0;
     float ploc_ms = 0.f;
+    bool ploc_tried = false;          // the PLOC build ran (it is lazy for scenes that have a SAH tree)
+    float sah_ms = 0.f;               // host time of the sweep-SAH build
     int tree = 0;                     // pt_scene_set_tree: 0 auto, 1 LBVH, 2 SAH, 3 PLOC
     // quantised 32-byte nodes of the tree in use (lbvh.cu quantize_nodes), built at the first launch that wants them
     float4* d_qnodes = nullptr;
     int qnodes_tree = 0;              // which tree (1 LBVH, 2 SAH, 3 PLOC) d_qnodes was made from; 0 = none
     float q_lo[3] = {0.f, 0.f, 0.f}, q_step[3] = {1.f, 1.f, 1.f};
-    uint32_t* d_wide_index = nullptr; // per binary node: index of the wide node rooted there (lbvh.cu wide_count)
-    float4* d_wnodes = nullptr;       // wide nodes, 8 per node (two binary levels per record)
-    uint32_t n_wide = 0;
-    int traversal = 0;                // pt_scene_set_traversal: 0 auto, 1 binary per lane, 2 wide (global), 3 binary cooperative (global), 4 quantised (global)
+    int traversal = 0;                // pt_scene_set_traversal: 0 auto, 1 exact nodes (staged when the scene fits), 2 exact nodes from
+                                      // global memory whatever the size, 3 quantised nodes (global memory)
 
     // launch-time scratch
     uint32_t* d_work_counter = nullptr;         // [0] pixel fetch counter  [1] LBVH depth (build)
@@ -110,17 +121,15 @@ struct Scene {
     // work order of the render kernels (render.cu tile_order_update): this rank's tiles, those a camera ray can hit
     // the scene through first.  Rebuilt when the key (image size, camera, partition) changes.
     float h_bounds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // scene AABB (lo xyz, hi xyz)
-    uint32_t* d_tile_order = nullptr;
-    size_t tile_order_capacity = 0;
-    uint32_t tile_order_count = 0;
-    float tile_order_key[16] = {-1.f};
+    TileOrder tile_orders[4];
+    uint64_t tile_order_clock = 0;
     bool tile_order_enabled = true;
 
     int* d_stack_over = nullptr;                // deeper stack levels of the wavefront kernel (scenes in global memory)
     size_t stack_over_capacity = 0;
 
     // last launch
-    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_wide = 0;   // last_wide: 0 binary per lane, 1 wide nodes, 2 binary cooperative, 3 binary quantised
+    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_trav = 0;   // last_trav: 0 exact 64-byte nodes, 1 quantised 32-byte nodes
 };
 
 constexpr uint32_t kSahMaxTris = 8192;    // the host build is O(n log^2 n); larger scenes keep the GPU-built LBVH
@@ -156,15 +165,13 @@ void sah_build_host(const float4* tri_bb, const uint32_t* sorted_prim, uint32_t 
 // lbvh.cu
 size_t lbvh_scan_scratch_entries(size_t n_tris);
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
-cudaError_t wide_count(Scene& s, cudaStream_t stream);
-cudaError_t wide_emit(Scene& s, cudaStream_t stream);
 cudaError_t ploc_build(Scene& s, cudaStream_t stream);
 cudaError_t quantize_nodes(Scene& s, cudaStream_t stream);
 
 // render.cu
 constexpr uint32_t kMaxFoldFrames = 64;
 cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint32_t n_ranks, cudaStream_t stream,
-                          const ptd::LaunchConst* probe_overrides, bool raw_mean = false);
+                          const ptd::LaunchConst* probe_overrides, bool raw_mean = false, uint32_t span = 1);
 cudaError_t fold_frames(void* accum, void* frame_out, const void* const* means, uint32_t first_frame, uint32_t n_frames,
                         uint32_t width, uint32_t height, cudaStream_t stream);
 cudaError_t trace_rays_device(Scene& s, const float* d_org, const float* d_dir, const float* d_tmin, const float* d_tmax,
@@ -174,11 +181,12 @@ cudaError_t partition_pack(const void* accum_full, const void* frame_full, void*
                            uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks, cudaStream_t stream);
 cudaError_t partition_unpack(const void* accum_compact_all, const void* frame_compact_all, void* accum_full,
                              void* frame_full, uint32_t width, uint32_t height, uint32_t n_ranks, cudaStream_t stream);
-uint32_t partition_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks);
+uint32_t partition_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks, uint32_t span);
 uint32_t partition_max_owned_tiles(uint32_t width, uint32_t height, uint32_t n_ranks);
 
 // wavefront.cu
 bool wavefront_supported(const Scene& s);
+bool wf_tune_apply(WfTune& t, const char* spec);   // "key=value,..."; false when a key is unknown
 cudaError_t wavefront_launch(Scene& s, const ptd::LaunchConst& lc, bool probe, cudaStream_t stream);
 
 // microbench.cu
@@ -186,7 +194,11 @@ cudaError_t bench_fp32_peak(double* tflops);
 cudaError_t bench_l2_bandwidth(double* gbps);
 cudaError_t bench_hbm_bandwidth(double* gbps);
 
-// error plumbing (capi.cu)
+// error plumbing and the registry of live scenes (capi.cu)
 void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);             // records the message, returns the code
+int cuda_fail(cudaError_t e, const char* what);         // PT_ERR_CUDA with the CUDA error's name and text
+Scene* scene_from_handle(uint64_t handle);              // null unless `handle` is a live pt_scene
+cudaError_t ensure_ploc(Scene& s);                      // builds the PLOC tree if the scene does not have it yet (current device)
 
 }  // namespace ptb

@@ -31,16 +31,16 @@ struct LaunchConst {   // everything a launch needs, passed by value as a kernel
     uchar4* frame_buffer;         // may be null
     // scene (global memory; kernels may stage it into shared memory)
     BvhView bvh;
-    const float4* wnodes;         // wide nodes (lbvh.cu wide_emit_kernel), 8 float4 each
     const float4* qnodes;         // quantised nodes of the tree in use (lbvh.cu quantize_nodes_kernel), 2 float4 each, or null
     float3 q_lo, q_step;
     uint32_t n_nodes, n_mats;
     const float4* tri_shade;      // per primitive: (N_0.xyz, material id)
     const DevMaterial* mats;      // 3 x float4 per material
-    // pixel partition (tiles of 8x4 pixels; tile L owned by rank L % n_ranks)
-    uint32_t tiles_x, tiles_y, rank, n_ranks, n_owned_tiles;
-    // work order: image tile of this rank's k-th work tile (expensive tiles first, render.cu tile_order_update);
-    // null = natural order rank + k * n_ranks
+    // pixel partition (tiles of 8x4 pixels; tile L belongs to class L % n_ranks; this launch owns the `span` classes
+    // rank .. rank + span - 1, i.e. its k-th tile is (k / span) * n_ranks + rank + k % span)
+    uint32_t tiles_x, tiles_y, rank, n_ranks, span, n_owned_tiles;
+    // work order: image tile of this launch's k-th work tile (expensive tiles first, render.cu tile_order_update);
+    // null = natural order
     const uint32_t* tile_order;
     // optional outputs
     unsigned long long* counters;   // pt_counters layout, or null

@@ -7,12 +7,16 @@
 //
 //   ptb_render --obj scene.obj [--width W --height H --spp N --depth D --direct --importance --frames F]
 //              [--background r g b] [--out image.ppm] [--accum-out file] [--accum-in file] [--pipeline 0|1|2]
+//              [--gpus N | --devices 0,1,...] [--transport peer|nccl]
+// With --gpus / --devices the frames are rendered by a pt_group (pt_launch_multi: all frames in one call, the image is
+// bit-identical to the single-GPU loop); the same device may be listed more than once with the peer transport.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <stdexcept>
 #include <string>
@@ -35,7 +39,8 @@ int main(int argc, char** argv)
     uint32_t width = 512, height = 512, spp = 128, depth = 4, frames = 1;   // :58-59, :43, :657
     bool direct = false, importance = false;                                // :655-656
     float bg[3] = {0.f, 0.f, 0.f};                                          // :568
-    int pipeline = 0;
+    int pipeline = 0, transport = PT_TRANSPORT_PEER;
+    std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&](const char* name) -> const char* {
@@ -55,6 +60,23 @@ int main(int argc, char** argv)
             else if (a == "--accum-out") accum_out = next("--accum-out");
             else if (a == "--accum-in") accum_in = next("--accum-in");
             else if (a == "--pipeline") pipeline = atoi(next("--pipeline"));
+            else if (a == "--gpus") {
+                const int n = atoi(next("--gpus"));
+                devices.clear();
+                for (int d = 0; d < n; ++d) devices.push_back(d);
+            } else if (a == "--devices") {
+                devices.clear();
+                std::string list = next("--devices");
+                for (size_t pos = 0; pos <= list.size();) {
+                    const size_t end = std::min(list.find(',', pos), list.size());
+                    devices.push_back(atoi(list.substr(pos, end - pos).c_str()));
+                    pos = end + 1;
+                }
+            } else if (a == "--transport") {
+                const std::string t = next("--transport");
+                if (t != "peer" && t != "nccl") throw std::runtime_error("--transport peer|nccl");
+                transport = t == "nccl" ? PT_TRANSPORT_NCCL : PT_TRANSPORT_PEER;
+            }
             else if (a == "--background") {
                 for (int c = 0; c < 3; ++c) bg[c] = (float)atof(next("--background"));
             } else {
@@ -76,11 +98,26 @@ int main(int argc, char** argv)
 
     pt_obj* obj = nullptr;
     pt_scene* scene = nullptr;
+    pt_group* group = nullptr;
     void *d_accum = nullptr, *d_frame = nullptr;
     int rc_main = 0;
     try {
         check(pt_obj_load(obj_path.c_str(), &obj));                                        // TinyObjWrapper obj(path) :650
-        check(pt_scene_create_from_obj(obj, &scene));                                      // :671-683
+        if (devices.empty()) {
+            check(pt_scene_create_from_obj(obj, &scene));                                  // :671-683
+        } else {
+            // several GPUs: one replica of the scene per device, owned by the group
+            check(pt_group_create_local(devices.data(), (uint32_t)devices.size(), transport, &group));
+            uint32_t nv = 0, ni = 0, nm = 0, nmat = 0;
+            check(pt_obj_counts(obj, &nv, &ni, &nm, &nmat));
+            std::vector<float> verts(nv);
+            std::vector<uint32_t> indices(ni), mat_ids(nm);
+            std::vector<pt_material> mats(nmat);
+            check(pt_obj_copy(obj, verts.data(), indices.data(), mat_ids.data(), mats.data()));
+            check(pt_group_scene_create(group, verts.data(), nv / 4, indices.data(), ni / 3, mat_ids.data(), mats.data(), nmat, &scene));
+            cuda_check(cudaSetDevice(devices[0]), "cudaSetDevice");
+            printf("Group: %zu device(s), %s transport\n", devices.size(), transport == PT_TRANSPORT_NCCL ? "NCCL" : "peer-copy");
+        }
         check(pt_scene_set_background(scene, bg[0], bg[1], bg[2]));
         check(pt_scene_set_pipeline(scene, pipeline));
         uint32_t n_tris = 0, n_nodes = 0;
@@ -131,7 +168,17 @@ int main(int argc, char** argv)
 
         double total_ms = 0.0;
         unsigned long long sample_sum = 0;
-        for (uint32_t f = 0; f < frames; ++f) {                                                                          // do ... while :700-730
+        if (group && frames) {
+            // the whole do-while of main (:700-730) in one collective call: frames dealt to the devices, slices folded in order
+            const auto t0 = std::chrono::high_resolution_clock::now();
+            check(pt_launch_multi(group, &params, frames, stream));
+            cuda_check(cudaStreamSynchronize(stream), "render");
+            params.currentFrameIdx += frames;
+            total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+            sample_sum = (unsigned long long)spp * frames;
+            printf("Frame Render Time: %.3fms (average over %u frames on %zu devices)", total_ms / frames, frames, devices.size());
+        }
+        for (uint32_t f = 0; f < frames && !group; ++f) {                                                                // do ... while :700-730
             const auto t0 = std::chrono::high_resolution_clock::now();
             check(pt_launch(&params, stream));                                                                           // LaunchCurrentFrame :184
             cuda_check(cudaStreamSynchronize(stream), "render");                                                         // CUDA_SYNC_CHECK :209
@@ -163,7 +210,8 @@ int main(int argc, char** argv)
     }
     if (d_accum) cudaFree(d_accum);                                                                                      // CleanAllTheThings :629
     if (d_frame) cudaFree(d_frame);
-    if (scene) pt_scene_destroy(scene);
+    if (group) pt_group_destroy(group);                                                                                 // destroys its scene replicas
+    else if (scene) pt_scene_destroy(scene);
     if (obj) pt_obj_free(obj);
     return rc_main;
 }

@@ -67,7 +67,7 @@ __device__ __forceinline__ bool take_pixel(const LaunchConst& lc, uint32_t n_wor
 {
     for (;;) {
         if (j >= n_work) return false;
-        const uint32_t tile = lc.tile_order ? __ldg(lc.tile_order + (j >> 5)) : lc.rank + (j >> 5) * lc.n_ranks;
+        const uint32_t tile = lc.tile_order ? __ldg(lc.tile_order + (j >> 5)) : owned_tile(j >> 5, lc.rank, lc.span, lc.n_ranks);
         const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
         ix = tx * 8u + (j & 7u);
         iy = ty * 4u + ((j >> 3) & 3u);
@@ -337,11 +337,14 @@ cudaError_t trace_rays_device(Scene& s, const float* d_org, const float* d_dir, 
     return cudaGetLastError();
 }
 
-// ---- pixel partition: tile k of rank r is image tile r + k * n_ranks (tiles of 8x4 pixels, row-major) ----------
-uint32_t partition_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks)
+// ---- pixel partition: tiles of 8x4 pixels, row-major; tile L has class L % n_ranks; a launch owns `span` consecutive
+// classes starting at `rank` (span = 1: tile k of rank r is image tile r + k * n_ranks) ----------------------------------
+uint32_t partition_owned_tiles(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks, uint32_t span)
 {
     const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
-    return rank < tiles ? (tiles - rank + n_ranks - 1) / n_ranks : 0;
+    uint32_t owned = 0;
+    for (uint32_t c = rank; c < rank + span && c < n_ranks; ++c) owned += c < tiles ? (tiles - c + n_ranks - 1) / n_ranks : 0;
+    return owned;
 }
 uint32_t partition_max_owned_tiles(uint32_t width, uint32_t height, uint32_t n_ranks)
 {
@@ -393,7 +396,7 @@ cudaError_t partition_pack(const void* accum_full, const void* frame_full, void*
 {
     const uint32_t tiles_x = (width + 7) / 8;
     const uint32_t cap = partition_max_owned_tiles(width, height, n_ranks);
-    const uint32_t owned = partition_owned_tiles(width, height, rank, n_ranks);
+    const uint32_t owned = partition_owned_tiles(width, height, rank, n_ranks, 1);
     const unsigned grid = (cap * 32u + 255u) / 256u;
     partition_pack_kernel<<<grid, 256, 0, stream>>>((const float4*)accum_full, (const uchar4*)frame_full, (float4*)accum_compact,
                                                     (uchar4*)frame_compact, width, height, tiles_x, rank, n_ranks, cap, owned);
@@ -421,14 +424,23 @@ static inline float3 to3(const pt_float3& v) { return make_float3(v.x, v.y, v.z)
 // the expensive tiles first the cheap ones fill the gaps at the end (longest-processing-time-first).  A tile counts as
 // expensive when the camera ray through its centre or one of its corners hits the scene's bounding box (host, double
 // precision; only the ORDER depends on it, never a pixel value).  Returns the device array or null (natural order).
-static const uint32_t* tile_order_update(Scene& s, const pt_params& p, uint32_t rank, uint32_t n_ranks, uint32_t owned,
-                                         cudaStream_t stream)
+static const uint32_t* tile_order_update(Scene& s, const pt_params& p, uint32_t rank, uint32_t n_ranks, uint32_t span,
+                                         uint32_t owned, cudaStream_t stream)
 {
     if (!s.tile_order_enabled || s.n_tris == 0 || owned == 0) return nullptr;
-    const float key[16] = {(float)p.width, (float)p.height, (float)rank, (float)n_ranks, p.cameraEye.x, p.cameraEye.y,
+    const float key[17] = {(float)span, (float)p.width, (float)p.height, (float)rank, (float)n_ranks, p.cameraEye.x, p.cameraEye.y,
                            p.cameraEye.z, p.cameraU.x, p.cameraU.y, p.cameraU.z, p.cameraV.x, p.cameraV.y, p.cameraV.z,
                            p.cameraW.x, p.cameraW.y, p.cameraW.z};
-    if (s.d_tile_order && s.tile_order_count == owned && memcmp(key, s.tile_order_key, sizeof(key)) == 0) return s.d_tile_order;
+    // a few orders are kept (a multi-GPU image alternates between whole frames and class ranges): a hit costs nothing and,
+    // unlike the upload below (pageable source: the copy waits for the stream), does not stall the host
+    TileOrder* slot = &s.tile_orders[0];
+    for (TileOrder& t : s.tile_orders) {
+        if (t.d && t.count == owned && memcmp(key, t.key, sizeof(key)) == 0) {
+            t.stamp = ++s.tile_order_clock;
+            return t.d;
+        }
+        if (t.stamp < slot->stamp) slot = &t;
+    }
     const uint32_t tiles_x = (p.width + 7) / 8;
     const double lo[3] = {s.h_bounds[0], s.h_bounds[1], s.h_bounds[2]}, hi[3] = {s.h_bounds[3], s.h_bounds[4], s.h_bounds[5]};
     const double o[3] = {p.cameraEye.x, p.cameraEye.y, p.cameraEye.z};
@@ -449,35 +461,45 @@ static const uint32_t* tile_order_update(Scene& s, const pt_params& p, uint32_t 
         }
         return tn <= tf;
     };
-    std::vector<uint32_t> order(owned);
-    uint32_t front = 0, back = owned;
+    // the slot's own pinned staging array: the upload is then truly asynchronous (a pageable source would make the copy wait
+    // for everything queued on the stream -- with several devices driven by one thread that serialises them)
+    if (slot->capacity < owned) {
+        if (slot->d) cudaFree(slot->d);
+        if (slot->h) cudaFreeHost(slot->h);
+        slot->d = nullptr;
+        slot->h = nullptr;
+        slot->capacity = 0;
+        slot->count = 0;
+        if (cudaMalloc((void**)&slot->d, sizeof(uint32_t) * owned) != cudaSuccess) return nullptr;
+        if (cudaMallocHost((void**)&slot->h, sizeof(uint32_t) * owned) != cudaSuccess) {
+            cudaFree(slot->d);
+            slot->d = nullptr;
+            return nullptr;
+        }
+        slot->capacity = owned;
+    }
+    if (!slot->copied && cudaEventCreateWithFlags(&slot->copied, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (slot->count) cudaEventSynchronize(slot->copied);   // the previous upload from this staging array has been read
+    slot->count = 0;
+    uint32_t* order = slot->h;
+    uint32_t front = 0;
     std::vector<uint32_t> cheap;
     cheap.reserve(owned);
     for (uint32_t k = 0; k < owned; ++k) {
-        const uint32_t tile = rank + k * n_ranks;
+        const uint32_t tile = owned_tile(k, rank, span, n_ranks);
         const double x0 = (tile % tiles_x) * 8.0, y0 = (tile / tiles_x) * 4.0;
         const bool expensive = hits(x0 + 4.0, y0 + 2.0) || hits(x0, y0) || hits(x0 + 8.0, y0) || hits(x0, y0 + 4.0) ||
                                hits(x0 + 8.0, y0 + 4.0);
         if (expensive) order[front++] = tile;
         else cheap.push_back(tile);
     }
-    (void)back;
     for (uint32_t t : cheap) order[front++] = t;
-    if (s.tile_order_capacity < owned) {
-        if (s.d_tile_order) cudaFree(s.d_tile_order);
-        s.d_tile_order = nullptr;
-        s.tile_order_capacity = 0;
-        if (cudaMalloc((void**)&s.d_tile_order, sizeof(uint32_t) * owned) != cudaSuccess) return nullptr;
-        s.tile_order_capacity = owned;
-    }
-    // pageable source: the copy is staged before the call returns, so `order` may go out of scope
-    if (cudaMemcpyAsync(s.d_tile_order, order.data(), sizeof(uint32_t) * owned, cudaMemcpyHostToDevice, stream) != cudaSuccess) {
-        s.tile_order_count = 0;
-        return nullptr;
-    }
-    s.tile_order_count = owned;
-    memcpy(s.tile_order_key, key, sizeof(key));
-    return s.d_tile_order;
+    if (cudaMemcpyAsync(slot->d, order, sizeof(uint32_t) * owned, cudaMemcpyHostToDevice, stream) != cudaSuccess) return nullptr;
+    cudaEventRecord(slot->copied, stream);
+    slot->count = owned;
+    slot->stamp = ++s.tile_order_clock;
+    memcpy(slot->key, key, sizeof(key));
+    return slot->d;
 }
 
 template <bool COUNT, bool PROBE, bool SMEM>
@@ -556,8 +578,9 @@ cudaError_t fold_frames(void* accum, void* frame_out, const void* const* means, 
 }
 
 cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint32_t n_ranks, cudaStream_t stream,
-                          const LaunchConst* probe_overrides, bool raw_mean)
+                          const LaunchConst* probe_overrides, bool raw_mean, uint32_t span)
 {
+    if (span == 0 || rank + span > n_ranks) return cudaErrorInvalidValue;
     LaunchConst lc = {};
     lc.raw_mean = raw_mean ? 1 : 0;
     lc.frame = params.currentFrameIdx;
@@ -580,7 +603,6 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.accum = (float4*)params.accumulationBuffer;
     lc.frame_buffer = raw_mean ? nullptr : (uchar4*)params.frameBuffer;
     lc.bvh = BvhView{scene_nodes(s), s.d_tris, s.n_tris};
-    lc.wnodes = s.d_wnodes;
     lc.n_nodes = s.n_nodes;
     lc.n_mats = s.n_mats;
     lc.tri_shade = s.d_tri_shade;
@@ -589,8 +611,9 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     lc.tiles_y = (params.height + 3) / 4;
     lc.rank = rank;
     lc.n_ranks = n_ranks;
-    lc.n_owned_tiles = partition_owned_tiles(params.width, params.height, rank, n_ranks);
-    lc.tile_order = tile_order_update(s, params, rank, n_ranks, lc.n_owned_tiles, stream);
+    lc.span = span;
+    lc.n_owned_tiles = partition_owned_tiles(params.width, params.height, rank, n_ranks, span);
+    lc.tile_order = tile_order_update(s, params, rank, n_ranks, span, lc.n_owned_tiles, stream);
     lc.counters = s.count_enabled ? s.d_counters : nullptr;
     lc.work_counter = s.d_work_counter;
     lc.error_flag = s.d_counters + 15;
@@ -607,10 +630,13 @@ cudaError_t render_launch(Scene& s, const pt_params& params, uint32_t rank, uint
     }
     if (lc.n_owned_tiles == 0) return cudaSuccess;
 
-    // pipeline 2 (wavefront.cu) whenever it can hold the scene, unless pipeline 1 was asked for
-    if (s.pipeline != 1 && wavefront_supported(s)) return wavefront_launch(s, lc, probe, stream);
+    // pipeline 2 (wavefront.cu) whenever it can hold the scene and the launch, unless pipeline 1 was asked for.  Its path
+    // record packs the depth into 8 bits and the pixel into 16 + 16 bits: deeper paths (maxDepth > 255 never terminates a
+    // path that Russian roulette keeps alive) and larger images run on pipeline 1, which has neither limit.
+    const bool wf_fits = params.maxDepth <= 255u && params.width <= 65535u && params.height <= 65535u;
+    if (s.pipeline != 1 && wf_fits && wavefront_supported(s)) return wavefront_launch(s, lc, probe, stream);
     if (s.pipeline == 2) return cudaErrorInvalidConfiguration;
-    s.last_wide = 0;
+    s.last_trav = 0;
 
     const size_t staged = staged_scene_float4s(s.n_nodes, s.n_tris, s.n_mats) * sizeof(float4);
     const bool smem = s.n_tris > 0 && staged <= kSmemSceneLimit;

@@ -91,7 +91,7 @@ __device__ __forceinline__ bool take_pixel(const LaunchConst& lc, uint32_t n_wor
 {
     for (;;) {
         if (j >= n_work) return false;
-        const uint32_t tile = lc.tile_order ? __ldg(lc.tile_order + (j >> 5)) : lc.rank + (j >> 5) * lc.n_ranks;
+        const uint32_t tile = lc.tile_order ? __ldg(lc.tile_order + (j >> 5)) : owned_tile(j >> 5, lc.rank, lc.span, lc.n_ranks);
         const uint32_t tx = tile % lc.tiles_x, ty = tile / lc.tiles_x;
         ix = tx * 8u + (j & 7u);
         iy = ty * 4u + ((j >> 3) & 3u);
@@ -196,15 +196,13 @@ __device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, cons
     return cand;
 }
 
-// TRAV (scenes in global memory only; 0 elsewhere): how NODE batches read the tree.
-//   TRAV_DIRECT  every lane reads its own 64-byte LBVH node (LDG.128 x4)
-//   TRAV_COOP    the warp reads its 32 nodes cooperatively, four lanes per record, and transposes through a per-warp
-//                staging buffer (pt_device.cuh coop_fetch64): 8 lines per instruction instead of 32
-//   TRAV_WIDE    wide nodes -- four child boxes, two LBVH levels, per 128-byte record (trav_wide_step)
+// TRAV (scenes in global memory only; TRAV_DIRECT elsewhere): how NODE batches read the tree.
+//   TRAV_DIRECT  every lane reads its own 64-byte node (two LDG.E.256)
 //   TRAV_QUANT   quantised nodes: twelve 16-bit planes + two child references in 32 bytes, ONE LDG.E.256 per lane and node
 //                (lbvh.cu quantize_nodes_kernel): half the L1 requests and half the node bytes of TRAV_DIRECT
-enum : int { TRAV_DIRECT = 0, TRAV_WIDE = 1, TRAV_COOP = 2, TRAV_QUANT = 3 };
-constexpr int kStageF4 = 128;          // float4s of staging per warp (TRAV_COOP)
+// (Round 1 also measured two-level wide nodes and a warp-cooperative transposed fetch; both lost on B200 --
+// profiles/r1_c3_c4_traversal_variants.txt -- and were removed.)
+enum : int { TRAV_DIRECT = 0, TRAV_QUANT = 1 };
 
 template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV>
 __global__ void __launch_bounds__(kWfBlock, 1)
@@ -226,8 +224,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     float4* S1 = S0 + NP;               // (next ray direction, add.y)
     uint32_t* CAND = reinterpret_cast<uint32_t*>(S1 + NP);          // per pixel: up to 4 leaves a camera ray can hit
     int* stack_mem = reinterpret_cast<int*>(CAND + NP);             // [stack_depth][NP]
-    float4* scene = reinterpret_cast<float4*>(stack_mem + (size_t)wc.stack_depth * NP);   // staged scene, or staging (TRAV_COOP)
-    constexpr bool WIDE = TRAV == TRAV_WIDE;
+    float4* scene = reinterpret_cast<float4*>(stack_mem + (size_t)wc.stack_depth * NP);   // staged scene
 
     typename WfFetch<SCENE>::type f;
     f.nodes = lc.bvh.nodes;
@@ -235,7 +232,6 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     f.shade = lc.tri_shade;
     f.mats = reinterpret_cast<const float4*>(lc.mats);
     if constexpr (SCENE < 0) {
-        f.wnodes = lc.wnodes;
         f.qnodes = lc.qnodes;
         f.q_lo = lc.q_lo;
         f.q_step = lc.q_step;
@@ -383,8 +379,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 if (__popc(bn) >= __popc(bl)) {
                     if (at_node) {
                         if (COUNT) ctr.n_node++;
-                        if constexpr (WIDE) trav_wide_step(t, stack, f, 0.01f);
-                        else if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
+                        if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
                         else trav_node_step(t, stack, f, 0.01f);
                     }
                 } else if (at_leaf) {
@@ -428,32 +423,15 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 const int n = __popc(__ballot_sync(kFull, at));
                 if (n == 0 || n * 8 < n0 * wc.node_keep8) break;
                 if (COUNT) st_steps++, st_step_lanes += n;
-                if constexpr (TRAV == TRAV_COOP) {
-                    float4 q0, q1, q2, q3;
-                    coop_fetch64(f.nodes, t.cur, scene + warp * kStageF4, lane, q0, q1, q2, q3);
-                    if (at) {
-                        if (COUNT) ctr.n_node++;
-                        trav_node_apply(t, stack, f, 0.01f, q0, q1, q2, q3);
-                    }
-                    if (__any_sync(kFull, t.cur >= 0)) {                         // second step under the same vote
-                        coop_fetch64(f.nodes, t.cur, scene + warp * kStageF4, lane, q0, q1, q2, q3);
-                        if (t.cur >= 0) {
-                            if (COUNT) ctr.n_node++;
-                            trav_node_apply(t, stack, f, 0.01f, q0, q1, q2, q3);
-                        }
-                    }
-                } else {
-                    if (at) {
-                        if (COUNT) ctr.n_node++;
-                        if constexpr (WIDE) trav_wide_step(t, stack, f, 0.01f);
-                        else if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
-                        else trav_node_step(t, stack, f, 0.01f);                 // tmin :754
-                    }
-                    if (!WIDE && t.cur >= 0) {                                   // second step under the same vote
-                        if (COUNT) ctr.n_node++;
-                        if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
-                        else trav_node_step(t, stack, f, 0.01f);
-                    }
+                if (at) {
+                    if (COUNT) ctr.n_node++;
+                    if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
+                    else trav_node_step(t, stack, f, 0.01f);                     // tmin :754
+                }
+                if (t.cur >= 0) {                                                // second step under the same vote
+                    if (COUNT) ctr.n_node++;
+                    if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
+                    else trav_node_step(t, stack, f, 0.01f);
                 }
             }
             if (active) {
@@ -680,6 +658,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                         (void)rnd(p.seed);                                                     // :765 (done anyway)
                         --left;
                         generate_camera_ray(lc, ix, iy, pixel_seed, p);
+                        if (COUNT) ctr.n_miss++, ctr.n_samples++, ctr.n_radiance++;
                     }
                     P0[pid] = pack(p.att, __uint_as_float(p.seed));
                     P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
@@ -700,6 +679,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                         const int leaf = (int)(c & 0xffu);
                         const float4 t0 = f.tri(leaf, 0), t1 = f.tri(leaf, 1), t2 = f.tri(leaf, 2);
                         float th;
+                        if (COUNT) ctr.n_tri++;
                         if (ray_tri(r, xyz(t0), xyz(t1), xyz(t2), 0.01f, 1e16f, th)) {         // tmin :754
                             const uint32_t prim = __float_as_uint(t0.w);
                             if (th < best_t || (th == best_t && prim < best_prim)) {
@@ -781,19 +761,12 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
 
 }  // namespace
 
-// How NODE batches read a scene that stays in global memory (pt_scene_set_traversal; PTB_TUNE wide= / coop= override).
-// Measured on B200 (gpurun wide1/wide2 logs): per-lane fetch of the binary LBVH is the fastest on C3 and
-// C4 (the upper levels are L1/L2-hot, where LDG.128 x4 per lane costs nothing extra); the cooperative fetch wins only
-// for DRAM-cold records (tools/fetchbench.cu) and wide nodes pay for their 128-byte per-lane fetch.  Both stay
-// selectable and bit-identical.
+// How NODE batches read a scene that stays in global memory (pt_scene_set_traversal; PTB_TUNE quant= overrides).
+// Measured on B200: per-lane 256-bit loads of the exact 64-byte nodes are the fastest while the records fit
+// in L2 (C3); above that the 32-byte quantised nodes win (C4).  Both are bit-identical in their pixels.
 static int choose_trav(const Scene& s, const WfTune& tune)
 {
-    const bool can_wide = s.n_wide != 0 && !s.count_enabled;   // the counted kernel walks the binary LBVH: its counters are the spec's
-    const bool wide = can_wide && (tune.wide >= 0 ? tune.wide != 0 : s.traversal == 2);
-    if (wide) return TRAV_WIDE;
-    // quantised nodes: never for counted launches (their counters are those of the exact boxes)
-    // (auto: only where the node and triangle records do not fit in L2 -- C4 +3 %; a scene that does fit is issue-bound and
-    // pays for the 36 extra instructions per node: C3 -12 %)
+    // quantised nodes: not for launches that count the SPECIFIED work (their counters are those of the exact boxes)
     static int l2_bytes = -1;
     if (l2_bytes < 0) {
         int dev = 0;
@@ -801,19 +774,81 @@ static int choose_trav(const Scene& s, const WfTune& tune)
         if (cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev) != cudaSuccess) l2_bytes = 0;
     }
     const bool larger_than_l2 = 64 * (size_t)s.n_nodes + 48 * (size_t)s.n_tris > (size_t)l2_bytes;
-    const bool quant = tune.quant >= 0 ? tune.quant != 0 : (s.traversal == 4 || (s.traversal == 0 && larger_than_l2));
-    if (!s.count_enabled && s.n_tris >= 2 && quant) return TRAV_QUANT;
-    return (tune.coop >= 0 ? tune.coop != 0 : s.traversal == 3) ? TRAV_COOP : TRAV_DIRECT;
+    const bool quant = tune.quant >= 0 ? tune.quant != 0 : (s.traversal == 3 || (s.traversal == 0 && larger_than_l2));
+    return ((!s.count_enabled || s.count_executed) && s.n_tris >= 2 && quant) ? TRAV_QUANT : TRAV_DIRECT;
+}
+
+// PTB_TUNE="node_votes=6,tail_cols=40,..." -- experiment overrides of WfTune from the environment, parsed once per
+// process; pt_scene_set_tune() applies the same "key=value,..." syntax to one scene.
+struct TuneKey {
+    const char* name;
+    int WfTune::*field;
+};
+static const TuneKey kTuneKeys[] = {{"node_votes_g", &WfTune::node_votes_g}, {"full_cols_g", &WfTune::full_cols_g},
+                                    {"node_votes", &WfTune::node_votes}, {"node_keep8", &WfTune::node_keep8},
+                                    {"full_cols", &WfTune::full_cols},   {"sticky", &WfTune::sticky},
+                                    {"tail_cols", &WfTune::tail_cols},   {"miss_loop", &WfTune::miss_loop},
+                                    {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
+                                    {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
+                                    {"quant", &WfTune::quant},           {"idle_ns", &WfTune::idle_ns},
+                                    {"idle_shift", &WfTune::idle_shift}, {"stack_smem", &WfTune::stack_smem},
+                                    {"team", &WfTune::team},             {"team_min", &WfTune::team_min}};
+
+bool wf_tune_apply(WfTune& t, const char* spec)
+{
+    if (!spec) return true;
+    bool ok = true;
+    const std::string str(spec);
+    size_t pos = 0;
+    while (pos < str.size()) {
+        size_t end = str.find(',', pos);
+        if (end == std::string::npos) end = str.size();
+        const std::string item = str.substr(pos, end - pos);
+        const size_t eq = item.find('=');
+        bool found = item.empty();
+        if (eq != std::string::npos)
+            for (const TuneKey& k : kTuneKeys)
+                if (item.compare(0, eq, k.name) == 0 && eq == strlen(k.name)) t.*(k.field) = atoi(item.c_str() + eq + 1), found = true;
+        ok = ok && found;
+        pos = end + 1;
+    }
+    // "node_votes=" / "full_cols=" without their "_g" twins apply to every scene (sweeps)
+    if (str.find("node_votes=") != std::string::npos && str.find("node_votes_g=") == std::string::npos) t.node_votes_g = t.node_votes;
+    if (str.find("full_cols=") != std::string::npos && str.find("full_cols_g=") == std::string::npos) t.full_cols_g = t.full_cols;
+    return ok;
+}
+
+// scene settings + environment overrides, clamped to what the kernel can run with
+static WfTune tuned(const WfTune& base)
+{
+    static const std::string env = [] {
+        const char* e = getenv("PTB_TUNE");
+        return std::string(e ? e : "");
+    }();
+    WfTune t = base;
+    if (!env.empty()) wf_tune_apply(t, env.c_str());
+    auto clamp = [](int& v, int lo, int hi) { v = v < lo ? lo : (v > hi ? hi : v); };
+    clamp(t.node_votes, 1, 64);
+    clamp(t.node_votes_g, 1, 64);
+    clamp(t.node_keep8, 0, 8);
+    clamp(t.full_cols, 1, 32);
+    clamp(t.full_cols_g, 1, 32);
+    clamp(t.sticky, 0, 64);
+    clamp(t.tail_cols, 0, 160);
+    clamp(t.miss_loop, 0, 1 << 20);
+    clamp(t.idle_ns, 0, 1 << 16);
+    clamp(t.idle_shift, 0, 10);
+    return t;
 }
 
 // Can the wavefront pipeline hold this scene?  Fills the launch layout when it can.
 static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size_t& smem_bytes, bool& smem_scene, int& trav)
 {
     if (s.n_mats > 0xffffu) return false;                 // material id is packed into 16 bits of the path record
-    uint32_t depth = scene_depth(s) + 1u;                 // deferred children never exceed the tree depth
+    const uint32_t depth = scene_depth(s) + 1u;           // deferred children never exceed the tree depth
     if (depth > 255u) return false;
     trav = TRAV_DIRECT;
-    const bool force_global = (s.traversal == 2 && !s.count_enabled && s.n_wide != 0) || s.traversal == 3 || s.traversal == 4;
+    const bool force_global = s.traversal == 2 || s.traversal == 3;
     const size_t scene_f4 = 4 * (size_t)s.n_nodes + 4 * (size_t)s.n_tris + 3 * (size_t)s.n_mats;
     const size_t fixed = (size_t)kCtlF4 * 16;
     const size_t per_path = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;   // state, candidate word, stack
@@ -835,18 +870,11 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
     // global-memory scene: node/triangle records come through L1/L2; the paths take most of the shared memory
     // (batch occupancy needs many more paths than threads) and the rest stays L1
     trav = choose_trav(s, tune);
-    // a wide step defers up to 3 children per wide level (two binary levels)
-    if (trav == TRAV_WIDE) depth = 3u * ((s.bvh_depth + 1u) / 2u) + 1u;
-    if (depth > 255u) {
-        trav = TRAV_DIRECT;
-        depth = scene_depth(s) + 1u;
-    }
     // shared-memory part of the stack: tune.stack_smem levels (deeper ones spill to global memory, StackSpill)
     const uint32_t smem_levels = (tune.stack_smem >= 2 && (uint32_t)tune.stack_smem < depth) ? (uint32_t)tune.stack_smem : depth;
     const size_t per_path_g = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)smem_levels;
-    const size_t per_warp = trav == TRAV_COOP ? (size_t)kStageF4 * 16 : 0;   // staging buffer of the cooperative fetch
     const size_t budget = (size_t)(tune.smem_kb >= 32 && tune.smem_kb <= 227 ? tune.smem_kb : 200) * 1024;
-    uint32_t P = (uint32_t)((budget - fixed) / (32 * per_path_g + per_warp));
+    uint32_t P = (uint32_t)((budget - fixed) / (32 * per_path_g));
     if (P > 32) P = 32;
     if (tune.paths32 >= 1 && (uint32_t)tune.paths32 < P) P = (uint32_t)tune.paths32;
     if (P < 4 && tune.paths32 < 1) return false;
@@ -854,7 +882,7 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
     wc.stack_depth = smem_levels;
     wc.stack_total = depth;
     wc.copies_shift = 0;
-    smem_bytes = fixed + wc.np * per_path_g + (P < 24u ? P : 24u) * per_warp;
+    smem_bytes = fixed + wc.np * per_path_g;
     smem_scene = false;
     return true;
 }
@@ -865,44 +893,7 @@ bool wavefront_supported(const Scene& s)
     size_t b;
     bool ss;
     int trav;
-    return wavefront_plan(s, s.wf, wc, b, ss, trav);
-}
-
-// PTB_TUNE="node_votes=6,tail_cols=40,..." -- experiment overrides of WfTune, read once per process.
-static WfTune tuned(const WfTune& base)
-{
-    WfTune t = base;
-    const char* env = getenv("PTB_TUNE");
-    if (!env) return t;
-    struct Key {
-        const char* name;
-        int WfTune::*field;
-    };
-    static const Key keys[] = {{"node_votes_g", &WfTune::node_votes_g}, {"full_cols_g", &WfTune::full_cols_g},
-                               {"node_votes", &WfTune::node_votes}, {"node_keep8", &WfTune::node_keep8},
-                               {"full_cols", &WfTune::full_cols},   {"sticky", &WfTune::sticky},
-                               {"tail_cols", &WfTune::tail_cols},   {"miss_loop", &WfTune::miss_loop},
-                               {"paths32", &WfTune::paths32},       {"block", &WfTune::block},
-                               {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
-                               {"wide", &WfTune::wide},             {"coop", &WfTune::coop},             {"quant", &WfTune::quant},
-                               {"idle_ns", &WfTune::idle_ns},       {"idle_shift", &WfTune::idle_shift},
-                               {"stack_smem", &WfTune::stack_smem}};
-    std::string str(env);
-    size_t pos = 0;
-    while (pos < str.size()) {
-        size_t end = str.find(',', pos);
-        if (end == std::string::npos) end = str.size();
-        const std::string item = str.substr(pos, end - pos);
-        const size_t eq = item.find('=');
-        if (eq != std::string::npos)
-            for (const Key& k : keys)
-                if (item.compare(0, eq, k.name) == 0 && eq == strlen(k.name)) t.*(k.field) = atoi(item.c_str() + eq + 1);
-        pos = end + 1;
-    }
-    // "node_votes=" / "full_cols=" without their "_g" twins apply to every scene (sweeps)
-    if (str.find("node_votes=") != std::string::npos && str.find("node_votes_g=") == std::string::npos) t.node_votes_g = t.node_votes;
-    if (str.find("full_cols=") != std::string::npos && str.find("full_cols_g=") == std::string::npos) t.full_cols_g = t.full_cols;
-    return t;
+    return wavefront_plan(s, tuned(s.wf), wc, b, ss, trav);
 }
 
 cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaStream_t stream)
@@ -921,7 +912,7 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     wc.miss_loop = tune.miss_loop;
     wc.block_override = tune.block;
     wc.idle_ns = tune.idle_ns;
-    wc.idle_shift = tune.idle_shift < 0 ? 0 : (tune.idle_shift > 10 ? 10 : tune.idle_shift);
+    wc.idle_shift = tune.idle_shift;
     wc.stack_over = nullptr;
     if (!smem_scene && wc.stack_total > wc.stack_depth) {
         int dev = 0, sms = 0;
@@ -943,12 +934,7 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     // cheap, i.e. tiny scenes staged with 8 copies.  The counted kernel always traverses, so that its node / triangle
     // counters stay the ones of the specified traversal (and equal to the oracle's).
     const bool use_short = scene == 3 && s.n_tris <= 64 && tune.shortlist != 0;
-    s.last_wide = 0;
-    if (scene < 0 && trav == TRAV_WIDE) {
-        s.last_wide = 1;
-        return probe ? launch_wavefront<false, true, -1, false, TRAV_WIDE>(s, lc, wc, smem_bytes, stream)
-                     : launch_wavefront<false, false, -1, false, TRAV_WIDE>(s, lc, wc, smem_bytes, stream);
-    }
+    s.last_trav = 0;
     if (scene < 0 && trav == TRAV_QUANT) {
         cudaError_t qe = quantize_nodes(s, stream);
         if (qe != cudaSuccess) return qe;
@@ -957,24 +943,19 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
             lq.qnodes = s.d_qnodes;
             lq.q_lo = make_float3(s.q_lo[0], s.q_lo[1], s.q_lo[2]);
             lq.q_step = make_float3(s.q_step[0], s.q_step[1], s.q_step[2]);
-            s.last_wide = 3;
-            return probe ? launch_wavefront<false, true, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream)
-                         : launch_wavefront<false, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
+            s.last_trav = 1;
+            if (probe) return launch_wavefront<false, true, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
+            if (count) return launch_wavefront<true, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
+            return launch_wavefront<false, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
         }
         trav = TRAV_DIRECT;                              // a box could not be contained (never expected): exact nodes
-    }
-    if (scene < 0 && trav == TRAV_COOP) {
-        s.last_wide = 2;
-        if (probe) return launch_wavefront<false, true, -1, false, TRAV_COOP>(s, lc, wc, smem_bytes, stream);
-        if (count) return launch_wavefront<true, false, -1, false, TRAV_COOP>(s, lc, wc, smem_bytes, stream);
-        return launch_wavefront<false, false, -1, false, TRAV_COOP>(s, lc, wc, smem_bytes, stream);
     }
 #define PTB_WF_DISPATCH(COUNT, PROBE, SHORT)                                                      \
     (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream)   \
      : scene == 0 ? launch_wavefront<COUNT, PROBE, 0, false, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream)   \
                   : launch_wavefront<COUNT, PROBE, -1, false, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream))
     if (probe) return use_short ? PTB_WF_DISPATCH(false, true, true) : PTB_WF_DISPATCH(false, true, false);
-    if (count) return PTB_WF_DISPATCH(true, false, false);
+    if (count) return (use_short && s.count_executed) ? PTB_WF_DISPATCH(true, false, true) : PTB_WF_DISPATCH(true, false, false);
     return use_short ? PTB_WF_DISPATCH(false, false, true) : PTB_WF_DISPATCH(false, false, false);
 #undef PTB_WF_DISPATCH
 }

@@ -1,12 +1,14 @@
-"""Owned-pixel exchange between ranks (one process per GPU): the one collective of the multi-GPU path.
+"""Multi-GPU rendering with one process per GPU (torchrun): the host side.
 
-Each rank renders the 8x4-pixel tiles it owns (pt_launch_partition) into full-size buffers for every launch of an
-image, keeps their running average on its own device, and after the LAST launch calls ``ImageExchange.gather`` once:
-pack owned pixels -> all-gather (NCCL on GPUs, gloo in the CPU tests) -> unpack, after which every rank holds the
-complete accumulation and frame buffers, bit-identical to a single-GPU run.
+The product path is ``rank_group`` -> ``api.Group.launch``: plan, slice exchange (NCCL), ordered fold and gather all happen
+inside ``libptb200.so`` (csrc/multigpu.cu, include/ptb200.h ``pt_launch_multi``); Python only ships the 128-byte NCCL id
+from rank 0 to the other ranks.
 
-The pack/unpack index math is acgpathtracing_b200/partition.py; on CUDA tensors it runs as the library's
-partition_pack/unpack kernels (include/ptb200.h), on CPU tensors as the numpy mirror -- same layout, same result.
+``MirrorGroup`` restates the same algorithm on CPU tensors -- the plan and the slices come from the library's own host-only
+entry points (``pt_multi_plan``, ``pt_multi_slice``), the exchange runs over ``torch.distributed`` (gloo in the CPU tests),
+the fold is numpy -- so that the N > 1 logic (who renders what, which piece of a frame a pixel is read from, the frame
+order of the running average, pathTracerPrograms.cu:803-811) is tested with world_size 2 and 3 on machines without a GPU
+(tests/test_multirank_gloo.py).  It is test infrastructure: nothing on the GPU path calls it.
 """
 import numpy as np
 import torch
@@ -15,68 +17,26 @@ import torch.distributed as dist
 from . import partition as P
 
 
-class ImageExchange:
-    def __init__(self, width, height, rank, world, device):
-        self.w, self.h, self.rank, self.world = width, height, rank, world
-        self.device = torch.device(device)
-        self.cap = P.capacity(width, height, world)
-        self.cuda = self.device.type == "cuda"
-        if world > 1:
-            self.my_acc = torch.zeros((self.cap, 4), dtype=torch.float32, device=self.device)
-            self.my_fb = torch.zeros((self.cap, 4), dtype=torch.uint8, device=self.device)
-            # rank-major concatenation (the layout pt_partition_unpack reads)
-            self.all_acc = torch.zeros((world * self.cap, 4), dtype=torch.float32, device=self.device)
-            self.all_fb = torch.zeros((world * self.cap, 4), dtype=torch.uint8, device=self.device)
-
-    def bytes_per_rank(self):
-        """Bytes this rank receives in one gather (accumulation + frame buffer of all ranks)."""
-        return 0 if self.world == 1 else self.world * self.cap * 20
-
-    def gather(self, acc, fb, stream=None):
-        """acc: (h, w, 4) float32, fb: (h, w, 4) uint8 or None -- full-size, valid at this rank's pixels; completed in
-        place.  Returns the number of library kernels launched."""
-        if self.world == 1:
-            return 0
-        if self.cuda:
-            from . import api
-            api.partition_pack(acc.data_ptr(), fb.data_ptr() if fb is not None else 0, self.my_acc.data_ptr(),
-                               self.my_fb.data_ptr() if fb is not None else 0, self.w, self.h, self.rank, self.world, stream)
-        else:
-            self.my_acc.copy_(torch.from_numpy(P.pack_numpy(acc.numpy(), self.w, self.h, self.rank, self.world)))
-            if fb is not None:
-                self.my_fb.copy_(torch.from_numpy(P.pack_numpy(fb.numpy(), self.w, self.h, self.rank, self.world)))
-        dist.all_gather_into_tensor(self.all_acc, self.my_acc)
-        if fb is not None:
-            dist.all_gather_into_tensor(self.all_fb, self.my_fb)
-        if self.cuda:
-            from . import api
-            api.partition_unpack(self.all_acc.data_ptr(), self.all_fb.data_ptr() if fb is not None else 0, acc.data_ptr(),
-                                 fb.data_ptr() if fb is not None else 0, self.w, self.h, self.world, stream)
-        else:
-            acc.copy_(torch.from_numpy(P.unpack_numpy(self.all_acc.numpy().reshape(self.world, self.cap, 4), self.w, self.h, self.world)))
-            if fb is not None:
-                fb.copy_(torch.from_numpy(P.unpack_numpy(self.all_fb.numpy().reshape(self.world, self.cap, 4), self.w, self.h, self.world)))
-        return 2
+def rank_group(rank, world, device_index=None):
+    """One process per GPU: every rank calls this once (collective).  Returns an api.Group on the current CUDA device."""
+    from . import api
+    if device_index is not None:
+        torch.cuda.set_device(device_index)
+    box = [api.group_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    return api.Group.rank(box[0], rank, world)
 
 
-def owned_mask(width, height, rank, world):
-    """bool[h, w]: pixels rendered by `rank`."""
-    return P.owner_map(width, height, world) == rank
-
-
-# ---- frame-parallel rendering: several launches ("frames") per image, more than one rank ---------------------------------
-def frame_plan(n_frames, world):
-    """Which rank renders what.  The mean image of frame k depends only on (pixel, k) (pathTracerPrograms.cu:721), so
-    whole frames can go to different ranks: frames 0 .. rounds*world-1 are dealt round-robin (frame k -> rank k % world,
-    full image, no tail of a small per-rank pixel share); the n_frames % world leftover frames are rendered by all ranks
-    together with the tile partition.  Returns (rounds, leftover_frames)."""
-    rounds = n_frames // world
-    return rounds, list(range(rounds * world, n_frames))
+def owned_mask(width, height, rank, world, n_classes=1):
+    """bool[h, w]: pixels of the tiles whose class (tile index % world) is in [rank, rank + n_classes)."""
+    cls = P.owner_map(width, height, world)
+    return (cls >= rank) & (cls < rank + n_classes)
 
 
 def fold_numpy(means, first_frame=0, acc=None):
-    """CPU mirror of pt_fold_frames: the reference's running average (pathTracerPrograms.cu:803-811) over per-launch mean
-    images (h, w, 4) float32, in frame order.  Returns (h, w, 4) with alpha 1."""
+    """CPU mirror of the fold kernels: the reference's running average (pathTracerPrograms.cu:803-811) over per-launch mean
+    images (..., 4) float32, in frame order.  Returns an array of the same shape with alpha 1."""
     out = None if acc is None else acc[..., :3].astype(np.float32).copy()
     for k, x in enumerate(means):
         f = first_frame + k
@@ -86,70 +46,85 @@ def fold_numpy(means, first_frame=0, acc=None):
         else:
             a = np.float32(1.0) / np.float32(f + 1)
             out = out + a * (x3 - out)
-    res = np.ones(out.shape[:2] + (4,), np.float32)
+    res = np.ones(out.shape[:-1] + (4,), np.float32)
     res[..., :3] = out
     return res
 
 
-class FrameParallel:
-    """Renders `n_frames` launches of one image on `world` ranks and leaves the complete running average (and frame
-    buffer) on every rank, bit-identical to the same launches issued one after the other on one GPU.
+class MirrorGroup:
+    """CPU restatement of pt_launch_multi for one rank of `world` (see the module docstring).
 
-    render_raw(frame, rank, n_ranks, out) must write the launch's own mean for the tiles of (rank, n_ranks) into the
-    (h, w, 4) float32 tensor `out` (pt_launch_raw on GPUs; the CPU tests pass a stand-in)."""
+    render_raw(frame, first_class, n_classes, n_ranks, out): writes the launch's own mean of `frame` for the tiles of
+    classes [first_class, first_class + n_classes) of n_ranks into the (h, w, 4) float32 array `out` (whole frame:
+    first_class 0, n_classes == n_ranks).  Pixels outside the job may hold anything -- the fold never reads them."""
 
-    def __init__(self, width, height, rank, world, device, n_frames, render_raw, fold=None, make_color=None):
-        self.w, self.h, self.rank, self.world, self.n = width, height, rank, world, n_frames
-        self.device = torch.device(device)
-        self.cuda = self.device.type == "cuda"
-        self.render_raw, self.fold_fn, self.make_color = render_raw, fold, make_color
-        self.rounds, self.leftover = frame_plan(n_frames, world)
-        f32 = dict(dtype=torch.float32, device=self.device)
-        self.mine = torch.zeros((max(self.rounds, 1), height, width, 4), **f32)
-        self.all_whole = torch.zeros((world * max(self.rounds, 1), height, width, 4), **f32) if world > 1 else self.mine
-        self.shared = torch.zeros((max(len(self.leftover), 1), height, width, 4), **f32)
-        self.exchange = ImageExchange(width, height, rank, world, device)
+    def __init__(self, width, height, rank, world, render_raw):
+        from . import api
+        self.api = api
+        self.w, self.h, self.rank, self.world = width, height, rank, world
+        self.render_raw = render_raw
+        self.slices = [api.multi_slice(width, height, r, world) for r in range(world)]
+        self.cls = P.owner_map(width, height, world).reshape(-1)
 
-    def my_frames(self):
-        """(frame index, kind) in the order this rank renders them."""
-        return [(i * self.world + self.rank, "whole") for i in range(self.rounds)] + [(f, "tiles") for f in self.leftover]
-
-    def render(self, frame, kind):
-        if kind == "whole":
-            self.render_raw(frame, 0, 1, self.mine[frame // self.world])
-        else:
-            self.render_raw(frame, self.rank, self.world, self.shared[frame - self.rounds * self.world])
-        return 1
-
-    def bytes_received(self):
-        if self.world == 1:
-            return 0
-        return self.world * self.rounds * self.w * self.h * 16 + len(self.leftover) * self.world * self.exchange.cap * 16
-
-    def finish(self, acc, fb, stream=None):
-        """Exchange the means and fold them in frame order into acc (h, w, 4) f32 and fb (h, w, 4) u8 (or None)."""
-        launches = 0
-        if self.world > 1:
-            if self.rounds:
-                dist.all_gather_into_tensor(self.all_whole.view(self.world * self.rounds, -1), self.mine.view(self.rounds, -1))
-            for i in range(len(self.leftover)):
-                launches += self.exchange.gather(self.shared[i], None, stream)
-        frames = []
-        for k in range(self.n):
-            if k < self.rounds * self.world:
-                r, i = k % self.world, k // self.world
-                frames.append(self.all_whole[r * self.rounds + i] if self.world > 1 else self.mine[i])
-            else:
-                frames.append(self.shared[k - self.rounds * self.world])
-        if self.cuda:
-            from . import api
-            for c in range(0, self.n, 64):
-                api.fold_frames(acc.data_ptr(), fb.data_ptr() if fb is not None else 0, [t.data_ptr() for t in frames[c:c + 64]],
-                                c, self.w, self.h, stream)
-                launches += 1
-        else:
-            res = fold_numpy([t.numpy() for t in frames])
-            acc.copy_(torch.from_numpy(res))
-            if fb is not None and self.make_color is not None:
-                fb.copy_(torch.from_numpy(self.make_color(res)))
-        return launches
+    def launch(self, acc, first_frame, n_launches):
+        """acc: (h, w, 4) float32 numpy, complete image of the frames before first_frame (ignored when first_frame == 0);
+        folded in place with frames first_frame .. first_frame + n_launches - 1.  Returns the jobs this rank rendered."""
+        w, h, me, world = self.w, self.h, self.rank, self.world
+        if world == 1:
+            means = []
+            for k in range(n_launches):
+                out = np.zeros((h, w, 4), np.float32)
+                self.render_raw(first_frame + k, 0, 1, 1, out)
+                means.append(out)
+            acc[...] = fold_numpy(means, first_frame, acc)
+            return [(k, 0, 0, 1) for k in range(n_launches)]
+        plan = self.api.multi_plan(n_launches, world)
+        rendered = {}
+        for q, (frame, r, c0, nc) in enumerate(plan):
+            if r != me:
+                continue
+            out = np.full((h, w, 4), np.nan, np.float32)          # poison: a read outside the job's tiles shows up
+            self.render_raw(first_frame + frame, c0, nc, world, out)
+            rendered[q] = out.reshape(-1, 4)
+        # exchange: slice d of every job goes to rank d (same order on both sides of every pair)
+        b, n = self.slices[me]
+        pieces = {}
+        ops, keep = [], []
+        for q, (frame, r, c0, nc) in enumerate(plan):
+            if r == me:
+                pieces[q] = rendered[q][b:b + n]
+                for d in range(world):
+                    if d != me and self.slices[d][1]:
+                        db, dn = self.slices[d]
+                        t = torch.from_numpy(np.ascontiguousarray(rendered[q][db:db + dn]))
+                        keep.append(t)
+                        ops.append(dist.P2POp(dist.isend, t, d))
+            elif n:
+                t = torch.empty((n, 4), dtype=torch.float32)
+                pieces[q] = t.numpy()
+                ops.append(dist.P2POp(dist.irecv, t, r))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        # fold my slice in frame order; a frame rendered in shares is read from the piece whose classes own the pixel
+        flat = acc.reshape(-1, 4)
+        cls = self.cls[b:b + n]
+        means = []
+        for k in range(n_launches):
+            m = np.zeros((n, 4), np.float32)
+            for q, (frame, r, c0, nc) in enumerate(plan):
+                if frame == k:
+                    sel = (cls >= c0) & (cls < c0 + nc)
+                    m[sel] = pieces[q][sel]
+            means.append(m)
+        if n:
+            flat[b:b + n] = fold_numpy(means, first_frame, flat[b:b + n])
+        # gather the folded slices on every rank
+        cap = max(s[1] for s in self.slices)
+        mine = torch.zeros((cap, 4), dtype=torch.float32)
+        mine[:n] = torch.from_numpy(flat[b:b + n])
+        everyone = [torch.zeros((cap, 4), dtype=torch.float32) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+        for r, (rb, rn) in enumerate(self.slices):
+            flat[rb:rb + rn] = everyone[r][:rn].numpy()
+        return [j for j in plan if j[1] == me]

@@ -9,13 +9,14 @@ samples for every pixel folded into the running average; step i uses currentFram
 1024 spp of config C2.  Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline,
 cpu_baseline, e2e, clocks, gpu_launches, grays_per_s).
 
-For N > 1 (torchrun, one rank per GPU) the scene and LBVH are replicated, 8x4-pixel tiles are interleaved over
-ranks.  The K launches of the image are dealt to the ranks as WHOLE frames (frame k -> rank k % N, K // N rounds; the
-mean image of a frame depends only on (pixel, frame index), pathTracerPrograms.cu:721); the K % N leftover frames are
-rendered by all ranks together, 8x4-pixel tiles interleaved.  The timed region ends with ONE exchange (NCCL all-gather of
-the per-frame means) and the reference's running average applied in frame order (pt_fold_frames), after which every
-rank holds the complete image, bit-identical to K launches on one GPU (acgpathtracing_b200/multirank.py).
-`--partition tiles` forces the pure tile partition instead.  Total work is fixed as N grows ("strong" scaling).
+For N > 1 (torchrun, one rank per GPU) every rank joins a pt_group and the K launches of the image are ONE call of
+pt_launch_multi (include/ptb200.h; csrc/multigpu.cu): scene and acceleration structure replicated, whole frames dealt to the
+ranks (frame k -> rank k % N; the mean image of a frame depends only on (pixel, frame index), pathTracerPrograms.cu:721),
+the K % N leftover frames cut into (frame, tile-class range) sub-shares so that every rank renders exactly K / N frames'
+worth of pixels; slice j of every rendered frame goes to rank j over NCCL, rank j applies the reference's running average
+to its slice in frame order, the folded slices are gathered: every rank ends with the complete image, bit-identical to K
+launches on one GPU.  `--partition tiles` issues K calls of one launch each instead (every launch split N ways -- the
+reference's one-optixLaunch-per-displayed-frame usage).  Total work is fixed as N grows ("strong" scaling).
 """
 import argparse
 import json
@@ -43,6 +44,18 @@ FLOP_NODE, FLOP_TRI = 24, 45
 FLOP_SAMPLE, FLOP_SEGMENT, FLOP_NEE = 40, 20, 60
 FLOP_HIT = (110, 190, 120)
 BYTES_NODE, BYTES_TRI = 64, 48
+
+
+def _load_profile_facts():
+    """profiles/facts.json: per workload the DRAM bytes and warp instructions of ONE launch, read by tools/ncu_facts.py from
+    the committed `ncu --set full` summaries under profiles/ (file named per entry)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "facts.json")))
+    except Exception:
+        return {}
+
+
+PROFILE_FACTS = _load_profile_facts()
 
 
 def algorithmic_work(c, nee):
@@ -195,7 +208,15 @@ def run_b200(args):
     if args.spp:
         spp = args.spp
     arr = make_scene_arrays(scene_name)
-    scene = api.Scene(arr)
+    group = None
+    t_create = time.perf_counter()
+    if world > 1:
+        from acgpathtracing_b200.multirank import rank_group
+        group = rank_group(rank, world)                  # NCCL communicator inside libptb200.so
+        scene = group.create_scene(arr)
+    else:
+        scene = api.Scene(arr)
+    scene_create_ms = 1e3 * (time.perf_counter() - t_create)
     if args.pipeline:
         scene.set_pipeline(args.pipeline)
     if args.tree:
@@ -205,10 +226,8 @@ def run_b200(args):
 
     acc = torch.zeros((h, w, 4), dtype=torch.float32, device=dev)
     fb = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
-    from acgpathtracing_b200.multirank import FrameParallel, ImageExchange
-    exchange = ImageExchange(w, h, rank, world, dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    frame_mode = world > 1 and args.partition == "auto"
+    per_launch_calls = world > 1 and args.partition == "tiles"
 
     def params(frame, acc_ptr=None, fb_ptr=None):
         p = api.make_params(w, h, spp, md, frame=frame, nee=nee, importance=imp, scene=scene)
@@ -216,33 +235,25 @@ def run_b200(args):
         p.frameBuffer = fb.data_ptr() if fb_ptr is None else fb_ptr
         return p
 
-    def render_raw(frame, r, n, out):
-        api.launch_raw(params(frame, out.data_ptr(), 0), r, n, stream)
-
-    fp = FrameParallel(w, h, rank, world, dev, args.steps, render_raw) if frame_mode else None
-
-    def my_steps():
-        """The launches this rank issues for one image: [(frame, kind)]."""
-        return fp.my_frames() if frame_mode else [(i, "seq") for i in range(args.steps)]
-
-    def step(frame, kind="seq"):
-        """One launch of the hot path with device-resident buffers; returns the number of our kernels launched."""
-        if kind != "seq":
-            return fp.render(frame, kind)
+    def step(frame):
+        """One launch of the hot path with device-resident buffers (N = 1); returns the number of our kernels launched."""
         p = params(frame)
         if args.emulate_ranks > 1:
             api.launch_partition(p, 0, args.emulate_ranks, stream)   # tuning aid: one rank's share of an N-rank job
-        elif world == 1:
-            api.launch(p, stream)
         else:
-            api.launch_partition(p, rank, world, stream)
+            api.launch(p, stream)
         return 1
 
-    def finish():
-        """N > 1: the one exchange of the image; returns the number of our kernels launched."""
-        if frame_mode:
-            return fp.finish(acc, fb, stream)
-        return exchange.gather(acc, fb, stream)
+    def image():
+        """N > 1: the K launches of the image through pt_launch_multi; returns the kernels this rank launched."""
+        if per_launch_calls:
+            n = 0
+            for i in range(args.steps):
+                group.launch(params(i), 1, stream)
+                n += group.last_kernels()
+            return n
+        group.launch(params(0), args.steps, stream)
+        return group.last_kernels()
 
     def barrier():
         if world > 1:
@@ -250,44 +261,47 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- warm-up ------------------------------------------------------------------------------------------------
-    if frame_mode:                                    # at least args.warmup launches per rank, in whole images
-        reps = -(-args.warmup // max(len(my_steps()), 1))
-        for _ in range(max(reps, 1)):
-            for f, kind in my_steps():
-                step(f, kind)
+    if world > 1:                                     # at least args.warmup launches, in whole images
+        for _ in range(max(1, -(-args.warmup // max(args.steps, 1)))):
+            image()
     else:
         for i in range(args.warmup):
             step(i)
-    finish()
     barrier()
 
-    # ---- timed region: the image's K launches (this rank's share of them), CUDA events around each, L2 flushed between
-    # launches, then the exchange ---------------------------------------------------------------------------------------
+    # ---- timed region: the image's K launches, CUDA events on the launching stream (pt_launch_multi is stream-ordered),
+    # N = 1: L2 flushed between launches ------------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
-    todo = my_steps()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(len(todo) + 1)]
     launches = 0
     barrier()
     t_wall0 = time.perf_counter()
-    for i, (f, kind) in enumerate(todo):
-        flush_buf.fill_(i & 0xFF)                     # evict L2 (untimed)
-        ev[i][0].record()
-        launches += step(f, kind)
-        ev[i][1].record()
-    ev[-1][0].record()
-    launches += finish()                              # N > 1: exchange (+ ordered fold), timed
-    ev[-1][1].record()
+    if world == 1:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            flush_buf.fill_(i & 0xFF)                 # evict L2 (untimed)
+            ev[i][0].record()
+            launches += step(i)
+            ev[i][1].record()
+    else:
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))]
+        flush_buf.fill_(1)
+        ev[0][0].record()
+        launches += image()
+        ev[0][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    exchange_ms = step_ms[-1]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    n_launch = torch.tensor([launches], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_launch)
     total_ms = float(total_ms.item())
+    launches = int(n_launch.item())
+    phases = group.last_timing(0) if world > 1 else None
     clocks = sampler.stop() if sampler else None
     checksum = float(acc[..., :3].double().mean().item())
     acc_after_timed = acc.clone()           # for the bit-for-bit comparison with the host-buffer path below
@@ -295,23 +309,32 @@ def run_b200(args):
     pixel_samples = float(w) * h * spp * args.steps / max(args.emulate_ranks, 1)
     value = pixel_samples / (total_ms * 1e-3) / 1e6
 
-    # ---- work counters for the timed frames (instrumented kernel, untimed) -> Grays/s and algorithmic flops ----
-    scene.enable_counters(True)
-    scene.counters(reset=True)
-    for f, kind in my_steps():
-        step(f, kind)
-    finish()
-    barrier()
-    c = scene.counters(reset=True)
-    sched = scene.sched_stats(reset=True)
-    scene.enable_counters(False)
-    ct = torch.tensor([c["n_samples"], c["n_radiance"], c["n_shadow"], c["n_node"], c["n_tri"], *c["n_hit"], c["n_miss"]],
-                      dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(ct)
-    ct = [int(x) for x in ct.tolist()]
-    counters = dict(n_samples=ct[0], n_radiance=ct[1], n_shadow=ct[2], n_node=ct[3], n_tri=ct[4], n_hit=ct[5:8], n_miss=ct[8])
+    # ---- work counters for the timed frames (instrumented kernel, untimed) -> Grays/s and algorithmic flops.  Two passes:
+    # the SPECIFIED work (every ray through the tree named in config.pipeline.tree; equals the oracle's counts) and the
+    # EXECUTED work of the timed kernel (camera rays of tiny scenes resolved from candidate lists, quantised nodes) ----
+    def counted(mode):
+        scene.enable_counters(mode)
+        scene.counters(reset=True)
+        if world > 1:
+            image()
+        else:
+            for i in range(args.steps):
+                step(i)
+        barrier()
+        c = scene.counters(reset=True)
+        sched = scene.sched_stats(reset=True)
+        scene.enable_counters(False)
+        ct = torch.tensor([c["n_samples"], c["n_radiance"], c["n_shadow"], c["n_node"], c["n_tri"], *c["n_hit"], c["n_miss"]],
+                          dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(ct)
+        ct = [int(x) for x in ct.tolist()]
+        return dict(n_samples=ct[0], n_radiance=ct[1], n_shadow=ct[2], n_node=ct[3], n_tri=ct[4], n_hit=ct[5:8], n_miss=ct[8]), sched
+
+    counters, sched = counted(1)
+    counters_exec, _ = counted(2)
     flops, tbytes = algorithmic_work(counters, nee)
+    flops_exec, tbytes_exec = algorithmic_work(counters_exec, nee)
     rays = counters["n_radiance"] + counters["n_shadow"]
 
     # ---- end to end through the host-buffer entry point (pt_launch_host): pinned host buffers, H2D + D2H in the
@@ -344,48 +367,26 @@ def run_b200(args):
                "ms_per_step": 1e3 * t_e2e / args.steps,
                "bit_identical_to_device_path": bool(torch.equal(h_acc.view(torch.int32), acc_after_timed.cpu().view(torch.int32)))}
     else:
-        # every rank: per launch the params record goes up and the launch's result comes down to a pinned host buffer
-        # (tile mode: previous accumulation up, accumulation + frame buffer down); after the last launch the exchange and
-        # a read of the complete image
+        # every rank: pt_launch_multi_host with pinned host buffers -- the image's K launches in one call, the complete image
+        # downloaded on every rank
         h_acc = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory()
         h_fb = torch.zeros((h, w, 4), dtype=torch.uint8).pin_memory()
-        up = down = 0
 
-        def host_step(i, f, kind):
-            nonlocal up, down
-            if kind == "seq":
-                if f > 0:
-                    acc.copy_(h_acc, non_blocking=True)
-                    up += w * h * 16
-                step(f, kind)
-                h_acc.copy_(acc, non_blocking=True)
-                h_fb.copy_(fb, non_blocking=True)
-                down += w * h * 20
-            else:
-                step(f, kind)
-                src = fp.mine[f // world] if kind == "whole" else fp.shared[f - fp.rounds * world]
-                h_acc.copy_(src, non_blocking=True)
-                down += w * h * 16
-            up += 168
-            torch.cuda.synchronize()
+        def host_image():
+            up = down = 0
+            calls = [(i, 1) for i in range(args.steps)] if per_launch_calls else [(0, args.steps)]
+            for f0, k in calls:
+                p = api.make_params(w, h, spp, md, frame=f0, nee=nee, importance=imp, scene=scene)
+                p.accumulationBuffer, p.frameBuffer = h_acc.data_ptr(), h_fb.data_ptr()
+                a, b = group.launch_host(p, k)
+                up += a
+                down += b
+            return up, down
 
-        def host_finish():
-            nonlocal down
-            finish()
-            h_acc.copy_(acc, non_blocking=True)
-            h_fb.copy_(fb, non_blocking=True)
-            down += w * h * 20
-            torch.cuda.synchronize()
-
-        for i, (f, kind) in enumerate(todo[:1]):
-            host_step(i, f, kind)
-        host_finish()
+        host_image()
         barrier()
-        up = down = 0
         t0 = time.perf_counter()
-        for i, (f, kind) in enumerate(todo):
-            host_step(i, f, kind)
-        host_finish()
+        up, down = host_image()
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
@@ -393,7 +394,7 @@ def run_b200(args):
         e2e = {"value": pixel_samples / t_e2e / 1e6, "unit": "Mpixel-samples/s",
                "h2d_bytes_per_step": up // args.steps, "d2h_bytes_per_step": down // args.steps,
                "ms_per_step": 1e3 * t_e2e / args.steps,
-               "note": "bytes moved by rank 0 divided by the image's K steps; includes the final full-image read",
+               "note": "pt_launch_multi_host on every rank; bytes moved by rank 0 divided by the image's K steps",
                "bit_identical_to_device_path": bool(torch.equal(h_acc.view(torch.int32), acc_after_timed.cpu().view(torch.int32)))}
 
     # ---- roofline denominators measured on this device -----------------------------------------------------------
@@ -410,31 +411,59 @@ def run_b200(args):
         l2_meas = api.bench_l2_bandwidth()
         sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
         fp32_nominal = dinfo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
-        # average duration of one render kernel on rank 0 (its own launches, exchange excluded)
-        kernel_ms = sum(step_ms[:-1]) / max(len(todo), 1)
-        per_launch_share = 1.0 / args.steps if (world == 1 or frame_mode) else 1.0 / args.steps / world
-        if frame_mode and fp.leftover:        # mixed whole / tile launches: use the job-wide average per launch issued
-            per_launch_share = 1.0 / (world * len(todo))
-        ach_tflops = flops * per_launch_share / (kernel_ms * 1e-3) / 1e12
-        ach_gbs = tbytes * per_launch_share / (kernel_ms * 1e-3) / 1e9
+        # Render-kernel time on rank 0 and the share of the image's work it did there.  N = 1: the K launches, one kernel each.
+        # N > 1: the render phase of pt_launch_multi (CUDA events inside the library); the plan gives every rank 1/N of the work.
+        if world == 1:
+            render_ms, n_kernels, share = sum(step_ms), args.steps, 1.0
+        else:
+            render_ms, n_kernels, share = phases["render_ms"], max(phases["kernels"] - 1, 1), 1.0 / world
+        kernel_ms = render_ms / n_kernels
+        facts = PROFILE_FACTS.get(args.workload) if (args.pipeline != 1 and not args.spp and not args.tree and world == 1) else None
+        sm_count = dinfo["sm_count"]
+        sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+
+        def rates(fl, by):
+            tf = fl * share / (render_ms * 1e-3) / 1e12
+            gb = by * share / (render_ms * 1e-3) / 1e9
+            return {"flops_per_launch": fl / args.steps, "bytes_per_launch": by / args.steps, "tflops": tf, "fp32_frac": tf / fp32_meas,
+                    "record_gbs": gb, "l2_frac": gb / l2_meas}
+
+        spec, exe = rates(flops, tbytes), rates(flops_exec, tbytes_exec)
+        # which roofline bounds the kernel: scenes staged in shared memory have no memory traffic to speak of (FP32 / issue
+        # bound); scenes read from global memory are bound by the record fetches through L1/L2
+        in_smem = scene.last_launch_info()["smem_bytes"] > 205 * 1024
+        bound = "fp32" if in_smem else "l2"
         roofline = {
             "kernel": "render_persistent_kernel" if args.pipeline == 1 else "render_wavefront_kernel",
-            "bound": "fp32", "achieved": ach_tflops, "peak": fp32_meas, "unit": "TFLOP/s", "frac": ach_tflops / fp32_meas,
-            "peak_source": "measured live by pt_bench_fp32_peak (dependent-free FFMA loop); MEASURED_PEAKS.json has no FP32 figure",
-            "peak_nominal": fp32_nominal,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this
-            # command on C2 (profiles/r1_v3g_sah_wavefront_ncu_summary.txt: 682,496 + 522,752 B); other workloads: not captured
-            "traffic": 1205248 if (args.workload == "c2" and args.pipeline != 1 and not args.spp and not args.tree) else None,
-            "l2": {"achieved": ach_gbs, "peak": l2_meas, "unit": "GB/s", "frac": ach_gbs / l2_meas,
-                   "note": "node/triangle record bytes; served from shared memory when the scene is staged there"},
-            "hbm": {"achieved": (w * h * 36) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
-                    "unit": "GB/s", "note": "image traffic only: 16 B read + 16 B write + 4 B framebuffer per pixel per launch"},
-            "algorithmic_flops_per_launch": flops / args.steps, "algorithmic_bytes_per_launch": tbytes / args.steps,
-            "algorithmic_note": "work of the SPECIFIED traversal (every ray through the tree named in config.pipeline.tree), counted by "
-                                "the instrumented kernel and equal to the oracle's counts; the timed kernel resolves camera rays of "
-                                "tiny scenes from per-pixel candidate lists instead, which lowers the work done, not the work credited",
+            "bound": bound,
+            "achieved": exe["tflops"] if bound == "fp32" else exe["record_gbs"],
+            "peak": fp32_meas if bound == "fp32" else l2_meas,
+            "unit": "TFLOP/s" if bound == "fp32" else "GB/s",
+            "frac": exe["fp32_frac"] if bound == "fp32" else exe["l2_frac"],
+            "achieved_is": "EXECUTED algorithmic work of the timed kernel (counter mode 2) / its CUDA-event time",
+            "peak_source": ("measured live by pt_bench_fp32_peak (dependent-free FFMA loop)" if bound == "fp32" else
+                            "measured live by pt_bench_l2_bandwidth (streaming read of an L2-resident buffer)") +
+                           "; MEASURED_PEAKS.json has no such figure",
+            "peak_nominal_fp32": fp32_nominal,
+            "kernel_ms": kernel_ms,
+            "executed": exe,
+            "specified": dict(spec, note="every ray through the tree named in config.pipeline.tree, exact nodes: the oracle's counts"),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload
+            "traffic": facts["dram_bytes"] if facts else None,
+            "traffic_source": facts["file"] if facts else None,
+            "hbm": {"achieved": (facts["dram_bytes"] if facts else w * h * 36) / (kernel_ms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"),
+                    "unit": "GB/s", "note": "measured DRAM bytes of the ncu capture / this run's kernel time" if facts else
+                    "image traffic only: 16 B read + 16 B write + 4 B framebuffer per pixel per launch"},
             "per_gpu": world > 1,
         }
+        if facts:
+            # issue-slot roofline: warp instructions the kernel issues per launch (ncu smsp__inst_executed.sum) against the
+            # schedulers' capacity, 4 per SM and clock
+            peak_ginst = sm_count * 4 * sm_mhz * 1e6 / 1e9
+            ach_ginst = facts["warp_inst"] / (kernel_ms * 1e-3) / 1e9
+            roofline["issue"] = {"warp_inst_per_launch": facts["warp_inst"], "achieved": ach_ginst, "peak": peak_ginst,
+                                 "unit": "Gwarp-inst/s", "frac": ach_ginst / peak_ginst, "sm_mhz": sm_mhz,
+                                 "source": facts["file"] + " (smsp__inst_executed.sum; deterministic for a given frame)"}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_run(args.workload, steps=1, warmup=0, prefer_ref=False, target_step_s=12.0)
             cpu = {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
@@ -448,16 +477,19 @@ def run_b200(args):
                        "spp_per_step": spp, "max_depth": md, "direct_lighting": nee, "importance_sampling": imp,
                        "frames": f"0..{args.steps - 1}",
                        "parallelism": f"pixel-tiles x{world}" + (f" (EMULATED rank 0 of {args.emulate_ranks}: not a bench value)" if args.emulate_ranks > 1 else ""),
-                       "l2": "flushed between timed steps (256 MiB fill)", "pipeline": dict(scene.last_launch_info(), tree=scene.tree_in_use()),
+                       "l2": "flushed between timed steps (256 MiB fill)" if world == 1 else
+                             "flushed before the call; the K launches of one pt_launch_multi call write K distinct scratch frames (> L2 together)",
+                       "pipeline": dict(scene.last_launch_info(), tree=scene.tree_in_use()),
                        "exchange": "none (1 GPU)" if world == 1 else (
-                           f"frames dealt to ranks ({fp.rounds} whole frame(s) per rank, {len(fp.leftover)} tile-partitioned); one "
-                           f"all-gather of per-frame means + ordered fold per image, {fp.bytes_received()} B received per rank, "
-                           f"{exchange_ms:.3f} ms on rank 0" if frame_mode else
-                           f"one all-gather of owned pixels per image, {exchange.bytes_per_rank()} B received per rank, {exchange_ms:.3f} ms on rank 0"),
+                           ("K calls of pt_launch_multi with one launch each (every launch split N ways)" if per_launch_calls else
+                            "one pt_launch_multi call: whole frames per rank + class-range sub-shares of the leftover frames") +
+                           f"; slices over NCCL send/recv, ordered fold per slice, gather; rank 0 device time: render "
+                           f"{phases['render_ms']:.3f} ms, exchange + fold {phases['exchange_fold_ms']:.3f} ms, gather {phases['gather_ms']:.3f} ms"),
+                       "scene_create_ms": scene_create_ms,
                        "lbvh_build_ms": info["build_ms"]},
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "rays_per_sample": rays / max(counters["n_samples"], 1),
-            "counters": counters, "sched_rank0": sched, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "counters": counters, "counters_executed": counters_exec, "sched_rank0": sched, "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "image_mean_radiance": checksum,
         }

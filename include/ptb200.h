@@ -79,7 +79,10 @@ int pt_scene_info(const pt_scene* scene, uint32_t* n_tris, uint32_t* n_nodes, fl
 /* ---- launch: replaces cudaMemcpyAsync(d_params) + optixLaunch(pipeline, stream, d_params, ..., w, h, 1)
  * (PathTracerMain.cpp:191-206).  One call = one subframe of samplesPerPixel samples per pixel folded into
  * the running average with weight 1/(currentFrameIdx+1) (pathTracerPrograms.cu:803-811); the caller
- * increments currentFrameIdx (:714).  Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default). ---- */
+ * increments currentFrameIdx (:714).  Asynchronous on `cuda_stream` (a cudaStream_t; NULL = default).
+ * A pt_scene holds the launch scratch (work counter, work order, spill stacks, watchdog flag): at most ONE launch per
+ * scene may be in flight, i.e. all launches of a scene go to the same stream (or are separated by a synchronisation),
+ * as in the reference (one stream, :161).  Different scenes and devices may be driven concurrently. ---- */
 int pt_launch(const pt_params* params, void* cuda_stream);
 
 /* Pixel-partitioned launch for multi-GPU rendering: renders only the 8x4-pixel tiles owned by `rank` of
@@ -109,13 +112,83 @@ int pt_partition_pack(const void* accum_full, const void* frame_full, void* accu
 int pt_partition_unpack(const void* accum_compact_all, const void* frame_compact_all, void* accum_full,
                         void* frame_full, uint32_t width, uint32_t height, uint32_t n_ranks, void* cuda_stream);
 
+/* ---- multi-GPU: one image on several B200s through this ABI (SURVEY.md 8e, Appendix D pt_launch_multi).  The reference
+ * is single-GPU: LaunchCurrentFrame (PathTracerMain.cpp:184-210) calls optixLaunch once per subframe on one device; a
+ * host that wants N GPUs calls pt_launch_multi where it called pt_launch.  Scene and acceleration structure are replicated
+ * (the builds are deterministic), pixel-samples are partitioned, and the result is bit-identical to the same launches on
+ * one GPU because a pixel's RNG stream depends only on (pixel index, currentFrameIdx) (pathTracerPrograms.cu:721).
+ *
+ * Work split for n_launches subframes ("frames") on n_ranks GPUs (pt_multi_plan is that function, host only):
+ *   - n_launches / n_ranks rounds of WHOLE frames, frame k -> rank k % n_ranks, each rendered as its own mean
+ *     (pt_launch_raw), so no GPU is ever left with a small share of a frame;
+ *   - the n_launches % n_ranks = L leftover frames are cut into L * n_ranks sub-shares (frame, tile class) and rank r
+ *     takes sub-shares [r L, (r + 1) L): consecutive tile classes of one frame (sometimes the end of one frame and the
+ *     start of the next), e.g. 4 frames on 8 GPUs = half a frame each, 1 frame on 8 GPUs = the classic 1/8 tile share.
+ * Exchange: the image is cut into n_ranks contiguous pixel slices (pt_multi_slice); every rendered frame (or share)
+ * sends slice j to rank j, rank j applies the reference's running average (:803-811) to its slice in frame order, and
+ * the folded slices are gathered: K/N + 1 images received per rank instead of K.
+ * Transport: NCCL send/recv between processes (one process per GPU: pt_group_create_rank; ncclCommInitRank) or inside
+ * one process (pt_group_create_local with transport 1; ncclCommInitAll); peer-to-peer copy engines inside one process
+ * by default (transport 0: cudaMemcpyPeerAsync over NVLink, no SM taken from the render kernel). ---------------------- */
+typedef struct pt_group pt_group;
+typedef struct {
+    uint32_t frame;        /* 0 .. n_launches-1, added to params.currentFrameIdx */
+    uint32_t rank;         /* who renders it */
+    uint32_t first_class;  /* tile classes first_class .. first_class + n_classes - 1 of n_ranks (tile L has class L % n_ranks) */
+    uint32_t n_classes;    /* n_ranks = the whole frame */
+} pt_multi_job;
+/* jobs in exchange order; *n_jobs receives the count (<= n_launches + 2 * n_ranks); capacity 0 + jobs NULL = count only */
+int pt_multi_plan(uint32_t n_launches, uint32_t n_ranks, pt_multi_job* jobs, uint32_t capacity, uint32_t* n_jobs);
+/* pixel slice [first, first + count) of the row-major image that `rank` folds */
+int pt_multi_slice(uint32_t width, uint32_t height, uint32_t rank, uint32_t n_ranks, uint64_t* first_pixel, uint64_t* n_pixels);
+
+#define PT_GROUP_ID_BYTES 128
+#define PT_TRANSPORT_PEER 0   /* cudaMemcpyPeerAsync between the devices of one process */
+#define PT_TRANSPORT_NCCL 1
+/* One process drives n_devices GPUs (the reference's single-threaded host).  The same device may be listed more than once
+ * with PT_TRANSPORT_PEER (tests on one GPU).  Ranks are 0 .. n_devices-1 in list order; rank 0's device holds the caller's
+ * buffers. */
+int pt_group_create_local(const int* devices, uint32_t n_devices, int transport, pt_group** out);
+/* One process per GPU (torchrun, MPI): rank 0 calls pt_group_unique_id and ships the PT_GROUP_ID_BYTES bytes to the
+ * other ranks by its own means; then EVERY rank calls pt_group_create_rank with its current CUDA device (collective). */
+int pt_group_unique_id(void* id_bytes);
+int pt_group_create_rank(const void* id_bytes, uint32_t rank, uint32_t n_ranks, pt_group** out);
+void pt_group_destroy(pt_group* group);                    /* also destroys the group's scene replicas */
+int pt_group_info(const pt_group* group, uint32_t* n_ranks, uint32_t* n_local, uint32_t* first_rank, int* transport);
+/* pt_scene_create on every local device of the group (replaces the group's previous scene).  *out = the replica on the
+ * group's first local device: its handle goes into pt_params.handle, and its settings (background, pipeline, tree,
+ * traversal, tune, counters on/off) are applied to every local replica at each pt_launch_multi; pt_group_scene(group, i) =
+ * the replica of local member i (to read its counters).  In a process-per-GPU group every rank sets its own replica. */
+int pt_group_scene_create(pt_group* group, const float* verts_xyzw, uint32_t n_verts, const uint32_t* indices, uint32_t n_tris,
+                          const uint32_t* mat_ids, const pt_material* materials, uint32_t n_materials, pt_scene** out);
+pt_scene* pt_group_scene(const pt_group* group, uint32_t local_index);
+/* Renders subframes currentFrameIdx .. currentFrameIdx + n_launches - 1 and folds them into accumulationBuffer /
+ * frameBuffer exactly as n_launches calls of pt_launch on one GPU would (replaces the do-while of main :700-730 for a
+ * multi-GPU host).  params: DEVICE buffers on this rank's device (process-per-GPU: every rank passes its own and every
+ * rank ends up with the complete image; local group: buffers on rank 0's device), handle = pt_group_scene_create's.
+ * Collective over the group; stream-ordered on `cuda_stream` (a stream of the first local device) like pt_launch. */
+int pt_launch_multi(pt_group* group, const pt_params* params, uint32_t n_launches, void* cuda_stream);
+/* The same with HOST buffers (the end-to-end entry point): uploads this process's slices of the previous accumulation
+ * when currentFrameIdx > 0, renders, downloads the image (process-per-GPU: the complete image on every rank; local
+ * group: each device writes its own slice into the one host image); synchronous.  Reports the bytes this process moved. */
+int pt_launch_multi_host(pt_group* group, const pt_params* params_host_buffers, uint32_t n_launches, uint64_t* h2d_bytes,
+                         uint64_t* d2h_bytes);
+/* Device time of the phases of the last pt_launch_multi* call on local member `local_index` (CUDA events; synchronises):
+ * ms[0] render, ms[1] slice exchange + fold, ms[2] final gather, ms[3] whole call; n_kernels = kernels of this library
+ * it launched there. */
+int pt_group_last_timing(pt_group* group, uint32_t local_index, float ms[4], uint32_t* n_kernels);
+
 /* Same launch with HOST buffers: uploads the previous accumulation when currentFrameIdx > 0, renders,
  * downloads accumulation (and frame buffer if non-NULL); synchronous.  This is the call the end-to-end
  * benchmark times.  Reports the bytes moved. */
 int pt_launch_host(const pt_params* params_host_buffers, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 /* ---- counters and tuning ----------------------------------------------------------------------------- */
-int pt_scene_enable_counters(pt_scene* scene, int enable);   /* counted launches use an instrumented kernel */
+/* Counted launches use an instrumented kernel.  enable = 1: the SPECIFIED work -- every ray walks the exact nodes of the tree
+ * in use (the counts equal the CPU oracle's); enable = 2: the EXECUTED work of an uncounted launch -- camera rays of tiny
+ * scenes resolved from per-pixel candidate lists (their triangle tests counted, no node visits), quantised nodes where
+ * the launch would use them; 0: off.  The pixels are the same in all three. */
+int pt_scene_enable_counters(pt_scene* scene, int enable);
 int pt_scene_get_counters(pt_scene* scene, pt_counters* out, int reset);
 /* Scheduler statistics of counted launches (wavefront pipeline): out16[0..3] batches run per stage (NODE, LEAF,
  * SHADE, END), [4..7] lanes that held a path in those batches, [8] NODE steps, [9] lanes active in NODE steps,
@@ -129,26 +202,31 @@ int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
  *   1 = the Morton-order LBVH, built on the GPU (always built; pt_bvh_export);
  *   2 = a sweep-SAH tree, built on the host at pt_scene_create for scenes of 2..8192 triangles (18-27 % fewer node
  *       visits than the LBVH);
- *   3 = a PLOC tree (parallel locally-ordered clustering, radius 8), built on the GPU for every scene of >= 2
- *       triangles (22-27 % fewer node visits on the 2 M-triangle scene);
+ *   3 = a PLOC tree (parallel locally-ordered clustering, radius 8), built on the GPU: at pt_scene_create where it is
+ *       the tree the kernels will walk (no usable SAH tree), else the first time it is asked for (22-27 % fewer node
+ *       visits than the LBVH on the 2 M-triangle scene);
  *   0 = auto: 2 where it exists, else 3, else 1 (a tree more than 64 levels deep is passed over).
  * Asking for a tree the scene does not have, or one deeper than 64 levels, is PT_ERR_INVALID.  Replaces the build
  * flags of optixAccelBuild (PathTracerMain.cpp:334-339). */
 int pt_scene_set_tree(pt_scene* scene, int tree);
 int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH, 3 PLOC */
-/* How the render kernel walks the acceleration structure:
- *   0 = auto: 1, except 4 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
- *   1 = the binary tree in use, every lane fetches its own 64-byte node (from shared memory when the scene fits);
- *   2 = wide nodes (two LBVH levels per 128-byte record), scene read from global memory whatever its size;
- *   3 = the binary tree in use with a warp-cooperative node fetch (four lanes per 64-byte node, transposed through
- *       shared memory), scene read from global memory whatever its size;
- *   4 = quantised nodes: 32 bytes per node (twelve 16-bit plane positions on the grid of the scene's bounding box,
+/* How the render kernel reads the acceleration structure:
+ *   0 = auto: 1, except 3 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
+ *   1 = the exact 64-byte nodes of the tree in use, every lane fetches its own (from shared memory when the scene fits);
+ *   2 = the same, but read from global memory whatever the scene's size (tests, A/B runs);
+ *   3 = quantised nodes: 32 bytes per node (twelve 16-bit plane positions on the grid of the scene's bounding box,
  *       rounded outwards and checked, + two child references), one 256-bit load per node; scene read from global memory.
  * The pixels do not depend on it: every variant culls with boxes that contain the tree's own and every hit comes from
  * the same triangle test (OptiX's acceleration structure, PathTracerMain.cpp:311-398, is closed). */
 int pt_scene_set_traversal(pt_scene* scene, int traversal);
-int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 binary tree per lane, 1 wide nodes,
-                                                         2 warp-cooperative node fetch, 3 quantised nodes */
+int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 exact nodes, 1 quantised nodes */
+/* Scheduling constants of the render kernel for ONE scene: "key=value,key=value" (keys: csrc/pt_scene.h WfTune).  They
+ * change how paths are batched, never a pixel (tests/test_gpu_parity.py::test_schedule_perturbation).  The environment
+ * variable PTB_TUNE, read once per process, overrides them for every scene.  PT_ERR_INVALID for an unknown key. */
+int pt_scene_set_tune(pt_scene* scene, const char* spec);
+/* pt_launch* are asynchronous: a kernel watchdog that fired (the scheduler made no progress -- never expected) is only
+ * seen here or by pt_launch_host / pt_scene_get_counters.  Synchronises the scene's device; PT_ERR_CUDA if it fired. */
+int pt_scene_check_error(pt_scene* scene);
 int pt_scene_last_launch_info(const pt_scene* scene, uint32_t* grid, uint32_t* block, uint32_t* smem_bytes,
                               uint32_t* kernels_launched);
 
@@ -169,9 +247,6 @@ int pt_bvh_export_quant(pt_scene* scene, void* qnodes32, float* lo3, float* step
 /* The host builder on its own (no device needed): tri_boxes8 = per PRIMITIVE (lo.xyz, -, hi.xyz, -), sorted_prim =
  * leaf slot -> primitive (pt_bvh_export), n_tris >= 2; writes (n_tris - 1) x 64 B. */
 int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth);
-/* Wide-node export; any pointer may be NULL.  wide_index[n_nodes]: exclusive count of wide-node roots among the
- * binary nodes before i (= the wide node's index where binary node i is a root); wnodes: n_wide x 128 B. */
-int pt_bvh_export_wide(const pt_scene* scene, uint32_t* n_wide, uint32_t* wide_index, void* wnodes128);
 /* Batch ray queries through the device traversal kernels (host arrays in/out). */
 int pt_trace_rays(const pt_scene* scene, const float* org3, const float* dir3, const float* tmin, const float* tmax,
                   uint64_t n, int32_t* prim_out, float* t_out, uint8_t* any_out, uint64_t* counters2);

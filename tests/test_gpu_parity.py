@@ -468,7 +468,7 @@ def test_full_size_c4_two_million_triangles(api, port):
         import torch
         acc_c, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
         assert gs.last_launch_info()["traversal"] == "binary-quant"               # auto: the records do not fit in L2
-        for trav, expect in ((3, "binary-coop"), (2, "wide"), (1, "binary")):
+        for trav, expect in ((2, "binary"), (1, "binary")):
             gs.set_traversal(trav)
             acc_t, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
             assert gs.last_launch_info()["traversal"] == expect
@@ -655,75 +655,22 @@ def test_random_soups_and_cameras(api, port, seed):
         gs.destroy()
 
 
-# ---- wide nodes (two LBVH levels per record): structure and pixels ------------------------------------------------
-def _wide_from_binary(nodes, parent):
-    """CPU statement of lbvh.cu wide_mark/wide_emit: binary nodes with an even number of ancestors become wide
-    nodes (numbered in binary-node order); children = grandchildren, or the child itself where it is a leaf."""
-    n = nodes.shape[0]
-    ni = nodes.view(np.int32)
-    depth = np.zeros(n, np.int64)
-    cur = parent.astype(np.int64).copy()
-    while (cur >= 0).any():
-        live = cur >= 0
-        depth[live] += 1
-        cur[live] = parent[cur[live]]
-    flag = (depth % 2 == 0).astype(np.uint32)
-    index = (np.cumsum(flag) - flag).astype(np.uint32)
-    out = np.zeros((int(flag.sum()), 32), np.uint32)
-    empty = np.zeros(8, np.uint32)
-    empty[3] = 0x80000000
-    for i in np.nonzero(flag)[0]:
-        slots = []
-        c = (int(ni[i, 3]), int(ni[i, 7]))
-        for s in range(2):
-            if s == 1 and c[1] == c[0]:
-                break
-            if c[s] < 0:
-                lo, hi = (nodes[i, 0:3], nodes[i, 4:7]) if s == 0 else (nodes[i, 8:11], nodes[i, 12:15])
-                slots.append((lo, hi, c[s]))
-            else:
-                r = c[s]
-                for lo, hi, g in ((nodes[r, 0:3], nodes[r, 4:7], int(ni[r, 3])), (nodes[r, 8:11], nodes[r, 12:15], int(ni[r, 7]))):
-                    slots.append((lo, hi, int(index[g]) if g >= 0 else g))
-        rec = out[index[i]]
-        for k in range(4):
-            if k < len(slots):
-                lo, hi, ch = slots[k]
-                rec[8 * k: 8 * k + 3] = lo
-                rec[8 * k + 3] = np.uint32(ch & 0xFFFFFFFF)
-                rec[8 * k + 4: 8 * k + 7] = hi
-            else:
-                rec[8 * k: 8 * k + 8] = empty
-    return index, out
-
-
-@pytest.mark.parametrize("name", ["cornell", "material", "tess40", "tess300"])
-def test_wide_nodes_bit_exact(api, port, scenes_cache, name):
-    arr, gs, osc = _get(scenes_cache, api, port, name)
-    b, w = gs.bvh_export(), gs.bvh_export_wide()
-    index, ref = _wide_from_binary(b["nodes"], b["parent"])
-    assert w["n_wide"] == ref.shape[0]
-    assert np.array_equal(w["wide_index"], index)
-    assert np.array_equal(w["wnodes"], ref)
-    # every leaf is referenced exactly once, every wide node but the root exactly once
-    ch = w["wnodes"].reshape(-1, 4, 8)[:, :, 3].view(np.int32).ravel()
-    ch = ch[ch != np.int32(-0x80000000)]
-    assert np.array_equal(np.sort(~ch[ch < 0]), np.arange(arr.n_tri))
-    assert np.array_equal(np.sort(ch[ch >= 0]), np.arange(1, w["n_wide"]))
+# ---- node fetch variants (pt_scene_set_traversal): same pixels ------------------------------------------------------------
+TRAVERSALS = ((2, "binary"), (3, "binary-quant"), (1, "binary"))   # exact nodes from global memory, quantised, auto placement
 
 
 @pytest.mark.parametrize("name,w,h,spp,md", [("cornell", 160, 90, 6, 16), ("material", 200, 112, 6, 28), ("tess40", 160, 90, 4, 8),
                                              ("tess300", 128, 72, 3, 8)])
-def test_wide_traversal_same_pixels(api, port, scenes_cache, name, w, h, spp, md):
-    """pt_scene_set_traversal: wide nodes and the warp-cooperative node fetch (both forced to global memory, also for
-    scenes that would be staged in shared memory), the per-lane binary LBVH and the oracle give the same primary hits
-    and the same pixels, bit for bit."""
+def test_traversal_variants_same_pixels(api, port, scenes_cache, name, w, h, spp, md):
+    """pt_scene_set_traversal: exact nodes read from global memory (also for scenes that would be staged in shared
+    memory), quantised 32-byte nodes, the default placement and the oracle give the same primary hits and the same
+    pixels, bit for bit."""
     arr, gs, osc = _get(scenes_cache, api, port, name)
     p = api.make_params(w, h, spp, md, frame=1, nee=True, importance=True, scene=gs)
     prev = np.random.default_rng(3).random((h, w, 4), dtype=np.float32)
     o = osc.render(p, accum=prev.copy(), math_mode=1, use_bvh=True, probes=True)
     try:
-        for trav, expect in ((2, "wide"), (3, "binary-coop"), (4, "binary-quant"), (1, "binary")):
+        for trav, expect in TRAVERSALS:
             gs.set_traversal(trav)
             g = gs.launch_host(p, accum=prev.copy())
             assert gs.last_launch_info()["traversal"] == expect
@@ -735,7 +682,7 @@ def test_wide_traversal_same_pixels(api, port, scenes_cache, name, w, h, spp, md
         gs.set_traversal(0)
 
 
-def test_wide_traversal_single_triangle_and_soups(api, port):
+def test_traversal_variants_single_triangle_and_soups(api, port):
     rng = np.random.default_rng(77)
     for n_tri in (1, 2, 3, 5, 70, 333):
         arr = _random_soup(rng, n_tri)
@@ -743,9 +690,9 @@ def test_wide_traversal_single_triangle_and_soups(api, port):
         try:
             p = api.make_params(64, 40, 4, 6, frame=0, nee=True, scene=gs)
             o = osc.render(p, math_mode=1, use_bvh=True)
-            for trav, expect in ((2, "wide"), (3, "binary-coop"), (4, "binary-quant")):
-                if n_tri < 2 and trav == 4:
-                    continue                                  # a single triangle has no quantised node array
+            for trav, expect in TRAVERSALS:
+                if n_tri < 2 and trav == 3:
+                    expect = "binary"                         # a single triangle has no quantised node array: exact nodes
                 gs.set_traversal(trav)
                 g = gs.launch_host(p)
                 assert gs.last_launch_info()["traversal"] == expect
@@ -756,7 +703,7 @@ def test_wide_traversal_single_triangle_and_soups(api, port):
                 a[:, [11, 15]] = 0
                 b[:, [11, 15]] = 0
                 assert gp["depth"] == op["depth"] and np.array_equal(a, b), n_tri
-                for trav in (0, 4):                          # exact and quantised nodes of each tree
+                for trav in (0, 3):                          # exact and quantised nodes of each tree
                     gs.set_traversal(trav)
                     for tree in (1, 2, 3):
                         gs.set_tree(tree)
@@ -764,12 +711,11 @@ def test_wide_traversal_single_triangle_and_soups(api, port):
                         assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), (n_tri, tree, trav)
                 gs.set_tree(0)
                 gs.set_traversal(0)
-            # counted launches with the cooperative fetch report the binary traversal's work counters
-            gs.set_traversal(3)
+            # counted launches from global memory report the specified traversal's work counters
+            gs.set_traversal(2)
             gs.enable_counters(True)
             gs.counters(reset=True)
             g = gs.launch_host(p)
-            assert gs.last_launch_info()["traversal"] == "binary-coop"
             assert gs.counters(reset=True) == o["counters"]
             gs.enable_counters(False)
         finally:
@@ -846,16 +792,16 @@ def test_ploc_tree_bit_exact(api, port, scenes_cache, name):
 
 @pytest.mark.parametrize("name,w,h,spp,md", [("material", 160, 90, 6, 28), ("tess40", 160, 90, 4, 8), ("tess300", 128, 72, 3, 8)])
 @pytest.mark.parametrize("levels", [2, 5, 0])
-def test_stack_spill_same_pixels(api, port, scenes_cache, monkeypatch, name, w, h, spp, md, levels):
+def test_stack_spill_same_pixels(api, port, scenes_cache, name, w, h, spp, md, levels):
     """Scenes read from global memory keep only the first levels of a path's traversal stack in shared memory (12 by
     default) and spill deeper ones to global memory; forced down to 2 and 5 levels (and with no spill at all) the pixels
     and the work counters are still the oracle's."""
     arr, gs, osc = _get(scenes_cache, api, port, name)
     p = api.make_params(w, h, spp, md, frame=1, nee=True, importance=True, scene=gs)
     o = osc.render(p, math_mode=1, use_bvh=True)
-    monkeypatch.setenv("PTB_TUNE", f"stack_smem={levels}")
+    gs.set_tune(f"stack_smem={levels}")
     try:
-        gs.set_traversal(3 if name == "material" else 0)          # material (672 triangles) would be staged in shared memory
+        gs.set_traversal(2)                                       # material (672 triangles) would be staged in shared memory
         g = gs.launch_host(p)
         assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32))
         gs.enable_counters(True)
@@ -866,6 +812,7 @@ def test_stack_spill_same_pixels(api, port, scenes_cache, monkeypatch, name, w, 
     finally:
         gs.enable_counters(False)
         gs.set_traversal(0)
+        gs.set_tune("")
 
 
 def _degenerate_scene(kind):
@@ -900,7 +847,7 @@ def test_degenerate_scenes_all_trees(api, port, kind):
             assert exp_g["depth"] == exp_o["depth"] and np.array_equal(a, b)
         p = api.make_params(96, 54, 3, 12, frame=0, nee=True, scene=gs)
         for tree in (0, 1, 2, 3):
-            for trav in (0, 3, 4):
+            for trav in (0, 2, 3):
                 used = osc.set_tree(tree)
                 try:
                     gs.set_tree(tree)
@@ -917,7 +864,7 @@ def test_degenerate_scenes_all_trees(api, port, kind):
 
 @pytest.mark.parametrize("name", ["cornell", "material", "tess40", "tess300"])
 def test_quantised_nodes_contain_the_exact_boxes(api, port, scenes_cache, name):
-    """32-byte nodes (pt_scene_set_traversal 4): every dequantised plane -- fma(q, step, lo), the traversal's expression,
+    """32-byte nodes (pt_scene_set_traversal 3): every dequantised plane -- fma(q, step, lo), the traversal's expression,
     evaluated here in float64 and rounded once like a float32 fma -- is on the outside of the exact plane, the child
     references are the exact node's, and a plane is never more than one grid step away."""
     arr, gs, osc = _get(scenes_cache, api, port, name)

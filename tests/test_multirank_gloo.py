@@ -1,7 +1,8 @@
-"""N > 1 host path on CPU: two processes, gloo backend, 127.0.0.1.  Each rank "renders" only the pixels it owns (the
-CPU oracle stands in for the GPU kernel, launch by launch, keeping its own running average), then the ranks run the
-product's exchange (acgpathtracing_b200.multirank.ImageExchange: pack -> all_gather -> unpack) ONCE after the last
-launch.  Both ranks must end with the image a single process renders, bit for bit."""
+"""N > 1 host logic on CPU: processes over the gloo backend on 127.0.0.1 run acgpathtracing_b200.multirank.MirrorGroup, the
+CPU restatement of pt_launch_multi (csrc/multigpu.cu) that takes its plan and its slices from the library's own host-only
+entry points (pt_multi_plan / pt_multi_slice).  A stand-in renderer supplies each launch's mean image; every rank must end
+with the image a single process folds, bit for bit.  The GPU tests (tests/test_gpu_parity.py::test_launch_multi_*) run the
+real thing through the C ABI."""
 import os
 import socket
 import sys
@@ -13,7 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-W, H, SPP, DEPTH, FRAMES = 41, 22, 2, 6, 3      # ragged: 41 and 22 are not multiples of the 8x4 tile
+W, H, SPP, DEPTH = 41, 22, 2, 6      # ragged: 41 and 22 are not multiples of the 8x4 tile
 
 
 def _free_port():
@@ -24,66 +25,14 @@ def _free_port():
     return p
 
 
-def _render_single():
-    import oracle_api as O
-    from acgpathtracing_b200 import scenes
-    port = O.load_port()
-    osc = O.OracleScene(port, scenes.cornell32())
-    acc = None
-    for f in range(FRAMES):
-        p = O.make_params(port, W, H, SPP, DEPTH, frame=f, nee=True, importance=True)
-        o = osc.render(p, accum=acc, math_mode=1, use_bvh=True)
-        acc = o["accum"]
-    return acc, o["fb"]
-
-
-def _worker(rank, world, port, out_dir):
+def _setup(rank, world, port):
     for p in (ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        from acgpathtracing_b200 import multirank as M
-        full_acc, full_fb = _render_single()          # what the GPU kernel would compute for every pixel ...
-        mine = M.owned_mask(W, H, rank, world)
-        acc = torch.zeros((H, W, 4), dtype=torch.float32)
-        fb = torch.zeros((H, W, 4), dtype=torch.uint8)
-        acc.numpy()[mine] = full_acc[mine]            # ... of which this rank has only its own tiles
-        fb.numpy()[mine] = full_fb[mine]
-        assert not np.array_equal(acc.numpy(), full_acc)
-        ex = M.ImageExchange(W, H, rank, world, "cpu")
-        ex.gather(acc, fb)
-        np.save(os.path.join(out_dir, f"acc{rank}.npy"), acc.numpy())
-        np.save(os.path.join(out_dir, f"fb{rank}.npy"), fb.numpy())
-        # max-over-ranks reduction used by bench.py for the timed region
-        t = torch.tensor([10.0 + rank], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        assert t.item() == 10.0 + world - 1
-    finally:
-        dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_two_rank_exchange_equals_single_rank(tmp_path, world):
-    port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
-    full_acc, full_fb = _render_single()
-    for r in range(world):
-        a = np.load(tmp_path / f"acc{r}.npy")
-        f = np.load(tmp_path / f"fb{r}.npy")
-        assert np.array_equal(a.view(np.uint32), full_acc.view(np.uint32))
-        assert np.array_equal(f, full_fb)
-
-
-def test_exchange_is_identity_for_one_rank():
-    from acgpathtracing_b200 import multirank as M
-    ex = M.ImageExchange(16, 8, 0, 1, "cpu")
-    a = torch.ones((8, 16, 4))
-    assert ex.gather(a, torch.zeros((8, 16, 4), dtype=torch.uint8)) == 0 and ex.bytes_per_rank() == 0
-
-
-# ---- frame-parallel plan: whole frames dealt round-robin + tile-partitioned leftovers, ordered fold --------------------
 def _fake_mean(frame):
     """Stand-in for a launch's mean image: any deterministic function of (pixel, frame)."""
     rng = np.random.default_rng(1000 + frame)
@@ -92,49 +41,134 @@ def _fake_mean(frame):
     return x
 
 
-def _fp_worker(rank, world, port, out_dir, n_frames):
-    for p in (ROOT, os.path.join(ROOT, "tests")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+# ---- the plan and the slices (no processes needed) --------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8, 16])
+def test_plan_covers_every_frame_and_class_once_and_is_balanced(world):
+    from acgpathtracing_b200 import api
+    for n in (1, 2, 3, 5, 8, 9, 16, 20, 37):
+        plan = api.multi_plan(n, world)
+        seen = np.zeros((n, world), np.int32)
+        share = np.zeros(world, np.int64)                          # work per rank in units of 1 / world of a frame
+        for frame, rank, c0, nc in plan:
+            assert 0 <= frame < n and 0 <= rank < world and nc >= 1 and c0 + nc <= world
+            seen[frame, c0:c0 + nc] += 1
+            share[rank] += nc
+        assert np.all(seen == 1)
+        assert np.all(share == n)                                   # n frames * world classes / world ranks, exactly
+        per_rank = [sum(1 for j in plan if j[1] == r) for r in range(world)]
+        assert max(per_rank) <= n // world + 2                      # whole frames + at most two leftover jobs
+        rounds = n // world
+        assert [j for j in plan[:rounds * world]] == [(i * world + r, r, 0, world) for i in range(rounds) for r in range(world)]
+
+
+def test_plan_examples():
+    from acgpathtracing_b200 import api
+    # 20 launches on 8 GPUs (the driver's scaling run): two whole frames each, then four frames in halves
+    plan = api.multi_plan(20, 8)
+    assert plan[16:] == [(16, 0, 0, 4), (16, 1, 4, 4), (17, 2, 0, 4), (17, 3, 4, 4), (18, 4, 0, 4), (18, 5, 4, 4), (19, 6, 0, 4), (19, 7, 4, 4)]
+    # one launch on 8 GPUs (the reference's per-displayed-frame usage): the classic 1/8 tile share
+    assert api.multi_plan(1, 8) == [(0, r, r, 1) for r in range(8)]
+
+
+@pytest.mark.parametrize("w,h", [(41, 22), (1920, 1080), (3840, 2160), (7, 3)])
+def test_slices_partition_the_image(w, h):
+    from acgpathtracing_b200 import api
+    for world in (1, 2, 3, 8, 16):
+        s = [api.multi_slice(w, h, r, world) for r in range(world)]
+        assert s[0][0] == 0 and s[-1][0] + s[-1][1] == w * h
+        for a, b in zip(s, s[1:]):
+            assert a[0] + a[1] == b[0]
+
+
+def test_bad_arguments():
+    from acgpathtracing_b200 import api
+    with pytest.raises(api.PtError):
+        api.multi_plan(4, 0)
+    with pytest.raises(api.PtError):
+        api.multi_plan(4, 17)
+    with pytest.raises(api.PtError):
+        api.multi_slice(16, 16, 2, 2)
+
+
+# ---- MirrorGroup over gloo -----------------------------------------------------------------------------------------------------
+def _mirror_worker(rank, world, port, out_dir, calls):
+    _setup(rank, world, port)
     try:
         from acgpathtracing_b200 import multirank as M
 
-        def render_raw(frame, r, n, out):
-            mask = M.owned_mask(W, H, r, n)
-            out.zero_()
-            out.numpy()[mask] = _fake_mean(frame)[mask]
+        def render_raw(frame, c0, nc, n, out):
+            mask = M.owned_mask(W, H, c0, n, nc)
+            out[mask] = _fake_mean(frame)[mask]                    # the rest keeps MirrorGroup's NaN poison
 
-        fp = M.FrameParallel(W, H, rank, world, "cpu", n_frames, render_raw)
-        mine = fp.my_frames()
-        assert len(mine) == n_frames // world + n_frames % world
-        for f, kind in mine:
-            fp.render(f, kind)
-        acc = torch.zeros((H, W, 4), dtype=torch.float32)
-        fp.finish(acc, None)
-        np.save(os.path.join(out_dir, f"fp{rank}.npy"), acc.numpy())
+        g = M.MirrorGroup(W, H, rank, world, render_raw)
+        acc = np.zeros((H, W, 4), np.float32)
+        first = 0
+        for k in calls:
+            mine = g.launch(acc, first, k)
+            assert sum(j[3] for j in mine) == k                    # this rank's share: k / world frames
+            first += k
+        assert not np.isnan(acc).any()
+        np.save(os.path.join(out_dir, f"acc{rank}.npy"), acc)
+        # max-over-ranks reduction used by bench.py for the timed region
+        t = torch.tensor([10.0 + rank], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == 10.0 + world - 1
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_frames", [(2, 4), (2, 5), (3, 2), (3, 7)])
-def test_frame_parallel_equals_sequential_fold(tmp_path, world, n_frames):
+@pytest.mark.parametrize("world,calls", [(2, (4,)), (2, (5,)), (3, (2,)), (3, (7,)), (3, (1,)), (2, (3, 1, 4)), (3, (4, 5))])
+def test_mirror_group_equals_sequential_fold(tmp_path, world, calls):
+    """Whole frames, leftover sub-shares (including shares that span two frames) and resumed calls (first frame > 0)."""
     from acgpathtracing_b200 import multirank as M
-    mp.spawn(_fp_worker, args=(world, _free_port(), str(tmp_path), n_frames), nprocs=world, join=True)
-    want = M.fold_numpy([_fake_mean(f) for f in range(n_frames)])
+    mp.spawn(_mirror_worker, args=(world, _free_port(), str(tmp_path), calls), nprocs=world, join=True)
+    want = M.fold_numpy([_fake_mean(f) for f in range(sum(calls))])
     for r in range(world):
-        got = np.load(tmp_path / f"fp{r}.npy")
+        got = np.load(tmp_path / f"acc{r}.npy")
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
-def test_frame_plan_covers_every_frame_once():
+def _oracle_frame0():
+    import oracle_api as O
+    from acgpathtracing_b200 import scenes
+    port = O.load_port()
+    osc = O.OracleScene(port, scenes.cornell32())
+    p = O.make_params(port, W, H, SPP, DEPTH, frame=0, nee=True, importance=True)
+    return osc.render(p, math_mode=1, use_bvh=True)["accum"]
+
+
+def _oracle_worker(rank, world, port, out_dir):
+    _setup(rank, world, port)
+    try:
+        from acgpathtracing_b200 import multirank as M
+        full = _oracle_frame0()                  # what the GPU kernel computes for every pixel of frame 0 ...
+
+        def render_raw(frame, c0, nc, n, out):
+            mask = M.owned_mask(W, H, c0, n, nc)
+            out[mask] = full[mask]               # ... of which a rank has only its tile classes
+
+        g = M.MirrorGroup(W, H, rank, world, render_raw)
+        acc = np.zeros((H, W, 4), np.float32)
+        g.launch(acc, 0, 1)                      # one launch on `world` ranks = the 1 / world tile share per rank
+        np.save(os.path.join(out_dir, f"o{rank}.npy"), acc)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_single_launch_tile_shares_equal_single_rank(tmp_path, world):
+    mp.spawn(_oracle_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    full = _oracle_frame0()
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"o{r}.npy").view(np.uint32), full.view(np.uint32))
+
+
+def test_mirror_group_single_rank_is_the_plain_fold():
     from acgpathtracing_b200 import multirank as M
-    for world in (1, 2, 3, 4, 8):
-        for n in (1, 2, 5, 8, 9, 16):
-            rounds, left = M.frame_plan(n, world)
-            whole = sorted(i * world + r for r in range(world) for i in range(rounds))
-            assert whole + left == list(range(n))
+    g = M.MirrorGroup(W, H, 0, 1, lambda frame, c0, nc, n, out: out.__setitem__(Ellipsis, _fake_mean(frame)))
+    acc = np.zeros((H, W, 4), np.float32)
+    g.launch(acc, 0, 3)
+    assert np.array_equal(acc.view(np.uint32), M.fold_numpy([_fake_mean(f) for f in range(3)]).view(np.uint32))
 
 
 def test_fold_numpy_first_frame_and_weights(port, cornell):
