@@ -74,7 +74,7 @@ static void scene_free(Scene* s)
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_scan_scratch, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
                     s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_qnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
-                    s->d_stack_over};
+                    s->d_stack_over, s->d_team_log};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (TileOrder& t : s->tile_orders) {

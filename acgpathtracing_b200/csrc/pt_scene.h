@@ -127,6 +127,8 @@ struct Scene {
 
     int* d_stack_over = nullptr;                // deeper stack levels of the wavefront kernel (scenes in global memory)
     size_t stack_over_capacity = 0;
+    void* d_team_log = nullptr;                 // term logs + marks of the wavefront kernel's sample teams
+    size_t team_log_bytes = 0;
 
     // last launch
     uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_trav = 0;   // last_trav: 0 exact 64-byte nodes, 1 quantised 32-byte nodes

@@ -30,6 +30,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 
 #include "pt_scene.h"
@@ -43,7 +44,7 @@ namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kWfBlock = 768;          // most threads per CTA (24 warps, 80 registers); one CTA per SM
-constexpr int kCtlF4 = 41;             // float4s in front of the state arrays: mask[5][32] + 4 control words
+constexpr int kCtlF4 = 129;            // float4s in front of the state arrays: mask[5][32] + 4 control words + idle[32] + team[10][32]
 constexpr int kStateF4 = 9;            // float4 state arrays per path
 constexpr size_t kMaxSmem = 227 * 1024;
 
@@ -51,7 +52,8 @@ enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3, ST_PIXEL = 4, S
 constexpr int kQueues = 5;
 constexpr uint32_t kCandNone = 0xffffffffu;       // per-pixel candidate list: no triangle can be hit by a camera ray
 constexpr uint32_t kCandOverflow = 0xfffffffeu;   // more than 4 candidates (or lists disabled): traverse the BVH
-enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3, MODE_NEWPIX = 4 };
+enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3, MODE_NEWPIX = 4, MODE_JOIN = 5 };
+constexpr int kTeamBit = 1 << 9;       // P1.x: this slot runs a sample of its column's team (depth | done << 8 | team << 9 | material << 16)
 
 struct WfConst {
     uint32_t np;             // paths per CTA
@@ -68,6 +70,13 @@ struct WfConst {
     int block_override;      // host only: threads per CTA when set by PTB_TUNE
     int idle_ns;             // sleep of a warp that found every queue empty ...
     int idle_shift;          // ... doubled for every further empty poll, at most this many times
+    // sample teams (see "Sample teams" below)
+    int team;                // 0 = off
+    int team_min;            // a pixel is handed to a team when it has at least this many samples left
+    uint32_t team_wmask;     // log window (samples in flight beyond the commit frontier) - 1; power of two - 1
+    uint32_t team_cap;       // log entries per sample = maxDepth + 2
+    float4* team_log;        // [grid][32 columns][window][team_cap]
+    uint32_t* team_meta;     // [grid][32 columns][window]: (sample + 1) << 9 | terms, written when the sample has ended
 };
 
 struct ThreadCounters {
@@ -196,6 +205,169 @@ __device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, cons
     return cand;
 }
 
+// ---- Sample teams -----------------------------------------------------------------------------------------------------
+// The reference runs a pixel's samples one after the other (pathTracerPrograms.cu:724-780) and so does a path slot here.
+// That chain is the latency floor of a launch: a slot needs ~25 us per sample, 3.5 ms for 128 of them, whatever else the
+// GPU is doing -- the tail of every launch, most of a launch that gives a GPU only a small share of the frame, and a
+// pixel on the rim of the glass sphere (28-bounce paths) holds its slot for a large part of a C3 launch.
+// The samples are independent, though: the pixel seed of sample k is the seed of sample 0 advanced by 2k draws
+// (only the two jitter draws move it) and the LCG can jump there in O(log k) integer steps (lcg_skip).  What is
+// ordered is only the float sum `result += emission; result += radiance * attenuation` (:760-761).  So, when a column
+// has slots with nothing to do (no pixels left to take), a pixel can be handed to the column's TEAM:
+//   * the team's state lives in ten shared-memory words of the column: how many samples it has, how many were handed
+//     out (one CAS), the pixel's seed / coordinates / candidate list, the running sum and how many samples are in it;
+//   * every slot of the column that has no pixel takes the next sample index k, runs that path exactly like any other,
+//     and instead of adding its (non-zero) terms to a result it appends them to the log of sample k in global memory
+//     (adding +-0 never changes this sum: it starts at +0 and can never become -0);
+//   * when its sample ends the slot publishes the term count (release), and whoever gets the team's lock adds the logged
+//     terms of all finished samples at the commit frontier, IN SAMPLE ORDER, to the running sum -- the same additions in
+//     the same order as the sequential loop, hence the same bits.  Nobody waits: the slot takes the next sample at once;
+//     a long sample only delays the frontier, bounded by the log window (then slots park until it moves);
+//   * the slot that commits the last sample carries the pixel to the PIXEL stage, which writes it as usual.
+// One team per column at a time; lanes only touch their own column's words, like the queues.
+enum : int { T_TAKE = 0, T_COMMIT, T_LOCK, T_CLAIM, T_SEED, T_PIX, T_CAND, T_RX, T_RY, T_RZ, kTeamWords };
+static_assert(kCtlF4 * 4 >= kQueues * 32 + 4 + 32 + kTeamWords * 32, "control block too small");
+
+struct Team {              // this lane's column
+    uint32_t* w;           // team word i at w[i * 32]:  T_TAKE = samples << 16 | handed out
+    uint32_t* idle;        // bit j: slot 32 j + lane is parked (its TS already says MODE_JOIN)
+    uint32_t* meta;        // [window]
+    float4* log;           // [window][cap]
+    uint32_t wmask, cap;
+};
+
+// n draws ahead: s -> A_n s + C_n, by repeated squaring of the affine map s -> 1664525 s + 1013904223 (cuda/random.h:49-56)
+__device__ __forceinline__ uint32_t lcg_skip(uint32_t s, uint32_t n)
+{
+    uint32_t A = 1u, C = 0u, a = 1664525u, c = 1013904223u;
+    while (n) {
+        if (n & 1u) {
+            A = a * A;
+            C = a * C + c;
+        }
+        c = (a + 1u) * c;
+        a = a * a;
+        n >>= 1;
+    }
+    return A * s + C;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) { asm volatile("st.release.cta.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// next sample of the column's team, or -1: no team, every sample handed out, or the log window is full
+__device__ __forceinline__ int team_take(const Team& t)
+{
+    for (;;) {
+        const uint32_t w = vol_ld(t.w + T_TAKE * 32), n = w >> 16, i = w & 0xffffu;
+        if (i >= n || i > vol_ld(t.w + T_COMMIT * 32) + t.wmask) return -1;
+        if (atomicCAS(t.w + T_TAKE * 32, w, w + 1u) == w) return (int)i;
+    }
+}
+
+// parked slots of this column back to work (END stage, MODE_JOIN)
+__device__ __forceinline__ void team_wake(const Team& t, uint32_t* mask, uint32_t* ctl, int lane)
+{
+    if (vol_ld(t.idle) == 0u) return;
+    const uint32_t m = atomicExch(t.idle, 0u);
+    if (m) {
+        atomicAdd(ctl, (uint32_t)__popc(m));          // before they become visible: the exit test must never see 0 too early
+        __threadfence_block();
+        atomicOr(mask + ST_END * 32 + lane, m);
+    }
+}
+
+// Park slot j (its TS must already say MODE_JOIN).  False: samples turned up meanwhile and the slot was not woken by
+// anyone else -- the caller still owns it and tries again.
+__device__ __forceinline__ bool team_park(const Team& t, uint32_t* ctl, int j)
+{
+    __threadfence_block();
+    atomicOr(t.idle, 1u << j);
+    atomicSub(ctl, 1u);
+    const uint32_t w = vol_ld(t.w + T_TAKE * 32), n = w >> 16, i = w & 0xffffu;
+    if (i < n && i <= vol_ld(t.w + T_COMMIT * 32) + t.wmask) {
+        if (atomicAnd(t.idle, ~(1u << j)) & (1u << j)) {
+            atomicAdd(ctl, 1u);
+            return false;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ void team_log_term(const Team& t, uint32_t k, uint32_t& n_terms, float3 v)
+{
+    if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
+        t.log[(size_t)(k & t.wmask) * t.cap + n_terms] = make_float4(v.x, v.y, v.z, 0.0f);
+        ++n_terms;
+    }
+}
+
+// Sample k of the column's team has ended with n_terms logged terms.  Publishes it and commits whatever is finished at
+// the frontier.  True: this call committed the pixel's last sample -- `result` is the pixel's sum, the team is dissolved.
+__device__ __noinline__ bool team_finish(const Team t, uint32_t k, uint32_t n_terms, float3& result, uint32_t* mask, uint32_t* ctl, int lane)
+{
+    st_release(t.meta + (k & t.wmask), ((k + 1u) << 9) | n_terms);
+    for (;;) {
+        if (atomicCAS(t.w + T_LOCK * 32, 0u, 1u) != 0u) return false;      // the holder re-checks the frontier after unlocking
+        __threadfence_block();
+        const uint32_t cm0 = vol_ld(t.w + T_COMMIT * 32), n = vol_ld(t.w + T_TAKE * 32) >> 16;
+        uint32_t cm = cm0;
+        float3 r = f3(__uint_as_float(vol_ld(t.w + T_RX * 32)), __uint_as_float(vol_ld(t.w + T_RY * 32)), __uint_as_float(vol_ld(t.w + T_RZ * 32)));
+        while (cm < n) {
+            const uint32_t m = ld_acquire(t.meta + (cm & t.wmask));
+            if ((m >> 9) != cm + 1u) break;
+            const float4* src = t.log + (size_t)(cm & t.wmask) * t.cap;
+            for (uint32_t i = 0; i < (m & 511u); ++i) {
+                const float4 v = src[i];
+                r = r + f3(v.x, v.y, v.z);                                 // :760-761, in sample order, term by term
+            }
+            ++cm;
+        }
+        if (cm == n) {
+            result = r;
+            *reinterpret_cast<volatile uint32_t*>(t.w + T_TAKE * 32) = 0u;   // no team: nothing can be taken (all n were)
+            __threadfence_block();
+            atomicExch(t.w + T_LOCK * 32, 0u);
+            atomicExch(t.w + T_CLAIM * 32, 0u);
+            return true;
+        }
+        *reinterpret_cast<volatile uint32_t*>(t.w + T_RX * 32) = __float_as_uint(r.x);
+        *reinterpret_cast<volatile uint32_t*>(t.w + T_RY * 32) = __float_as_uint(r.y);
+        *reinterpret_cast<volatile uint32_t*>(t.w + T_RZ * 32) = __float_as_uint(r.z);
+        *reinterpret_cast<volatile uint32_t*>(t.w + T_COMMIT * 32) = cm;
+        __threadfence_block();
+        atomicExch(t.w + T_LOCK * 32, 0u);
+        if (cm != cm0) team_wake(t, mask, ctl, lane);                      // the window moved
+        if ((ld_acquire(t.meta + (cm & t.wmask)) >> 9) != cm + 1u) return false;
+    }
+}
+
+// A slot that works alone on a pixel (`left` samples to go, pixel seed before the next sample's jitter draws) hands it to
+// the column's team.  False: the team is taken.
+__device__ __noinline__ bool team_create(const Team t, uint32_t left, uint32_t pixel_seed, uint32_t pix, uint32_t cand, float3 result,
+                                         uint32_t* mask, uint32_t* ctl, int lane)
+{
+    if (atomicCAS(t.w + T_CLAIM * 32, 0u, 1u) != 0u) return false;
+    for (uint32_t i = 0; i <= t.wmask; i += 4) *reinterpret_cast<uint4*>(t.meta + i) = make_uint4(0u, 0u, 0u, 0u);   // marks of an earlier team
+    volatile uint32_t* w = t.w;
+    w[T_COMMIT * 32] = 0u;
+    w[T_SEED * 32] = pixel_seed;
+    w[T_PIX * 32] = pix;
+    w[T_CAND * 32] = cand;
+    w[T_RX * 32] = __float_as_uint(result.x);
+    w[T_RY * 32] = __float_as_uint(result.y);
+    w[T_RZ * 32] = __float_as_uint(result.z);
+    __threadfence();                                      // the cleared marks (global) and the words above before the team opens
+    w[T_TAKE * 32] = left << 16;
+    team_wake(t, mask, ctl, lane);
+    return true;
+}
+
 // TRAV (scenes in global memory only; TRAV_DIRECT elsewhere): how NODE batches read the tree.
 //   TRAV_DIRECT  every lane reads its own 64-byte node (two LDG.E.256)
 //   TRAV_QUANT   quantised nodes: twelve 16-bit planes + two child references in 32 bytes, ONE LDG.E.256 per lane and node
@@ -211,8 +383,17 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t NP = wc.np;
-    uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);            // [4][32]
-    uint32_t* ctl = mask + kQueues * 32;                            // [0] idle paths  [1] error flag
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);            // [5][32]
+    uint32_t* ctl = mask + kQueues * 32;                            // [0] slots that are not parked  [1] error flag
+    constexpr bool TEAM = !PROBE;                                   // the probes record per-pixel sequential state
+    Team tm;
+    tm.idle = ctl + 4 + lane;
+    tm.w = ctl + 4 + 32 + lane;
+    tm.wmask = wc.team_wmask;
+    tm.cap = wc.team_cap;
+    tm.meta = wc.team_meta + ((size_t)blockIdx.x * 32 + lane) * (wc.team_wmask + 1u);
+    tm.log = wc.team_log + ((size_t)blockIdx.x * 32 + lane) * (wc.team_wmask + 1u) * wc.team_cap;
+    const bool use_teams = TEAM && wc.team != 0;
     float4* R0 = smem4 + kCtlF4;        // (ray origin, -)
     float4* R1 = R0 + NP;               // (ray direction, -)
     float4* R2 = R1 + NP;               // (1 / direction, -)
@@ -255,13 +436,14 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     }
 
     // every path starts "fresh": waiting in PIXEL for its first pixel
-    for (uint32_t i = threadIdx.x; i < kQueues * 32 + 4; i += blockDim.x) mask[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < kCtlF4 * 4; i += blockDim.x) mask[i] = 0u;
     for (uint32_t pid = threadIdx.x; pid < NP; pid += blockDim.x)
         TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_FRESH << 8));
     __syncthreads();
     if (warp == 0) {
         const uint32_t P = NP >> 5;
         mask[ST_PIXEL * 32 + lane] = P >= 32u ? 0xffffffffu : ((1u << P) - 1u);
+        if (lane == 0) ctl[0] = NP;
     }
     __syncthreads();
 
@@ -295,7 +477,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             const uint32_t b2 = __ballot_sync(kFull, m2 != 0u), b3 = __ballot_sync(kFull, m3 != 0u);
             const uint32_t b4 = __ballot_sync(kFull, m4 != 0u);
             if ((b0 | b1 | b2 | b3 | b4) == 0u) {
-                if (vol_ld(ctl) >= NP) break;                // every path has run out of pixels
+                if (vol_ld(ctl) == 0u) break;                // every slot is parked: no pixel left to take, no team to serve
                 if (++idle_polls > (1u << 26)) {             // watchdog: never spin forever
                     ctl[1] = 1u;
                     break;
@@ -479,6 +661,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 p.att = xyz(p0);
                 p.seed = __float_as_uint(p0.w);
                 p.depth = __float_as_int(p1.x) & 0xff;
+                const int team_bit = TEAM ? (__float_as_int(p1.x) & kTeamBit) : 0;
                 const float t_hit = ts.x;
                 const uint32_t prim = __float_as_uint(ts.y);
                 if (PROBE && __float_as_uint(p1.y) == lc.spp && p.depth == 0) {
@@ -492,7 +675,14 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 float3 emission, rad;
                 bool done;
                 shade_hit(lc, f, l_area, prim, t_hit, p, emission, rad, done, sq, hit_type, mat_id);
-                const float3 result = xyz(rs) + emission;                                       // :760
+                float3 result = xyz(rs);
+                if (TEAM && team_bit) {                                                         // :760, into the sample's log
+                    uint32_t n_terms = CAND[pid];
+                    team_log_term(tm, __float_as_uint(p1.y), n_terms, emission);
+                    CAND[pid] = n_terms;
+                } else {
+                    result = result + emission;                                                 // :760
+                }
                 if (COUNT) {
                     ctr.n_hit0 += hit_type == 0;
                     ctr.n_hit1 += hit_type == 1;
@@ -500,7 +690,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 }
                 // rad is the material's emission when it is emissive (done), else 0: END re-reads it from the table
                 P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                P1[pid] = make_float4(__int_as_float(p.depth | ((done ? 1 : 0) << 8) | (mat_id << 16)), p1.y, p1.z, p1.w);
+                P1[pid] = make_float4(__int_as_float(p.depth | ((done ? 1 : 0) << 8) | team_bit | (mat_id << 16)), p1.y, p1.z, p1.w);
                 const float3 add = sq.want ? sq.add : f3(0.0f);
                 S0[pid] = pack(p.o, add.x);
                 S1[pid] = pack(p.d, add.y);
@@ -545,7 +735,10 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_NEWPIX << 8));
                     wf_push(mask, ST_END, lane, j);
                 } else {
-                    atomicAdd(ctl, 1u);                       // this path is done for the launch
+                    // no pixel left: serve the column's team, or park (END, MODE_JOIN)
+                    P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
+                    TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
+                    wf_push(mask, ST_END, lane, j);
                 }
             }
         } else {
@@ -558,9 +751,10 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             p.att = f3(1.0f);
             p.seed = 0u;
             p.depth = 0;
+            // left: samples this slot still owes its pixel -- or, for a slot that serves its column's team, the sample index
             uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
             float3 result = f3(0.0f);
-            bool alive = j >= 0, need_sample = false;
+            bool alive = j >= 0, need_sample = false, team = false;
             if (j >= 0) {
                 const float4 ts = TS[pid];
                 const int mode = __float_as_int(ts.w) >> 8;
@@ -570,8 +764,16 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 const uint32_t pix = __float_as_uint(p1.w);
                 ix = pix & 0xffffu;
                 iy = pix >> 16;
+                team = TEAM && (__float_as_int(p1.x) & kTeamBit) != 0;
                 if (mode == MODE_NEWPIX) {
                     need_sample = true;                      // first sample of a new pixel; result starts at 0
+                } else if (mode == MODE_JOIN) {
+                    if (use_teams) {
+                        team = need_sample = true;           // a slot without a pixel: take a sample of the column's team below
+                    } else {
+                        atomicSub(ctl, 1u);                  // parked for the rest of the launch
+                        alive = false;
+                    }
                 } else {
                     const float4 p0 = P0[pid], rs = RS[pid];
                     p.att = xyz(p0);
@@ -600,11 +802,29 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                         if (mode == MODE_SHADOW && __float_as_uint(ts.y) == kNoPrim)
                             rad = rad + f3(s0.w, s1.w, rs.w);                                  // unoccluded, :1019-1024
                     }
-                    result = result + rad * p.att;                                             // :761
+                    uint32_t n_terms = 0u;
+                    if (TEAM && team) {                                                        // :761, into the sample's log
+                        n_terms = CAND[pid];
+                        team_log_term(tm, left, n_terms, rad * p.att);
+                    } else {
+                        result = result + rad * p.att;                                         // :761
+                    }
                     const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                      // :763
                     const bool rr = rnd(p.seed) > pr;                                          // :765
                     if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                     // :767
-                        if (--left == 0u) {                  // pixel finished: the PIXEL stage writes it
+                        if (TEAM && team) {
+                            // the team's sample `left` has ended: publish it; whoever holds the lock commits in sample order
+                            if (team_finish(tm, left, n_terms, result, mask, ctl, lane)) {
+                                // ... and this slot committed the pixel's last sample: it carries the pixel to the PIXEL stage
+                                P0[pid] = pack(p.att, __uint_as_float(p.seed));
+                                P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), p1.w);
+                                RS[pid] = pack(result, 0.0f);
+                                wf_push(mask, ST_PIXEL, lane, j);
+                                alive = false;
+                            } else {
+                                need_sample = true;
+                            }
+                        } else if (--left == 0u) {           // pixel finished: the PIXEL stage writes it
                             P0[pid] = pack(p.att, __uint_as_float(p.seed));
                             P1[pid] = make_float4(p1.x, __uint_as_float(0u), p1.z, p1.w);
                             RS[pid] = pack(result, 0.0f);
@@ -612,10 +832,37 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                             alive = false;
                         } else {
                             need_sample = true;
+                            // slots of this column are parked and the pixel has samples to spare: hand it to the column's team
+                            // (and go on as one of its members)
+                            if (use_teams && left >= (uint32_t)wc.team_min && left <= 0xffffu && vol_ld(tm.idle) != 0u &&
+                                (!SHORT || CAND[pid] != kCandNone))
+                                team = team_create(tm, left, pixel_seed, pix, SHORT ? CAND[pid] : kCandOverflow, result, mask, ctl, lane);
                         }
                     } else {
+                        if (TEAM && team) CAND[pid] = n_terms;
                         p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
                         ++p.depth;
+                    }
+                }
+                if (TEAM && need_sample && team) {
+                    // next sample of the column's team: its pixel seed is the team's base seed 2k draws on
+                    int k;
+                    for (;;) {
+                        k = team_take(tm);
+                        if (k >= 0) break;
+                        TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
+                        P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
+                        if (team_park(tm, ctl, j)) break;
+                    }
+                    if (k < 0) {
+                        alive = need_sample = false;         // parked: a waker pushes the slot back to END
+                    } else {
+                        left = (uint32_t)k;
+                        const uint32_t tpix = vol_ld(tm.w + T_PIX * 32);
+                        ix = tpix & 0xffffu;
+                        iy = tpix >> 16;
+                        pixel_seed = lcg_skip(vol_ld(tm.w + T_SEED * 32), 2u * (uint32_t)k);
+                        result = f3(0.0f);
                     }
                 }
                 if (need_sample) {
@@ -638,10 +885,12 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             if (alive) {
                 if (COUNT) ctr.n_radiance++;
                 P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
+                P1[pid] = make_float4(__int_as_float(p.depth | ((TEAM && team) ? kTeamBit : 0)), __uint_as_float(left), __uint_as_float(pixel_seed),
                                       __uint_as_float(ix | (iy << 16)));
                 RS[pid] = pack(result, 0.0f);
-                const uint32_t cand = (SHORT && need_sample) ? CAND[pid] : kCandOverflow;
+                uint32_t cand = kCandOverflow;
+                if (SHORT && need_sample) cand = (TEAM && team) ? vol_ld(tm.w + T_CAND * 32) : CAND[pid];
+                if (TEAM && team && need_sample) CAND[pid] = 0u;                               // terms logged for this sample so far
                 if (SHORT && cand == kCandNone) {
                     // No triangle can be reached from this pixel: every camera ray is a miss.  Finish up to
                     // wc.miss_loop samples right here, each exactly as the miss branch above does (:833-847, :760-772):
@@ -739,8 +988,11 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint64_t n_work = (uint64_t)lc.n_owned_tiles * 32u;
     uint32_t grid = (uint32_t)sms;                                       // persistent: one CTA per SM
-    const uint32_t grid_needed = (uint32_t)((n_work + wc.np - 1) / wc.np);
-    if (grid > grid_needed) grid = grid_needed;
+    // fewer CTAs when the launch is small: one pixel per path slot -- or, with sample teams, down to 64 pixels per CTA as
+    // long as every slot still gets about four samples (slots without a pixel serve their column's team)
+    uint64_t grid_needed = (n_work + wc.np - 1) / wc.np;
+    if (wc.team) grid_needed = std::max<uint64_t>(grid_needed, std::min<uint64_t>(n_work / 64u, n_work * lc.spp / (4ull * wc.np)));
+    if (grid > grid_needed) grid = (uint32_t)grid_needed;
     if (grid == 0) grid = 1;
     e = cudaMemsetAsync(s.d_work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
@@ -927,6 +1179,30 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
             s.stack_over_capacity = need;
         }
         wc.stack_over = s.d_stack_over;
+    }
+    // sample teams: the term log, sized for every SM
+    wc.team = 0;
+    wc.team_min = tune.team_min < 1 ? 1 : tune.team_min;
+    wc.team_cap = lc.max_depth + 2u;                     // emission + one term per segment (maxDepth + 1 segments)
+    wc.team_wmask = (wc.team_cap <= 32u ? 128u : (wc.team_cap <= 64u ? 64u : (wc.team_cap <= 128u ? 32u : 16u))) - 1u;
+    if (tune.team != 0 && !probe) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const size_t per_column = (size_t)(wc.team_wmask + 1u) * (wc.team_cap * sizeof(float4) + sizeof(uint32_t));
+        const size_t need = (size_t)sms * 32u * per_column;
+        if (s.team_log_bytes < need) {
+            if (s.d_team_log) cudaFree(s.d_team_log);
+            s.d_team_log = nullptr;
+            s.team_log_bytes = 0;
+            if (cudaMalloc((void**)&s.d_team_log, need) == cudaSuccess) s.team_log_bytes = need;
+            else cudaGetLastError();                     // no memory for the log: this launch runs without teams
+        }
+        if (s.team_log_bytes >= need) {
+            wc.team = 1;
+            wc.team_log = reinterpret_cast<float4*>(s.d_team_log);
+            wc.team_meta = reinterpret_cast<uint32_t*>(wc.team_log + (size_t)sms * 32u * (wc.team_wmask + 1u) * wc.team_cap);
+        }
     }
     const bool count = s.count_enabled;
     const int scene = smem_scene ? (int)wc.copies_shift : -1;

@@ -209,14 +209,17 @@ def run_b200(args):
         spp = args.spp
     arr = make_scene_arrays(scene_name)
     group = None
-    t_create = time.perf_counter()
+    torch.zeros(1, device=dev)                           # CUDA context up before anything is timed
+    torch.cuda.synchronize()
+    group_init_ms = None
     if world > 1:
         from acgpathtracing_b200.multirank import rank_group
+        t0 = time.perf_counter()
         group = rank_group(rank, world)                  # NCCL communicator inside libptb200.so
-        scene = group.create_scene(arr)
-    else:
-        scene = api.Scene(arr)
-    scene_create_ms = 1e3 * (time.perf_counter() - t_create)
+        group_init_ms = 1e3 * (time.perf_counter() - t0)
+    t_create = time.perf_counter()
+    scene = group.create_scene(arr) if world > 1 else api.Scene(arr)
+    scene_create_ms = 1e3 * (time.perf_counter() - t_create)          # host wall-clock of pt_scene_create: upload + trees
     if args.pipeline:
         scene.set_pipeline(args.pipeline)
     if args.tree:
@@ -244,16 +247,23 @@ def run_b200(args):
             api.launch(p, stream)
         return 1
 
+    phases = {}
+
     def image():
-        """N > 1: the K launches of the image through pt_launch_multi; returns the kernels this rank launched."""
-        if per_launch_calls:
-            n = 0
-            for i in range(args.steps):
-                group.launch(params(i), 1, stream)
-                n += group.last_kernels()
-            return n
-        group.launch(params(0), args.steps, stream)
-        return group.last_kernels()
+        """N > 1: the K launches of the image through pt_launch_multi; returns the kernels this rank launched and leaves the
+        device time of the phases (summed over the calls) in `phases`."""
+        phases.clear()
+        if not per_launch_calls:
+            group.launch(params(0), args.steps, stream)          # asynchronous; collect_phases() reads the timing afterwards
+            return
+        for i in range(args.steps):                              # a display loop: one launch per call, synchronised per frame
+            group.launch(params(i), 1, stream)                   # like the reference's CUDA_SYNC_CHECK (PathTracerMain.cpp:209)
+            collect_phases()
+
+    def collect_phases():
+        for key, v in group.last_timing(0).items():              # synchronises this rank's stream
+            phases[key] = phases.get(key, 0) + v
+        phases["calls"] = phases.get("calls", 0) + 1
 
     def barrier():
         if world > 1:
@@ -289,8 +299,12 @@ def run_b200(args):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))]
         flush_buf.fill_(1)
         ev[0][0].record()
-        launches += image()
+        image()
         ev[0][1].record()
+        torch.cuda.synchronize()
+        if not per_launch_calls:
+            collect_phases()
+        launches += phases["kernels"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -301,7 +315,7 @@ def run_b200(args):
         dist.all_reduce(n_launch)
     total_ms = float(total_ms.item())
     launches = int(n_launch.item())
-    phases = group.last_timing(0) if world > 1 else None
+    phases_timed = dict(phases) if world > 1 else None
     clocks = sampler.stop() if sampler else None
     checksum = float(acc[..., :3].double().mean().item())
     acc_after_timed = acc.clone()           # for the bit-for-bit comparison with the host-buffer path below
@@ -416,7 +430,7 @@ def run_b200(args):
         if world == 1:
             render_ms, n_kernels, share = sum(step_ms), args.steps, 1.0
         else:
-            render_ms, n_kernels, share = phases["render_ms"], max(phases["kernels"] - 1, 1), 1.0 / world
+            render_ms, n_kernels, share = phases_timed["render_ms"], max(phases_timed["kernels"] - phases_timed["calls"], 1), 1.0 / world
         kernel_ms = render_ms / n_kernels
         facts = PROFILE_FACTS.get(args.workload) if (args.pipeline != 1 and not args.spp and not args.tree and world == 1) else None
         sm_count = dinfo["sm_count"]
@@ -484,8 +498,8 @@ def run_b200(args):
                            ("K calls of pt_launch_multi with one launch each (every launch split N ways)" if per_launch_calls else
                             "one pt_launch_multi call: whole frames per rank + class-range sub-shares of the leftover frames") +
                            f"; slices over NCCL send/recv, ordered fold per slice, gather; rank 0 device time: render "
-                           f"{phases['render_ms']:.3f} ms, exchange + fold {phases['exchange_fold_ms']:.3f} ms, gather {phases['gather_ms']:.3f} ms"),
-                       "scene_create_ms": scene_create_ms,
+                           f"{phases_timed['render_ms']:.3f} ms, exchange + fold {phases_timed['exchange_fold_ms']:.3f} ms, gather {phases_timed['gather_ms']:.3f} ms"),
+                       "scene_create_ms": scene_create_ms, "group_init_ms": group_init_ms,
                        "lbvh_build_ms": info["build_ms"]},
             "grays_per_s": rays / (total_ms * 1e-3) / 1e9,
             "rays_per_sample": rays / max(counters["n_samples"], 1),

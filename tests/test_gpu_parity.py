@@ -890,3 +890,172 @@ def test_quantised_nodes_contain_the_exact_boxes(api, port, scenes_cache, name):
             assert np.all(np.abs(deq.astype(np.float64) - ex) <= 1.001 * step[axis] + 1e-4), tree
     finally:
         gs.set_tree(0)
+
+
+# ---- sample teams (wavefront.cu "Sample teams"): several slots work on one pixel, ordered commit ------------------------------
+TEAM_CASES = [
+    # scene, w, h, spp, maxDepth, tune -- few pixels and many samples: almost every sample is rendered by a team
+    ("cornell", 40, 24, 64, 16, ""),
+    ("cornell", 9, 5, 200, 16, ""),                    # fewer pixels than columns
+    ("material", 48, 27, 48, 28, ""),                  # long refractive / conductor paths: the commit frontier lags
+    ("material", 48, 27, 48, 28, "team_min=40"),       # pixels switch late or not at all
+    ("tess40", 32, 18, 32, 8, ""),                     # scene in global memory
+    ("cornell", 24, 16, 96, 200, ""),                  # deep logs: 202 entries per sample, a window of 16 samples (parking)
+    ("cornell", 40, 24, 64, 16, "paths32=4,block=128"),
+    ("cornell", 40, 24, 64, 16, "team=0"),             # the sequential chain, for reference
+]
+
+
+@pytest.mark.parametrize("case", TEAM_CASES, ids=lambda c: "-".join(str(x) for x in c))
+def test_sample_teams_bit_exact(api, port, scenes_cache, case):
+    name, w, h, spp, md, tune = case
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    gs.set_tune(tune)
+    try:
+        prev = None
+        fresh = lambda: None if prev is None else prev.copy()       # both sides fold in place: give each its own copy
+        for f in range(2):
+            p = api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs)
+            o = osc.render(p, accum=fresh(), math_mode=1, use_bvh=True)
+            g = gs.launch_host(p, accum=fresh())
+            assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), f"frame {f}"
+            assert np.array_equal(g["fb"], o["fb"]), f"frame {f}"
+            gs.enable_counters(True)                 # the counted kernel forms its own teams: same work, same pixels
+            gs.counters(reset=True)
+            g = gs.launch_host(p, accum=fresh())
+            assert gs.counters(reset=True) == o["counters"]
+            gs.enable_counters(False)
+            assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), f"frame {f} (counted)"
+            prev = o["accum"]
+        gs.check_error()
+    finally:
+        gs.enable_counters(False)
+        gs.set_tune("")
+
+
+def test_small_share_of_a_frame_uses_every_sm(api, port, scenes_cache):
+    """One 1/8 tile share of a 16:9 frame at 128 spp: with teams the launch spreads over the whole GPU (64 pixels per CTA are
+    enough) instead of one CTA per 1024 pixels, and the pixels are the oracle's."""
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    w, h = 256, 144
+    acc, fb = _dev_buffers(w, h)
+    p = api.make_params(w, h, 128, 16, frame=0, nee=True, importance=True, scene=gs)
+    _launch_dev(api, gs, p, acc, fb, rank=3, n=8)
+    grid_team = gs.last_launch_info()["grid"]
+    got = acc.cpu().numpy().copy()
+    gs.set_tune("team=0")
+    try:
+        acc.zero_()
+        _launch_dev(api, gs, p, acc, fb, rank=3, n=8)
+        grid_solo = gs.last_launch_info()["grid"]
+        assert np.array_equal(acc.cpu().numpy().view(np.uint32), got.view(np.uint32))
+    finally:
+        gs.set_tune("")
+    assert grid_solo == 5 and grid_team == 72, (grid_solo, grid_team)     # 4608 owned pixels: / 1024 slots vs / 64 pixels
+    from acgpathtracing_b200.multirank import owned_mask
+    mine = owned_mask(w, h, 3, 8)
+    o = osc.render(p, math_mode=1, use_bvh=True)
+    assert np.array_equal(got[mine].view(np.uint32), o["accum"][mine].view(np.uint32))
+
+
+# ---- the lock-free scheduler under perturbation (stands in for compute-sanitizer racecheck, which this GPU pool does not
+# allow): the image and the work counters must not depend on how paths are batched -------------------------------------------
+def test_schedule_perturbation(api, port, scenes_cache):
+    arr, gs, osc = _get(scenes_cache, api, port, "material")
+    w, h, spp, md = 160, 90, 24, 28
+    p = api.make_params(w, h, spp, md, frame=1, nee=True, importance=True, scene=gs)
+    prev = np.random.default_rng(5).random((h, w, 4), dtype=np.float32)
+    o = osc.render(p, accum=prev.copy(), math_mode=1, use_bvh=True)
+    rng = np.random.default_rng(2024)
+    tried = []
+    try:
+        for trial in range(20):
+            block = int(rng.choice([0, 128, 256, 384, 512, 768]))
+            paths32 = int(rng.choice([0, 4, 8, 16, 24]))
+            if paths32 and block > 32 * paths32:
+                block = 32 * paths32
+            spec = dict(block=block, paths32=paths32, node_votes=int(rng.integers(1, 9)), node_keep8=int(rng.integers(0, 9)),
+                        full_cols=int(rng.integers(1, 33)), sticky=int(rng.integers(0, 9)), tail_cols=int(rng.choice([0, 8, 24, 64, 160])),
+                        idle_ns=int(rng.choice([0, 16, 64, 512])), idle_shift=int(rng.integers(0, 6)), stack_smem=int(rng.choice([0, 2, 5, 12])),
+                        team=int(rng.choice([0, 1, 1])), team_min=int(rng.choice([1, 2, 8, 20])))
+            tune = ",".join(f"{k}={v}" for k, v in spec.items())
+            tried.append(tune)
+            gs.set_tune(tune)
+            gs.set_traversal(int(rng.choice([1, 2, 3])))          # staged, global exact, global quantised
+            gs.set_pipeline(2)
+            g = gs.launch_host(p, accum=prev.copy())
+            assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), tune
+            assert np.array_equal(g["fb"], o["fb"]), tune
+            gs.enable_counters(True)
+            gs.counters(reset=True)
+            g = gs.launch_host(p, accum=prev.copy())
+            assert gs.counters(reset=True) == o["counters"], tune
+            gs.enable_counters(False)
+            assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), tune
+        gs.check_error()
+    finally:
+        gs.enable_counters(False)
+        gs.set_tune("")
+        gs.set_traversal(0)
+        gs.set_pipeline(0)
+    assert len(set(tried)) >= 16
+
+
+def test_soak_200_launches_no_watchdog(api, port, scenes_cache):
+    """200 launches of a team-heavy configuration in a row: every one equal to the first, the watchdog flag never set."""
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    w, h = 64, 36
+    acc, fb = _dev_buffers(w, h)
+    p = api.make_params(w, h, 48, 16, frame=0, nee=True, importance=True, scene=gs)
+    _launch_dev(api, gs, p, acc, fb)
+    first = acc.clone()
+    o = osc.render(p, math_mode=1, use_bvh=True)
+    assert np.array_equal(first.cpu().numpy().view(np.uint32), o["accum"].view(np.uint32))
+    import torch
+    for i in range(200):
+        acc.zero_()
+        _launch_dev(api, gs, p, acc, fb)
+        assert torch.equal(acc.view(torch.int32), first.view(torch.int32)), i
+    gs.check_error()
+
+
+# ---- launches the wavefront record cannot hold fall back to pipeline 1 (ADVICE round 1) ----------------------------------------
+def test_max_depth_above_255_terminates_and_matches_oracle(api, port):
+    """maxDepth = 300 on a closed refractive box with Kd = 1: total internal reflection keeps Russian roulette from ever
+    ending a path, so only `depth >= maxDepth` (pathTracerPrograms.cu:767) does.  The wavefront record packs the depth
+    into 8 bits; such launches run on pipeline 1 and equal the oracle."""
+    c = np.array([[100, 100, 200], [400, 100, 200], [400, 400, 200], [100, 400, 200],
+                  [100, 100, 500], [400, 100, 500], [400, 400, 500], [100, 400, 500]], np.float32)
+    quads = [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (2, 3, 7, 6), (1, 2, 6, 5), (0, 3, 7, 4)]
+    idx = np.array([t for q in quads for t in ((q[0], q[1], q[2]), (q[0], q[2], q[3]))], np.uint32)
+    v4 = np.ones((8, 4), np.float32)
+    v4[:, :3] = c
+    mats = [dict(name="RefractiveBox", Kd=(1, 1, 1), Ke=(0, 0, 0), Ni=1.5)]
+    arr = S.SceneArrays(verts=v4, indices=idx, mat_ids=np.zeros(12, np.uint32), materials=mats, name="glassbox")
+    gs, osc = api.Scene(arr, background=(0.2, 0.3, 0.4)), O.OracleScene(port, arr, background=(0.2, 0.3, 0.4))
+    try:
+        p = api.make_params(48, 32, 2, 300, frame=0, nee=True, importance=True, scene=gs)
+        g = gs.launch_host(p)
+        o = osc.render(p, math_mode=1, use_bvh=True)
+        assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32))
+        assert gs.last_launch_info()["block"] == 256                       # render_persistent_kernel
+        p255 = api.make_params(48, 32, 2, 255, frame=0, nee=True, importance=True, scene=gs)
+        g = gs.launch_host(p255)
+        o = osc.render(p255, math_mode=1, use_bvh=True)
+        assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32))
+        assert gs.last_launch_info()["block"] != 256                       # the wavefront kernel holds 255
+        gs.set_pipeline(2)
+        with pytest.raises(api.PtError):                                   # asked for the wavefront explicitly: refused, not wrong
+            gs.launch_host(p)
+    finally:
+        gs.destroy()
+
+
+def test_image_wider_than_65535_pixels(api, port, scenes_cache):
+    """The wavefront record packs a pixel into 16 + 16 bits; a 70000 x 2 image runs on pipeline 1 and equals the oracle."""
+    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
+    p = api.make_params(70000, 2, 1, 4, frame=0, nee=True, importance=True, scene=gs)
+    g = gs.launch_host(p)
+    o = osc.render(p, math_mode=1, use_bvh=True)
+    assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32))
+    assert gs.last_launch_info()["block"] == 256
