@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -209,6 +210,11 @@ int pt_scene_create(const float* verts_xyzw, uint32_t n_verts, const uint32_t* i
         const float l2 = src.emission.x * src.emission.x + src.emission.y * src.emission.y + src.emission.z * src.emission.z;
         d.emissive = sqrtf(l2) > 0.0f ? 1 : 0;
     }
+    {
+        bool seen[3] = {false, false, false};
+        for (uint32_t m = 0; m < n_materials; ++m) seen[materials[m].bsdfType] = true;
+        s->n_bsdf_types = (uint32_t)seen[0] + (uint32_t)seen[1] + (uint32_t)seen[2];
+    }
     cudaStream_t stream = 0;
     A(cudaMemsetAsync(s->d_counters, 0, 32 * sizeof(unsigned long long), stream));
     if (n_verts) A(cudaMemcpyAsync(s->d_verts, verts_xyzw, sizeof(float4) * n_verts, cudaMemcpyHostToDevice, stream));
@@ -379,6 +385,10 @@ int pt_launch_host(const pt_params* hp, uint64_t* h2d_bytes, uint64_t* d2h_bytes
         PT_CUDA(cudaMemcpyAsync(s->d_stage_accum, hp->accumulationBuffer, pixels * sizeof(float4), cudaMemcpyHostToDevice, stream));
         up += pixels * sizeof(float4);
     }
+    // test aid (PTB_POISON=1 in the environment): frame 0 must write every pixel, so the staging image starts as NaNs --
+    // a pixel the kernel failed to write cannot hide behind the previous launch's value
+    static const bool poison = getenv("PTB_POISON") != nullptr;
+    if (poison && hp->currentFrameIdx == 0) PT_CUDA(cudaMemsetAsync(s->d_stage_accum, 0xff, pixels * sizeof(float4), stream));
     pt_params dp = *hp;
     dp.accumulationBuffer = s->d_stage_accum;
     dp.frameBuffer = hp->frameBuffer ? s->d_stage_frame : nullptr;

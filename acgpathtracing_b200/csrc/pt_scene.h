@@ -42,6 +42,7 @@ struct WfTune {
     int quant = -1;          // -1: follow Scene::traversal; 0 / 1: exact 64-byte / quantised 32-byte nodes for scenes in global memory
     int team = 1;            // sample teams: idle path slots take samples of a pixel another slot of their column is working on
     int team_min = 2;        // ... when that pixel has at least this many samples left to hand out
+    int msort = 0;           // material-sorted SHADE: one queue per BSDF type (scenes with more than one type); measured, see DESIGN.md
 };
 
 struct TileOrder {           // one cached work order (render.cu tile_order_update)
@@ -58,6 +59,7 @@ struct Scene {
     uint64_t magic = kSceneMagic;
     int device = 0;
     uint32_t n_verts = 0, n_tris = 0, n_mats = 0, n_nodes = 0;
+    uint32_t n_bsdf_types = 0;     // distinct BSDF types in the material table
     uint32_t bvh_depth = 0;        // internal nodes on the longest root-to-leaf chain
     float background[3] = {0.f, 0.f, 0.f};
     float build_ms = 0.f;

@@ -44,12 +44,14 @@ namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kWfBlock = 768;          // most threads per CTA (24 warps, 80 registers); one CTA per SM
-constexpr int kCtlF4 = 129;            // float4s in front of the state arrays: mask[5][32] + 4 control words + idle[32] + team[10][32]
+constexpr int kCtlF4 = 137;            // float4s in front of the state arrays: mask[7][32] + 4 control words + idle[32] + team[9][32]
 constexpr int kStateF4 = 9;            // float4 state arrays per path
 constexpr size_t kMaxSmem = 227 * 1024;
 
-enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3, ST_PIXEL = 4, ST_TAIL = 5 };   // 0..4 have queues; TAIL serves NODE + LEAF
-constexpr int kQueues = 5;
+// stages 0..4 have a queue row each; rows 5 and 6 are the SHADE queues of metallic and refractive hits when shading is sorted by
+// material (MSORT: row 2 then holds the diffuse hits only); TAIL serves NODE + LEAF
+enum : int { ST_NODE = 0, ST_LEAF = 1, ST_SHADE = 2, ST_END = 3, ST_PIXEL = 4, ST_SHADE1 = 5, ST_SHADE2 = 6, ST_TAIL = 7 };
+constexpr int kQueues = 7;
 constexpr uint32_t kCandNone = 0xffffffffu;       // per-pixel candidate list: no triangle can be hit by a camera ray
 constexpr uint32_t kCandOverflow = 0xfffffffeu;   // more than 4 candidates (or lists disabled): traverse the BVH
 enum : int { MODE_RAD = 0, MODE_SHADOW = 1, MODE_SHADED = 2, MODE_FRESH = 3, MODE_NEWPIX = 4, MODE_JOIN = 5 };
@@ -214,7 +216,7 @@ __device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, cons
 // (only the two jitter draws move it) and the LCG can jump there in O(log k) integer steps (lcg_skip).  What is
 // ordered is only the float sum `result += emission; result += radiance * attenuation` (:760-761).  So, when a column
 // has slots with nothing to do (no pixels left to take), a pixel can be handed to the column's TEAM:
-//   * the team's state lives in ten shared-memory words of the column: how many samples it has, how many were handed
+//   * the team's state lives in nine shared-memory words of the column: how many samples it has, how many were handed
 //     out (one CAS), the pixel's seed / coordinates / candidate list, the running sum and how many samples are in it;
 //   * every slot of the column that has no pixel takes the next sample index k, runs that path exactly like any other,
 //     and instead of adding its (non-zero) terms to a result it appends them to the log of sample k in global memory
@@ -225,7 +227,7 @@ __device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, cons
 //     a long sample only delays the frontier, bounded by the log window (then slots park until it moves);
 //   * the slot that commits the last sample carries the pixel to the PIXEL stage, which writes it as usual.
 // One team per column at a time; lanes only touch their own column's words, like the queues.
-enum : int { T_TAKE = 0, T_COMMIT, T_LOCK, T_CLAIM, T_SEED, T_PIX, T_CAND, T_RX, T_RY, T_RZ, kTeamWords };
+enum : int { T_TAKE = 0, T_COMMIT, T_LOCK, T_SEED, T_PIX, T_CAND, T_RX, T_RY, T_RZ, kTeamWords };
 static_assert(kCtlF4 * 4 >= kQueues * 32 + 4 + 32 + kTeamWords * 32, "control block too small");
 
 struct Team {              // this lane's column
@@ -252,6 +254,8 @@ __device__ __forceinline__ uint32_t lcg_skip(uint32_t s, uint32_t n)
     return A * s + C;
 }
 
+// tune "team=2": a team still open at kernel exit (a bug) leaves its words in d_counters[27..30] (pt_scene_get_sched_stats 11..14)
+__device__ __forceinline__ bool team_debug_dump(const WfConst& wc) { return wc.team > 1; }
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p)
 {
     uint32_t v;
@@ -273,7 +277,8 @@ __device__ __forceinline__ int team_take(const Team& t)
 // parked slots of this column back to work (END stage, MODE_JOIN)
 __device__ __forceinline__ void team_wake(const Team& t, uint32_t* mask, uint32_t* ctl, int lane)
 {
-    if (vol_ld(t.idle) == 0u) return;
+    __threadfence_block();                            // "samples available, then look for parked slots" against team_park's
+    if (vol_ld(t.idle) == 0u) return;                 // "parked, then look for samples": sequentially consistent on both sides
     const uint32_t m = atomicExch(t.idle, 0u);
     if (m) {
         atomicAdd(ctl, (uint32_t)__popc(m));          // before they become visible: the exit test must never see 0 too early
@@ -289,6 +294,7 @@ __device__ __forceinline__ bool team_park(const Team& t, uint32_t* ctl, int j)
     __threadfence_block();
     atomicOr(t.idle, 1u << j);
     atomicSub(ctl, 1u);
+    __threadfence_block();
     const uint32_t w = vol_ld(t.w + T_TAKE * 32), n = w >> 16, i = w & 0xffffu;
     if (i < n && i <= vol_ld(t.w + T_COMMIT * 32) + t.wmask) {
         if (atomicAnd(t.idle, ~(1u << j)) & (1u << j)) {
@@ -308,14 +314,26 @@ __device__ __forceinline__ void team_log_term(const Team& t, uint32_t k, uint32_
 }
 
 // Sample k of the column's team has ended with n_terms logged terms.  Publishes it and commits whatever is finished at
-// the frontier.  True: this call committed the pixel's last sample -- `result` is the pixel's sum, the team is dissolved.
-__device__ __noinline__ bool team_finish(const Team t, uint32_t k, uint32_t n_terms, float3& result, uint32_t* mask, uint32_t* ctl, int lane)
+// the frontier.  True: this call committed the last sample of a pixel -- `result` is its sum, `pix` its coordinates, the
+// team is dissolved and the caller carries the pixel to the PIXEL stage.  (The lock holder works for whatever team is open:
+// a slot whose own sample was committed by someone else may find the next team here and complete that one.)
+__device__ __noinline__ bool team_finish(const Team t, uint32_t k, uint32_t n_terms, float3& result, uint32_t& pix, uint32_t* mask,
+                                         uint32_t* ctl, int lane)
 {
     st_release(t.meta + (k & t.wmask), ((k + 1u) << 9) | n_terms);
     for (;;) {
+        // "publish, then look at the lock" here against "unlock, then look at the frontier" in the holder: a store followed by a
+        // load of another location on both sides.  Without a sequentially consistent fence between them both can read the old
+        // value -- the holder leaves, this slot gives up, and if it was the team's last sample nobody ever commits it.
+        __threadfence_block();
         if (atomicCAS(t.w + T_LOCK * 32, 0u, 1u) != 0u) return false;      // the holder re-checks the frontier after unlocking
         __threadfence_block();
-        const uint32_t cm0 = vol_ld(t.w + T_COMMIT * 32), n = vol_ld(t.w + T_TAKE * 32) >> 16;
+        const uint32_t n = vol_ld(t.w + T_TAKE * 32) >> 16;
+        if (n == 0u) {                                                     // no team open: mine has been completed
+            atomicExch(t.w + T_LOCK * 32, 0u);
+            return false;
+        }
+        const uint32_t cm0 = vol_ld(t.w + T_COMMIT * 32);
         uint32_t cm = cm0;
         float3 r = f3(__uint_as_float(vol_ld(t.w + T_RX * 32)), __uint_as_float(vol_ld(t.w + T_RY * 32)), __uint_as_float(vol_ld(t.w + T_RZ * 32)));
         while (cm < n) {
@@ -328,31 +346,36 @@ __device__ __noinline__ bool team_finish(const Team t, uint32_t k, uint32_t n_te
             }
             ++cm;
         }
+        volatile uint32_t* w = t.w;
         if (cm == n) {
             result = r;
-            *reinterpret_cast<volatile uint32_t*>(t.w + T_TAKE * 32) = 0u;   // no team: nothing can be taken (all n were)
+            pix = w[T_PIX * 32];
+            w[T_TAKE * 32] = 0u;                                           // the team is closed (all n samples were taken long ago)
             __threadfence_block();
             atomicExch(t.w + T_LOCK * 32, 0u);
-            atomicExch(t.w + T_CLAIM * 32, 0u);
             return true;
         }
-        *reinterpret_cast<volatile uint32_t*>(t.w + T_RX * 32) = __float_as_uint(r.x);
-        *reinterpret_cast<volatile uint32_t*>(t.w + T_RY * 32) = __float_as_uint(r.y);
-        *reinterpret_cast<volatile uint32_t*>(t.w + T_RZ * 32) = __float_as_uint(r.z);
-        *reinterpret_cast<volatile uint32_t*>(t.w + T_COMMIT * 32) = cm;
+        w[T_RX * 32] = __float_as_uint(r.x);
+        w[T_RY * 32] = __float_as_uint(r.y);
+        w[T_RZ * 32] = __float_as_uint(r.z);
+        w[T_COMMIT * 32] = cm;
         __threadfence_block();
         atomicExch(t.w + T_LOCK * 32, 0u);
+        __threadfence_block();                                             // (see above)
         if (cm != cm0) team_wake(t, mask, ctl, lane);                      // the window moved
         if ((ld_acquire(t.meta + (cm & t.wmask)) >> 9) != cm + 1u) return false;
     }
 }
 
 // A slot that works alone on a pixel (`left` samples to go, pixel seed before the next sample's jitter draws) hands it to
-// the column's team.  False: the team is taken.
+// the column's team.  False: a team is open already.  The claim is a CAS on T_TAKE itself (closed -> "being set up": no
+// samples, so nobody takes or commits anything) and never touches T_LOCK: whoever holds T_LOCK is a committer that
+// re-checks the frontier when it unlocks -- team_finish relies on that when it finds the lock taken.
+constexpr uint32_t kTeamSetup = 0x0000ffffu;
 __device__ __noinline__ bool team_create(const Team t, uint32_t left, uint32_t pixel_seed, uint32_t pix, uint32_t cand, float3 result,
                                          uint32_t* mask, uint32_t* ctl, int lane)
 {
-    if (atomicCAS(t.w + T_CLAIM * 32, 0u, 1u) != 0u) return false;
+    if (vol_ld(t.w + T_TAKE * 32) != 0u || atomicCAS(t.w + T_TAKE * 32, 0u, kTeamSetup) != 0u) return false;
     for (uint32_t i = 0; i <= t.wmask; i += 4) *reinterpret_cast<uint4*>(t.meta + i) = make_uint4(0u, 0u, 0u, 0u);   // marks of an earlier team
     volatile uint32_t* w = t.w;
     w[T_COMMIT * 32] = 0u;
@@ -376,14 +399,14 @@ __device__ __noinline__ bool team_create(const Team t, uint32_t left, uint32_t p
 // profiles/r1_c3_c4_traversal_variants.txt -- and were removed.)
 enum : int { TRAV_DIRECT = 0, TRAV_QUANT = 1 };
 
-template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV>
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV, bool MSORT>
 __global__ void __launch_bounds__(kWfBlock, 1)
 render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_constant__ WfConst wc)
 {
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t NP = wc.np;
-    uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);            // [5][32]
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);            // [7][32]
     uint32_t* ctl = mask + kQueues * 32;                            // [0] slots that are not parked  [1] error flag
     constexpr bool TEAM = !PROBE;                                   // the probes record per-pixel sequential state
     Team tm;
@@ -453,7 +476,13 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     ThreadCounters ctr = {};
     uint32_t st_batches[4] = {0, 0, 0, 0}, st_lanes[4] = {0, 0, 0, 0}, st_steps = 0, st_step_lanes = 0, st_idle = 0;
     uint32_t it = 0, idle_polls = 0;
-    int stage = -1, sticky = 0;
+    int stage = -1, sticky = 0, row = 0;     // row: the queue the stage pops from (its own; SHADE has three when MSORT)
+    // MSORT: which SHADE queue a hit goes to -- the BSDF type of the primitive's material (the switch at :905-983)
+    auto shade_row_of = [&](uint32_t prim) -> int {
+        if (!MSORT) return ST_SHADE;
+        const int b = __float_as_int(f.mat(__float_as_int(f.tri_shade(prim).w), 1).w);
+        return b == 0 ? ST_SHADE : (b == 1 ? ST_SHADE1 : ST_SHADE2);
+    };
 
     for (;;) {
         // ---- vote ---------------------------------------------------------------------------------------------------
@@ -463,7 +492,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         uint32_t msnap = 0u, msnap2 = 0u;
         bool decided = false;
         if (stage >= 0 && stage != ST_TAIL && sticky < wc.sticky) {
-            msnap = vol_ld(mask + stage * 32 + lane);
+            msnap = vol_ld(mask + row * 32 + lane);
             if (__all_sync(kFull, msnap != 0u)) {
                 ++sticky;
                 decided = true;
@@ -474,8 +503,17 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             const uint32_t m2 = vol_ld(mask + 2 * 32 + lane), m3 = vol_ld(mask + 3 * 32 + lane);
             const uint32_t m4 = vol_ld(mask + 4 * 32 + lane);
             const uint32_t b0 = __ballot_sync(kFull, m0 != 0u), b1 = __ballot_sync(kFull, m1 != 0u);
-            const uint32_t b2 = __ballot_sync(kFull, m2 != 0u), b3 = __ballot_sync(kFull, m3 != 0u);
+            uint32_t b2 = __ballot_sync(kFull, m2 != 0u);
+            const uint32_t b3 = __ballot_sync(kFull, m3 != 0u);
             const uint32_t b4 = __ballot_sync(kFull, m4 != 0u);
+            uint32_t mshade = m2;
+            int shade_row = ST_SHADE;
+            if (MSORT) {                                     // the fullest of the three SHADE queues stands for the stage
+                const uint32_t m5 = vol_ld(mask + ST_SHADE1 * 32 + lane), m6 = vol_ld(mask + ST_SHADE2 * 32 + lane);
+                const uint32_t b5 = __ballot_sync(kFull, m5 != 0u), b6 = __ballot_sync(kFull, m6 != 0u);
+                if (__popc(b5) > __popc(b2)) b2 = b5, mshade = m5, shade_row = ST_SHADE1;
+                if (__popc(b6) > __popc(b2)) b2 = b6, mshade = m6, shade_row = ST_SHADE2;
+            }
             if ((b0 | b1 | b2 | b3 | b4) == 0u) {
                 if (vol_ld(ctl) == 0u) break;                // every slot is parked: no pixel left to take, no team to serve
                 if (++idle_polls > (1u << 26)) {             // watchdog: never spin forever
@@ -521,7 +559,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 }
             }
             if (stage != ST_TAIL)
-                msnap = stage == ST_NODE ? m0 : (stage == ST_LEAF ? m1 : (stage == ST_SHADE ? m2 : (stage == ST_END ? m3 : m4)));
+                msnap = stage == ST_NODE ? m0 : (stage == ST_LEAF ? m1 : (stage == ST_SHADE ? mshade : (stage == ST_END ? m3 : m4)));
+            row = stage == ST_SHADE ? shade_row : stage;
         }
         const int rot = (warp * 7 + (int)(it++)) & 31;
 
@@ -571,7 +610,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
             if (active) {
                 TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(kTravDone), __int_as_float(t.sp | (mode << 8)));
-                wf_push(mask, (mode == MODE_RAD && t.prim != kNoPrim) ? ST_SHADE : ST_END, lane, j);
+                wf_push(mask, (mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of(t.prim) : ST_END, lane, j);
             }
             stage = -1;
         } else if (stage == ST_NODE) {
@@ -620,7 +659,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(t.cur), __int_as_float(t.sp | (mode << 8)));
                 const int next = t.cur >= 0 ? ST_NODE
                                             : (t.cur != kTravDone ? ST_LEAF
-                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? ST_SHADE : ST_END));
+                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of(t.prim) : ST_END));
                 wf_push(mask, next, lane, j);
             }
         } else if (stage == ST_LEAF) {
@@ -645,12 +684,12 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(t.cur), __int_as_float(t.sp | (mode << 8)));
                 const int next = t.cur >= 0 ? ST_NODE
                                             : (t.cur != kTravDone ? ST_LEAF
-                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? ST_SHADE : ST_END));
+                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of(t.prim) : ST_END));
                 wf_push(mask, next, lane, j);
             }
         } else if (stage == ST_SHADE) {
             // ---- SHADE: __closesthit__diffuse__ch :866-1031 up to the occlusion trace -------------------------------
-            const int j = wf_pop_converged(mask + ST_SHADE * 32 + lane, msnap, rot);
+            const int j = wf_pop_converged(mask + row * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_SHADE]++, st_lanes[ST_SHADE] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
@@ -814,10 +853,11 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                     // :767
                         if (TEAM && team) {
                             // the team's sample `left` has ended: publish it; whoever holds the lock commits in sample order
-                            if (team_finish(tm, left, n_terms, result, mask, ctl, lane)) {
-                                // ... and this slot committed the pixel's last sample: it carries the pixel to the PIXEL stage
+                            uint32_t done_pix = 0u;
+                            if (team_finish(tm, left, n_terms, result, done_pix, mask, ctl, lane)) {
+                                // ... and this slot committed a pixel's last sample: it carries that pixel to the PIXEL stage
                                 P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                                P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), p1.w);
+                                P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(done_pix));
                                 RS[pid] = pack(result, 0.0f);
                                 wf_push(mask, ST_PIXEL, lane, j);
                                 alive = false;
@@ -834,7 +874,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                             need_sample = true;
                             // slots of this column are parked and the pixel has samples to spare: hand it to the column's team
                             // (and go on as one of its members)
-                            if (use_teams && left >= (uint32_t)wc.team_min && left <= 0xffffu && vol_ld(tm.idle) != 0u &&
+                            if (use_teams && left >= (uint32_t)wc.team_min && left < 0xffffu && vol_ld(tm.idle) != 0u &&
                                 (!SHORT || CAND[pid] != kCandNone))
                                 team = team_create(tm, left, pixel_seed, pix, SHORT ? CAND[pid] : kCandOverflow, result, mask, ctl, lane);
                         }
@@ -940,7 +980,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     R0[pid] = pack(r.o, 0.0f);
                     R1[pid] = pack(r.d, 0.0f);
                     TS[pid] = make_float4(best_t, __uint_as_float(best_prim), __int_as_float(kTravDone), __int_as_float(MODE_RAD << 8));
-                    wf_push(mask, best_prim != kNoPrim ? ST_SHADE : ST_END, lane, j);
+                    wf_push(mask, best_prim != kNoPrim ? shade_row_of(best_prim) : ST_END, lane, j);
                 } else {
                     const Ray r = make_ray(p.o, p.d);                                          // traceRadiance :577-635
                     R0[pid] = pack(r.o, 0.0f);
@@ -974,13 +1014,28 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             atomicAdd(lc.counters + 26, (unsigned long long)st_idle);
         }
     }
+    // a team that is still open when every slot has parked would be a lost pixel: never expected, reported like the watchdog
+    if (use_teams && warp == 0 && vol_ld(tm.w + T_TAKE * 32) != 0u) {
+        ctl[1] = 1u;
+        if (team_debug_dump(wc)) {
+            const uint32_t tk = vol_ld(tm.w + T_TAKE * 32), cm = vol_ld(tm.w + T_COMMIT * 32);
+            atomicAdd(lc.error_flag + 12, 1ull);
+            lc.error_flag[13] = tk;
+            lc.error_flag[14] = cm;
+            unsigned long long marks = 0;
+            for (uint32_t k2 = 0; k2 < 32u && k2 < (tk >> 16); ++k2)
+                if ((ld_acquire(tm.meta + (k2 & tm.wmask)) >> 9) == k2 + 1u) marks |= 1ull << k2;
+            lc.error_flag[15] = marks | ((unsigned long long)vol_ld(tm.w + T_LOCK * 32) << 40) | ((unsigned long long)vol_ld(tm.idle) << 44 >> 44 << 48);
+        }
+    }
+    __syncwarp();
     if (threadIdx.x == 0 && vol_ld(ctl + 1)) atomicAdd(lc.error_flag, 1ull);   // watchdog fired
 }
 
-template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV>
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV, bool MSORT = false>
 cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc, size_t smem_bytes, cudaStream_t stream)
 {
-    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE, SHORT, TRAV>;
+    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE, SHORT, TRAV, MSORT>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -1044,7 +1099,8 @@ static const TuneKey kTuneKeys[] = {{"node_votes_g", &WfTune::node_votes_g}, {"f
                                     {"smem_kb", &WfTune::smem_kb},       {"shortlist", &WfTune::shortlist},
                                     {"quant", &WfTune::quant},           {"idle_ns", &WfTune::idle_ns},
                                     {"idle_shift", &WfTune::idle_shift}, {"stack_smem", &WfTune::stack_smem},
-                                    {"team", &WfTune::team},             {"team_min", &WfTune::team_min}};
+                                    {"team", &WfTune::team},             {"team_min", &WfTune::team_min},
+                                    {"msort", &WfTune::msort}};
 
 bool wf_tune_apply(WfTune& t, const char* spec)
 {
@@ -1195,11 +1251,13 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
             if (s.d_team_log) cudaFree(s.d_team_log);
             s.d_team_log = nullptr;
             s.team_log_bytes = 0;
-            if (cudaMalloc((void**)&s.d_team_log, need) == cudaSuccess) s.team_log_bytes = need;
+            if (cudaMalloc((void**)&s.d_team_log, need) == cudaSuccess) {
+                s.team_log_bytes = need;
+            }
             else cudaGetLastError();                     // no memory for the log: this launch runs without teams
         }
         if (s.team_log_bytes >= need) {
-            wc.team = 1;
+            wc.team = tune.team;
             wc.team_log = reinterpret_cast<float4*>(s.d_team_log);
             wc.team_meta = reinterpret_cast<uint32_t*>(wc.team_log + (size_t)sms * 32u * (wc.team_wmask + 1u) * wc.team_cap);
         }
@@ -1225,6 +1283,11 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
             return launch_wavefront<false, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
         }
         trav = TRAV_DIRECT;                              // a box could not be contained (never expected): exact nodes
+    }
+    // material-sorted SHADE batches (pt_scene_set_tune "msort=1"; A/B in profiles/): scenes with more than one BSDF type
+    if (tune.msort != 0 && s.n_bsdf_types > 1 && !probe && !count && !use_short) {
+        if (scene == 0) return launch_wavefront<false, false, 0, false, TRAV_DIRECT, true>(s, lc, wc, smem_bytes, stream);
+        if (scene < 0) return launch_wavefront<false, false, -1, false, TRAV_DIRECT, true>(s, lc, wc, smem_bytes, stream);
     }
 #define PTB_WF_DISPATCH(COUNT, PROBE, SHORT)                                                      \
     (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream)   \

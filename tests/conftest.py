@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("PTB_POISON", "1")      # pt_launch_host starts frame 0 from NaNs: an unwritten pixel cannot pass a comparison
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:

@@ -903,6 +903,7 @@ TEAM_CASES = [
     ("cornell", 24, 16, 96, 200, ""),                  # deep logs: 202 entries per sample, a window of 16 samples (parking)
     ("cornell", 40, 24, 64, 16, "paths32=4,block=128"),
     ("cornell", 40, 24, 64, 16, "team=0"),             # the sequential chain, for reference
+    ("material", 64, 36, 24, 28, "msort=1"),           # SHADE batches sorted by BSDF type (three queues)
 ]
 
 
@@ -977,7 +978,7 @@ def test_schedule_perturbation(api, port, scenes_cache):
             spec = dict(block=block, paths32=paths32, node_votes=int(rng.integers(1, 9)), node_keep8=int(rng.integers(0, 9)),
                         full_cols=int(rng.integers(1, 33)), sticky=int(rng.integers(0, 9)), tail_cols=int(rng.choice([0, 8, 24, 64, 160])),
                         idle_ns=int(rng.choice([0, 16, 64, 512])), idle_shift=int(rng.integers(0, 6)), stack_smem=int(rng.choice([0, 2, 5, 12])),
-                        team=int(rng.choice([0, 1, 1])), team_min=int(rng.choice([1, 2, 8, 20])))
+                        team=int(rng.choice([0, 1, 1])), team_min=int(rng.choice([1, 2, 8, 20])), msort=int(rng.choice([0, 1])))
             tune = ",".join(f"{k}={v}" for k, v in spec.items())
             tried.append(tune)
             gs.set_tune(tune)
