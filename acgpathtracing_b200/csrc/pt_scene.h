@@ -40,7 +40,8 @@ struct WfTune {
     int stack_smem = 12;     // scenes in global memory: traversal-stack levels kept in shared memory, deeper ones spill to
                              // global memory (0 = all in shared memory).  C4: 672 -> 992 paths per CTA, +21 %
     int quant = -1;          // -1: follow Scene::traversal; 0 / 1: exact 64-byte / quantised 32-byte nodes for scenes in global memory
-    int team = 1;            // sample teams: idle path slots take samples of a pixel another slot of their column is working on
+    int team = 1;            // sample teams (idle path slots take samples of a pixel another slot of their column is working on):
+                             // 0 off, 1 auto (scenes read from global memory), 2 on, 3 on + state dump when a team is left open
     int team_min = 2;        // ... when that pixel has at least this many samples left to hand out
     int msort = 0;           // material-sorted SHADE: one queue per BSDF type (scenes with more than one type); measured, see DESIGN.md
 };

@@ -183,10 +183,12 @@ __device__ __forceinline__ float to_srgb(float c)
     const float powed = ptdet::powf_(c, invGamma);
     return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
 }
+// one channel; out of line so that the three channels share one copy of the ~220-instruction powf (it runs once per pixel and
+// launch, and the render kernel's hot code is larger than the instruction cache as it is)
+static __device__ __noinline__ unsigned int srgb8(float c) { return quantize8(to_srgb(clampf(c, 0.0f, 1.0f))); }
 __device__ __forceinline__ uchar4 make_color(float3 c)
 {
-    c = f3(clampf(c.x, 0.0f, 1.0f), clampf(c.y, 0.0f, 1.0f), clampf(c.z, 0.0f, 1.0f));
-    return make_uchar4(quantize8(to_srgb(c.x)), quantize8(to_srgb(c.y)), quantize8(to_srgb(c.z)), 255u);
+    return make_uchar4((unsigned char)srgb8(c.x), (unsigned char)srgb8(c.y), (unsigned char)srgb8(c.z), 255u);
 }
 
 // Per-path registers (RadiancePayloadRayData, pathTracer.h:19-32, minus what never leaves a stage).

@@ -44,7 +44,7 @@ namespace {
 
 constexpr uint32_t kFull = 0xffffffffu;
 constexpr int kWfBlock = 768;          // most threads per CTA (24 warps, 80 registers); one CTA per SM
-constexpr int kCtlF4 = 137;            // float4s in front of the state arrays: mask[7][32] + 4 control words + idle[32] + team[9][32]
+constexpr int kCtlF4 = 169;            // float4s in front of the state arrays: mask[7][32] + 4 control words + idle[32] + team[13][32]
 constexpr int kStateF4 = 9;            // float4 state arrays per path
 constexpr size_t kMaxSmem = 227 * 1024;
 
@@ -76,9 +76,8 @@ struct WfConst {
     int team;                // 0 = off
     int team_min;            // a pixel is handed to a team when it has at least this many samples left
     uint32_t team_wmask;     // log window (samples in flight beyond the commit frontier) - 1; power of two - 1
-    uint32_t team_cap;       // log entries per sample = maxDepth + 2
+    uint32_t team_cap;       // log entries per sample = maxDepth + 3 (emission, one term per segment, terminator)
     float4* team_log;        // [grid][32 columns][window][team_cap]
-    uint32_t* team_meta;     // [grid][32 columns][window]: (sample + 1) << 9 | terms, written when the sample has ended
 };
 
 struct ThreadCounters {
@@ -216,27 +215,44 @@ __device__ __forceinline__ uint32_t pixel_candidates(const LaunchConst& lc, cons
 // (only the two jitter draws move it) and the LCG can jump there in O(log k) integer steps (lcg_skip).  What is
 // ordered is only the float sum `result += emission; result += radiance * attenuation` (:760-761).  So, when a column
 // has slots with nothing to do (no pixels left to take), a pixel can be handed to the column's TEAM:
-//   * the team's state lives in nine shared-memory words of the column: how many samples it has, how many were handed
-//     out (one CAS), the pixel's seed / coordinates / candidate list, the running sum and how many samples are in it;
+//   * the team's state lives in thirteen shared-memory words of the column: how many samples it has and how many were
+//     handed out (one word, one CAS), the commit frontier, the pixel's seed / coordinates / candidate list, the running
+//     sum, and one "ended" bit per sample of the log window;
 //   * every slot of the column that has no pixel takes the next sample index k, runs that path exactly like any other,
 //     and instead of adding its (non-zero) terms to a result it appends them to the log of sample k in global memory
 //     (adding +-0 never changes this sum: it starts at +0 and can never become -0);
-//   * when its sample ends the slot publishes the term count (release), and whoever gets the team's lock adds the logged
-//     terms of all finished samples at the commit frontier, IN SAMPLE ORDER, to the running sum -- the same additions in
-//     the same order as the sequential loop, hence the same bits.  Nobody waits: the slot takes the next sample at once;
-//     a long sample only delays the frontier, bounded by the log window (then slots park until it moves);
+//   * when its sample ends the slot closes the log with a terminator, sets the sample's bit, and whoever gets the team's
+//     lock adds the logged terms of all ended samples at the commit frontier, IN SAMPLE ORDER, to the running sum -- the
+//     same additions in the same order as the sequential loop, hence the same bits.  Nobody waits: the slot takes the
+//     next sample at once; a long sample only delays the frontier, bounded by the log window (then slots park until it
+//     moves);
 //   * the slot that commits the last sample carries the pixel to the PIXEL stage, which writes it as usual.
-// One team per column at a time; lanes only touch their own column's words, like the queues.
-enum : int { T_TAKE = 0, T_COMMIT, T_LOCK, T_SEED, T_PIX, T_CAND, T_RX, T_RY, T_RZ, kTeamWords };
+// One team per column at a time; lanes only touch their own column's words, like the queues.  All of it is out of line
+// (noinline functions that rebuild their view from the kernel parameters): a slot that works alone pays one flag test
+// per stage visit and one shared-memory load per sample.
+enum : int { T_TAKE = 0, T_COMMIT, T_LOCK, T_SEED, T_PIX, T_CAND, T_RX, T_RY, T_RZ, T_DONE, kTeamWords = T_DONE + 4 };
+constexpr uint32_t kTeamWindowMax = 128;   // 4 words of "ended" bits
 static_assert(kCtlF4 * 4 >= kQueues * 32 + 4 + 32 + kTeamWords * 32, "control block too small");
+constexpr uint32_t kTeamSetup = 0x0000ffffu;        // T_TAKE while a team is being set up: no samples, nothing to take or commit
+constexpr float kLogEnd = 1.0f;                     // .w of the entry that closes a sample's log (terms carry 0)
 
 struct Team {              // this lane's column
     uint32_t* w;           // team word i at w[i * 32]:  T_TAKE = samples << 16 | handed out
     uint32_t* idle;        // bit j: slot 32 j + lane is parked (its TS already says MODE_JOIN)
-    uint32_t* meta;        // [window]
     float4* log;           // [window][cap]
     uint32_t wmask, cap;
 };
+
+__device__ __forceinline__ Team team_view(const WfConst& wc, uint32_t* ctl, int lane)
+{
+    Team t;
+    t.idle = ctl + 4 + lane;
+    t.w = ctl + 4 + 32 + lane;
+    t.wmask = wc.team_wmask;
+    t.cap = wc.team_cap;
+    t.log = wc.team_log + ((size_t)blockIdx.x * 32 + lane) * (wc.team_wmask + 1u) * wc.team_cap;
+    return t;
+}
 
 // n draws ahead: s -> A_n s + C_n, by repeated squaring of the affine map s -> 1664525 s + 1013904223 (cuda/random.h:49-56)
 __device__ __forceinline__ uint32_t lcg_skip(uint32_t s, uint32_t n)
@@ -253,16 +269,6 @@ __device__ __forceinline__ uint32_t lcg_skip(uint32_t s, uint32_t n)
     }
     return A * s + C;
 }
-
-// tune "team=2": a team still open at kernel exit (a bug) leaves its words in d_counters[27..30] (pt_scene_get_sched_stats 11..14)
-__device__ __forceinline__ bool team_debug_dump(const WfConst& wc) { return wc.team > 1; }
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.cta.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) { asm volatile("st.release.cta.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // next sample of the column's team, or -1: no team, every sample handed out, or the log window is full
 __device__ __forceinline__ int team_take(const Team& t)
@@ -305,24 +311,21 @@ __device__ __forceinline__ bool team_park(const Team& t, uint32_t* ctl, int j)
     return true;
 }
 
-__device__ __forceinline__ void team_log_term(const Team& t, uint32_t k, uint32_t& n_terms, float3 v)
+// entry `at` of sample k's log
+__device__ __noinline__ void team_log(const WfConst& wc, uint32_t* ctl, int lane, uint32_t k, uint32_t at, float3 v)
 {
-    if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
-        t.log[(size_t)(k & t.wmask) * t.cap + n_terms] = make_float4(v.x, v.y, v.z, 0.0f);
-        ++n_terms;
-    }
+    const Team t = team_view(wc, ctl, lane);
+    t.log[(size_t)(k & t.wmask) * t.cap + at] = make_float4(v.x, v.y, v.z, 0.0f);
 }
 
-// Sample k of the column's team has ended with n_terms logged terms.  Publishes it and commits whatever is finished at
-// the frontier.  True: this call committed the last sample of a pixel -- `result` is its sum, `pix` its coordinates, the
-// team is dissolved and the caller carries the pixel to the PIXEL stage.  (The lock holder works for whatever team is open:
-// a slot whose own sample was committed by someone else may find the next team here and complete that one.)
-__device__ __noinline__ bool team_finish(const Team t, uint32_t k, uint32_t n_terms, float3& result, uint32_t& pix, uint32_t* mask,
-                                         uint32_t* ctl, int lane)
+// Commits whatever has ended at the frontier of the column's team.  True: this call committed the last sample of a pixel
+// -- `result` is its sum, `pix` its coordinates, the team is closed and the caller carries the pixel to the PIXEL stage.
+// (The lock holder works for whatever team is open: a slot whose own sample was committed by someone else may find the
+// next team here and complete that one.)
+__device__ __forceinline__ bool team_commit(const Team& t, float3& result, uint32_t& pix, uint32_t* mask, uint32_t* ctl, int lane)
 {
-    st_release(t.meta + (k & t.wmask), ((k + 1u) << 9) | n_terms);
     for (;;) {
-        // "publish, then look at the lock" here against "unlock, then look at the frontier" in the holder: a store followed by a
+        // "set my bit, then look at the lock" here against "unlock, then look at the frontier" in the holder: a store followed by a
         // load of another location on both sides.  Without a sequentially consistent fence between them both can read the old
         // value -- the holder leaves, this slot gives up, and if it was the team's last sample nobody ever commits it.
         __threadfence_block();
@@ -337,11 +340,16 @@ __device__ __noinline__ bool team_finish(const Team t, uint32_t k, uint32_t n_te
         uint32_t cm = cm0;
         float3 r = f3(__uint_as_float(vol_ld(t.w + T_RX * 32)), __uint_as_float(vol_ld(t.w + T_RY * 32)), __uint_as_float(vol_ld(t.w + T_RZ * 32)));
         while (cm < n) {
-            const uint32_t m = ld_acquire(t.meta + (cm & t.wmask));
-            if ((m >> 9) != cm + 1u) break;
-            const float4* src = t.log + (size_t)(cm & t.wmask) * t.cap;
-            for (uint32_t i = 0; i < (m & 511u); ++i) {
-                const float4 v = src[i];
+            const uint32_t slot = cm & t.wmask, bit = 1u << (slot & 31u);
+            uint32_t* dw = t.w + (T_DONE + (slot >> 5)) * 32;
+            if ((vol_ld(dw) & bit) == 0u) break;
+            __threadfence_block();                                         // acquire: the log of a sample whose bit is set
+            atomicAnd(dw, ~bit);                                           // the window slot is free again once T_COMMIT has passed it
+            const float4* src = t.log + (size_t)slot * t.cap;
+            float4 e0 = __ldcg(src), e1 = __ldcg(src + 1), e2 = __ldcg(src + 2);   // most samples have at most two terms
+            for (uint32_t i = 0;; ++i) {
+                const float4 v = i == 0 ? e0 : (i == 1 ? e1 : (i == 2 ? e2 : __ldcg(src + i)));
+                if (v.w != 0.0f) break;                                    // the terminator
                 r = r + f3(v.x, v.y, v.z);                                 // :760-761, in sample order, term by term
             }
             ++cm;
@@ -358,25 +366,73 @@ __device__ __noinline__ bool team_finish(const Team t, uint32_t k, uint32_t n_te
         w[T_RX * 32] = __float_as_uint(r.x);
         w[T_RY * 32] = __float_as_uint(r.y);
         w[T_RZ * 32] = __float_as_uint(r.z);
+        __threadfence_block();
         w[T_COMMIT * 32] = cm;
         __threadfence_block();
         atomicExch(t.w + T_LOCK * 32, 0u);
         __threadfence_block();                                             // (see above)
         if (cm != cm0) team_wake(t, mask, ctl, lane);                      // the window moved
-        if ((ld_acquire(t.meta + (cm & t.wmask)) >> 9) != cm + 1u) return false;
+        const uint32_t slot = cm & t.wmask;
+        if ((vol_ld(t.w + (T_DONE + (slot >> 5)) * 32) & (1u << (slot & 31u))) == 0u) return false;
+    }
+}
+
+// What a slot of a team does between two samples.  ended >= 0: sample `ended` of the column's team has just finished with
+// n_terms logged terms -- close its log, publish it, commit what can be committed.  Then take the next sample.
+// Everything it hands back goes through the slot's shared-memory record (no reference parameters: a variable whose
+// address is passed to an out-of-line function lives in local memory for the whole kernel):
+//   k >= 0  the slot runs sample k now: P1[pid] = (team bit, k, pixel seed BEFORE the sample's two jitter draws, pixel),
+//           CAND[pid] = 0 terms logged so far; the pixel's candidate list is the team word T_CAND;
+//   -1      nothing to take -- the slot is parked (TS / P1 say so) and must not be touched any more;
+//   -2      this slot committed a pixel's last sample: P1 / RS hold the pixel and the slot is queued for the PIXEL stage.
+__device__ __noinline__ int team_next(const WfConst& wc, float4* smem4, int lane, int j, int ended, uint32_t n_terms)
+{
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);
+    uint32_t* ctl = mask + kQueues * 32;
+    const uint32_t NP = wc.np;
+    const int pid = j * 32 + lane;
+    float4* TS = smem4 + kCtlF4 + 3 * NP;
+    float4* P1 = smem4 + kCtlF4 + 5 * NP;
+    float4* RS = smem4 + kCtlF4 + 6 * NP;
+    uint32_t* CAND = reinterpret_cast<uint32_t*>(smem4 + kCtlF4 + kStateF4 * NP);
+    const Team t = team_view(wc, ctl, lane);
+    if (ended >= 0) {
+        const uint32_t slot = (uint32_t)ended & t.wmask;
+        __stcg(t.log + (size_t)slot * t.cap + n_terms, make_float4(0.0f, 0.0f, 0.0f, kLogEnd));
+        __threadfence();                                                   // release: the log (global memory) before the bit
+        atomicOr(t.w + (T_DONE + (slot >> 5)) * 32, 1u << (slot & 31u));
+        float3 result;
+        uint32_t pix;
+        if (team_commit(t, result, pix, mask, ctl, lane)) {
+            P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(pix));
+            RS[pid] = pack(result, 0.0f);
+            wf_push(mask, ST_PIXEL, lane, j);
+            return -2;
+        }
+    }
+    for (;;) {
+        const int k = team_take(t);
+        if (k >= 0) {
+            const uint32_t seed = lcg_skip(vol_ld(t.w + T_SEED * 32), 2u * (uint32_t)k);
+            P1[pid] = make_float4(__int_as_float(kTeamBit), __uint_as_float((uint32_t)k), __uint_as_float(seed), __uint_as_float(vol_ld(t.w + T_PIX * 32)));
+            CAND[pid] = 0u;
+            return k;
+        }
+        TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
+        P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
+        if (team_park(t, ctl, j)) return -1;
     }
 }
 
 // A slot that works alone on a pixel (`left` samples to go, pixel seed before the next sample's jitter draws) hands it to
 // the column's team.  False: a team is open already.  The claim is a CAS on T_TAKE itself (closed -> "being set up": no
 // samples, so nobody takes or commits anything) and never touches T_LOCK: whoever holds T_LOCK is a committer that
-// re-checks the frontier when it unlocks -- team_finish relies on that when it finds the lock taken.
-constexpr uint32_t kTeamSetup = 0x0000ffffu;
-__device__ __noinline__ bool team_create(const Team t, uint32_t left, uint32_t pixel_seed, uint32_t pix, uint32_t cand, float3 result,
-                                         uint32_t* mask, uint32_t* ctl, int lane)
+// re-checks the frontier when it unlocks -- team_commit relies on that when it finds the lock taken.
+__device__ __noinline__ bool team_create(const WfConst& wc, uint32_t* mask, uint32_t* ctl, int lane, uint32_t left, uint32_t pixel_seed,
+                                         uint32_t pix, uint32_t cand, float3 result)
 {
+    const Team t = team_view(wc, ctl, lane);
     if (vol_ld(t.w + T_TAKE * 32) != 0u || atomicCAS(t.w + T_TAKE * 32, 0u, kTeamSetup) != 0u) return false;
-    for (uint32_t i = 0; i <= t.wmask; i += 4) *reinterpret_cast<uint4*>(t.meta + i) = make_uint4(0u, 0u, 0u, 0u);   // marks of an earlier team
     volatile uint32_t* w = t.w;
     w[T_COMMIT * 32] = 0u;
     w[T_SEED * 32] = pixel_seed;
@@ -385,10 +441,247 @@ __device__ __noinline__ bool team_create(const Team t, uint32_t left, uint32_t p
     w[T_RX * 32] = __float_as_uint(result.x);
     w[T_RY * 32] = __float_as_uint(result.y);
     w[T_RZ * 32] = __float_as_uint(result.z);
-    __threadfence();                                      // the cleared marks (global) and the words above before the team opens
+    __threadfence_block();                                // the words above before the team opens
     w[T_TAKE * 32] = left << 16;
     team_wake(t, mask, ctl, lane);
     return true;
+}
+
+// MSORT: which SHADE queue a hit goes to -- the BSDF type of the primitive's material (the switch at :905-983)
+template <bool MSORT, class FETCH>
+__device__ __forceinline__ int shade_row_of(const FETCH& f, uint32_t prim)
+{
+    if (!MSORT) return ST_SHADE;
+    const int b = __float_as_int(f.mat(__float_as_int(f.tri_shade(prim).w), 1).w);
+    return b == 0 ? ST_SHADE : (b == 1 ? ST_SHADE1 : ST_SHADE2);
+}
+
+// ---- END stage, one slot: finish the segment (__miss__ms :833-847, shadow result, :760-778), Russian roulette, then the
+// next ray / the next sample / the finished pixel.  Two instantiations:
+//   TEAMSLOT = false  the slot works alone on its pixel (or the lane holds none: j < 0).  Inlined into the kernel -- this
+//                     is the hot path, and it contains nothing of the teams but one flag test and one shared-memory load;
+//   TEAMSLOT = true   the slot serves its column's team, or has no pixel and wants to (MODE_JOIN).  Out of line
+//                     (end_team_slot), so that its code stays out of the instruction cache while no team exists.
+// Returns the work counted (COUNT): misses | samples << 16 | radiance rays << 32 | triangle tests << 48.
+template <bool COUNT, bool PROBE, bool SHORT, bool MSORT, bool TEAM, bool TEAMSLOT, class FETCH>
+__device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, const WfConst& wc, float4* smem4, const FETCH& f, int lane, int j,
+                                                       bool have_tris)
+{
+    const uint32_t NP = wc.np;
+    uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);
+    uint32_t* ctl = mask + kQueues * 32;
+    float4* R0 = smem4 + kCtlF4;
+    float4* R1 = R0 + NP;
+    float4* R2 = R1 + NP;
+    float4* TS = R2 + NP;
+    float4* P0 = TS + NP;
+    float4* P1 = P0 + NP;
+    float4* RS = P1 + NP;
+    float4* S0 = RS + NP;
+    float4* S1 = S0 + NP;
+    uint32_t* CAND = reinterpret_cast<uint32_t*>(S1 + NP);
+    uint32_t c_miss = 0u, c_samples = 0u, c_radiance = 0u, c_tri = 0u;
+
+    const int pid = (j >= 0 ? j : 0) * 32 + lane;
+    Path p;
+    p.o = p.d = f3(0.0f);
+    p.att = f3(1.0f);
+    p.seed = 0u;
+    p.depth = 0;
+    // left: samples this slot still owes its pixel -- or, for a slot that serves its column's team, the sample index
+    uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
+    float3 result = f3(0.0f);
+    bool alive = j >= 0, need_sample = false;
+    if (j >= 0) {
+        const float4 ts = TS[pid];
+        const int mode = __float_as_int(ts.w) >> 8;
+        const float4 p1 = P1[pid];
+        left = __float_as_uint(p1.y);
+        pixel_seed = __float_as_uint(p1.z);
+        const uint32_t pix = __float_as_uint(p1.w);
+        ix = pix & 0xffffu;
+        iy = pix >> 16;
+        int ended = -2;                              // team slots: -1 = take a sample, k >= 0 = sample k has just ended
+        uint32_t n_terms = 0u;
+        if (!TEAMSLOT && mode == MODE_NEWPIX) {
+            need_sample = true;                      // first sample of a new pixel; result starts at 0
+        } else if (TEAMSLOT && mode == MODE_JOIN) {
+            if (TEAM && wc.team != 0) {
+                ended = -1;                          // a slot without a pixel: take a sample of the column's team below
+            } else {
+                atomicSub(ctl, 1u);                  // parked for the rest of the launch
+                alive = false;
+            }
+        } else {
+            const float4 p0 = P0[pid], rs = RS[pid];
+            p.att = xyz(p0);
+            p.seed = __float_as_uint(p0.w);
+            const int dw = __float_as_int(p1.x);
+            p.depth = dw & 0xff;
+            bool done = ((dw >> 8) & 1) != 0;
+            result = xyz(rs);
+            float3 rad;
+            if (mode == MODE_RAD) {                  // miss
+                if (PROBE && left == lc.spp && p.depth == 0) {
+                    const uint32_t image_index = iy * lc.width + ix;
+                    if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
+                    if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = 0.0f;
+                }
+                rad = lc.background;
+                done = true;
+                result = result + f3(0.0f);                                            // emissionColor = 0, :760
+                if (COUNT) c_miss++;
+            } else {
+                const float4 s0 = S0[pid], s1 = S1[pid];
+                p.o = xyz(s0);
+                p.d = xyz(s1);
+                rad = f3(0.0f);
+                if (done) rad = xyz(f.mat((int)((uint32_t)dw >> 16), 1));               // emissive hit, :992-996
+                if (mode == MODE_SHADOW && __float_as_uint(ts.y) == kNoPrim)
+                    rad = rad + f3(s0.w, s1.w, rs.w);                                  // unoccluded, :1019-1024
+            }
+            const float3 term = rad * p.att;
+            if (TEAMSLOT) {                                                            // :761, into the sample's log
+                n_terms = CAND[pid];
+                if (term.x != 0.0f || term.y != 0.0f || term.z != 0.0f) team_log(wc, ctl, lane, left, n_terms++, term);
+            } else {
+                result = result + term;                                                // :761
+            }
+            const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                      // :763
+            const bool rr = rnd(p.seed) > pr;                                          // :765
+            if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                     // :767
+                if (TEAMSLOT) {
+                    ended = (int)left;               // the team's sample `left` has ended (published below)
+                } else if (--left == 0u) {           // pixel finished: the PIXEL stage writes it
+                    P0[pid] = pack(p.att, __uint_as_float(p.seed));
+                    P1[pid] = make_float4(p1.x, __uint_as_float(0u), p1.z, p1.w);
+                    RS[pid] = pack(result, 0.0f);
+                    wf_push(mask, ST_PIXEL, lane, j);
+                    alive = false;
+                } else {
+                    need_sample = true;
+                    // slots of this column are parked and the pixel has samples to spare: hand it to the column's team and
+                    // come back as one of its members (MODE_JOIN)
+                    if (TEAM && wc.team != 0 && __builtin_expect(vol_ld(ctl + 4 + lane) != 0u, 0) && left >= (uint32_t)wc.team_min &&
+                        left < 0xffffu && (!SHORT || CAND[pid] != kCandNone) &&
+                        team_create(wc, mask, ctl, lane, left, pixel_seed, pix, SHORT ? CAND[pid] : kCandOverflow, result)) {
+                        P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
+                        TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
+                        wf_push(mask, ST_END, lane, j);
+                        alive = need_sample = false;
+                    }
+                }
+            } else {
+                if (TEAMSLOT) CAND[pid] = n_terms;
+                p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
+                ++p.depth;
+            }
+        }
+        if (TEAMSLOT && ended >= -1) {
+            // between two samples of the column's team: publish the one that ended, commit, take the next one
+            if (team_next(wc, smem4, lane, j, ended, n_terms) >= 0) {
+                const float4 q1 = P1[pid];           // (team bit, sample, pixel seed before its jitter draws, pixel)
+                left = __float_as_uint(q1.y);
+                pixel_seed = __float_as_uint(q1.z);
+                ix = __float_as_uint(q1.w) & 0xffffu;
+                iy = __float_as_uint(q1.w) >> 16;
+                result = f3(0.0f);
+                need_sample = true;
+            } else {
+                need_sample = alive = false;         // parked (a waker pushes the slot back to END), or gone to PIXEL with a finished pixel
+            }
+        }
+    }
+    // "continue the path" and "next sample" took different branches above; reconverge before the part they share
+    // (set up the next ray), or it runs once per branch at half occupancy.  (Lanes with a team slot check in before they
+    // leave for end_team_slot.)
+    if (!TEAMSLOT) __syncwarp();
+    if (alive) {
+        uint32_t cand = kCandOverflow;
+        if (need_sample) {
+            if (SHORT) cand = TEAMSLOT ? vol_ld(ctl + 4 + 32 + T_CAND * 32 + lane) : CAND[pid];
+            // The next sample's camera ray, in place.  SHORT: when no triangle can be reached from this pixel (empty
+            // candidate list) every camera ray is a miss; up to wc.miss_loop samples are then finished right here, each
+            // exactly as the miss branch above does (:833-847, :760-772): background times attenuation 1, the
+            // Russian-roulette draw, next sample.  Background tiles are handed out together (tile order), so the lanes
+            // of a batch take this loop together.  (One copy of the ray generation for both uses: instruction cache.)
+            for (int rep = 0;; ++rep) {
+                generate_camera_ray(lc, ix, iy, pixel_seed, p);
+                if (COUNT) c_samples++;
+                if (PROBE && left == lc.spp) {
+                    const uint32_t image_index = iy * lc.width + ix;
+                    if (lc.dbg_seed_after_jitter) lc.dbg_seed_after_jitter[image_index] = pixel_seed;
+                    if (lc.dbg_primary_dir) {
+                        lc.dbg_primary_dir[3 * image_index + 0] = p.d.x;
+                        lc.dbg_primary_dir[3 * image_index + 1] = p.d.y;
+                        lc.dbg_primary_dir[3 * image_index + 2] = p.d.z;
+                    }
+                }
+                if (!(SHORT && !TEAMSLOT && cand == kCandNone && rep < wc.miss_loop && left > 1u)) break;
+                if (PROBE && left == lc.spp) {
+                    const uint32_t image_index = iy * lc.width + ix;
+                    if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
+                    if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = 0.0f;
+                }
+                result = result + f3(0.0f);                                            // :760
+                result = result + lc.background * p.att;                               // :761
+                (void)rnd(p.seed);                                                     // :765 (done anyway)
+                --left;
+                if (COUNT) c_miss++, c_radiance++;
+            }
+        }
+        if (COUNT) c_radiance++;
+        P0[pid] = pack(p.att, __uint_as_float(p.seed));
+        P1[pid] = make_float4(__int_as_float(p.depth | (TEAMSLOT ? kTeamBit : 0)), __uint_as_float(left), __uint_as_float(pixel_seed),
+                              __uint_as_float(ix | (iy << 16)));
+        RS[pid] = pack(result, 0.0f);
+        if (SHORT && cand != kCandOverflow) {
+            // camera ray of a pixel with a candidate list: closest hit among <= 4 triangles, no traversal.  The
+            // list holds every triangle any camera ray of the pixel can reach (pixel_candidates), and the
+            // closest hit under (t, primIdx) does not depend on the order of the tests => same (t, prim).
+            Ray r;
+            r.o = p.o;
+            r.d = p.d;
+            r.inv = r.ood = f3(0.0f);
+            float best_t = 1e16f;                                                      // tmax :755
+            uint32_t best_prim = kNoPrim;
+            for (uint32_t c = cand; (c & 0xffu) != 0xffu; c = (c >> 8) | 0xff000000u) {
+                const int leaf = (int)(c & 0xffu);
+                const float4 t0 = f.tri(leaf, 0), t1 = f.tri(leaf, 1), t2 = f.tri(leaf, 2);
+                float th;
+                if (COUNT) c_tri++;
+                if (ray_tri(r, xyz(t0), xyz(t1), xyz(t2), 0.01f, 1e16f, th)) {         // tmin :754
+                    const uint32_t prim = __float_as_uint(t0.w);
+                    if (th < best_t || (th == best_t && prim < best_prim)) {
+                        best_t = th;
+                        best_prim = prim;
+                    }
+                }
+            }
+            R0[pid] = pack(r.o, 0.0f);
+            R1[pid] = pack(r.d, 0.0f);
+            TS[pid] = make_float4(best_t, __uint_as_float(best_prim), __int_as_float(kTravDone), __int_as_float(MODE_RAD << 8));
+            wf_push(mask, best_prim != kNoPrim ? shade_row_of<MSORT>(f, best_prim) : ST_END, lane, j);
+        } else {
+            const Ray r = make_ray(p.o, p.d);                                          // traceRadiance :577-635
+            R0[pid] = pack(r.o, 0.0f);
+            R1[pid] = pack(r.d, 0.0f);
+            R2[pid] = pack(r.inv, 0.0f);
+            TS[pid] = make_float4(1e16f, __uint_as_float(kNoPrim), __int_as_float(have_tris ? 0 : kTravDone),
+                                  __int_as_float(MODE_RAD << 8));                      // tmax :755
+            wf_push(mask, have_tris ? ST_NODE : ST_END, lane, j);
+        }
+    }
+    return COUNT ? ((unsigned long long)c_miss | ((unsigned long long)c_samples << 16) | ((unsigned long long)c_radiance << 32) |
+                    ((unsigned long long)c_tri << 48))
+                 : 0ull;
+}
+
+template <bool COUNT, bool PROBE, bool SHORT, bool MSORT, class FETCH>
+__device__ __noinline__ unsigned long long end_team_slot(const LaunchConst& lc, const WfConst& wc, float4* smem4, const FETCH f, int lane, int j,
+                                                         bool have_tris)
+{
+    return end_slot<COUNT, PROBE, SHORT, MSORT, true, true>(lc, wc, smem4, f, lane, j, have_tris);
 }
 
 // TRAV (scenes in global memory only; TRAV_DIRECT elsewhere): how NODE batches read the tree.
@@ -399,7 +692,7 @@ __device__ __noinline__ bool team_create(const Team t, uint32_t left, uint32_t p
 // profiles/r1_c3_c4_traversal_variants.txt -- and were removed.)
 enum : int { TRAV_DIRECT = 0, TRAV_QUANT = 1 };
 
-template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV, bool MSORT>
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV, bool MSORT, bool TEAM>
 __global__ void __launch_bounds__(kWfBlock, 1)
 render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_constant__ WfConst wc)
 {
@@ -408,15 +701,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     const uint32_t NP = wc.np;
     uint32_t* mask = reinterpret_cast<uint32_t*>(smem4);            // [7][32]
     uint32_t* ctl = mask + kQueues * 32;                            // [0] slots that are not parked  [1] error flag
-    constexpr bool TEAM = !PROBE;                                   // the probes record per-pixel sequential state
-    Team tm;
-    tm.idle = ctl + 4 + lane;
-    tm.w = ctl + 4 + 32 + lane;
-    tm.wmask = wc.team_wmask;
-    tm.cap = wc.team_cap;
-    tm.meta = wc.team_meta + ((size_t)blockIdx.x * 32 + lane) * (wc.team_wmask + 1u);
-    tm.log = wc.team_log + ((size_t)blockIdx.x * 32 + lane) * (wc.team_wmask + 1u) * wc.team_cap;
-    const bool use_teams = TEAM && wc.team != 0;
+    static_assert(!(TEAM && PROBE), "the probes record per-pixel sequential state");
     float4* R0 = smem4 + kCtlF4;        // (ray origin, -)
     float4* R1 = R0 + NP;               // (ray direction, -)
     float4* R2 = R1 + NP;               // (1 / direction, -)
@@ -477,12 +762,6 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
     uint32_t st_batches[4] = {0, 0, 0, 0}, st_lanes[4] = {0, 0, 0, 0}, st_steps = 0, st_step_lanes = 0, st_idle = 0;
     uint32_t it = 0, idle_polls = 0;
     int stage = -1, sticky = 0, row = 0;     // row: the queue the stage pops from (its own; SHADE has three when MSORT)
-    // MSORT: which SHADE queue a hit goes to -- the BSDF type of the primitive's material (the switch at :905-983)
-    auto shade_row_of = [&](uint32_t prim) -> int {
-        if (!MSORT) return ST_SHADE;
-        const int b = __float_as_int(f.mat(__float_as_int(f.tri_shade(prim).w), 1).w);
-        return b == 0 ? ST_SHADE : (b == 1 ? ST_SHADE1 : ST_SHADE2);
-    };
 
     for (;;) {
         // ---- vote ---------------------------------------------------------------------------------------------------
@@ -492,7 +771,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         uint32_t msnap = 0u, msnap2 = 0u;
         bool decided = false;
         if (stage >= 0 && stage != ST_TAIL && sticky < wc.sticky) {
-            msnap = vol_ld(mask + row * 32 + lane);
+            msnap = vol_ld(mask + (MSORT ? row : stage) * 32 + lane);
             if (__all_sync(kFull, msnap != 0u)) {
                 ++sticky;
                 decided = true;
@@ -610,7 +889,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
             if (active) {
                 TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(kTravDone), __int_as_float(t.sp | (mode << 8)));
-                wf_push(mask, (mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of(t.prim) : ST_END, lane, j);
+                wf_push(mask, (mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of<MSORT>(f, t.prim) : ST_END, lane, j);
             }
             stage = -1;
         } else if (stage == ST_NODE) {
@@ -659,7 +938,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(t.cur), __int_as_float(t.sp | (mode << 8)));
                 const int next = t.cur >= 0 ? ST_NODE
                                             : (t.cur != kTravDone ? ST_LEAF
-                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of(t.prim) : ST_END));
+                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of<MSORT>(f, t.prim) : ST_END));
                 wf_push(mask, next, lane, j);
             }
         } else if (stage == ST_LEAF) {
@@ -684,12 +963,12 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 TS[pid] = make_float4(t.tfar, __uint_as_float(t.prim), __int_as_float(t.cur), __int_as_float(t.sp | (mode << 8)));
                 const int next = t.cur >= 0 ? ST_NODE
                                             : (t.cur != kTravDone ? ST_LEAF
-                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of(t.prim) : ST_END));
+                                                                  : ((mode == MODE_RAD && t.prim != kNoPrim) ? shade_row_of<MSORT>(f, t.prim) : ST_END));
                 wf_push(mask, next, lane, j);
             }
         } else if (stage == ST_SHADE) {
             // ---- SHADE: __closesthit__diffuse__ch :866-1031 up to the occlusion trace -------------------------------
-            const int j = wf_pop_converged(mask + row * 32 + lane, msnap, rot);
+            const int j = wf_pop_converged(mask + (MSORT ? row : (int)ST_SHADE) * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_SHADE]++, st_lanes[ST_SHADE] += __popc(__ballot_sync(kFull, j >= 0));
             if (j >= 0) {
                 const int pid = j * 32 + lane;
@@ -715,10 +994,12 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 bool done;
                 shade_hit(lc, f, l_area, prim, t_hit, p, emission, rad, done, sq, hit_type, mat_id);
                 float3 result = xyz(rs);
-                if (TEAM && team_bit) {                                                         // :760, into the sample's log
-                    uint32_t n_terms = CAND[pid];
-                    team_log_term(tm, __float_as_uint(p1.y), n_terms, emission);
-                    CAND[pid] = n_terms;
+                if (TEAM && __builtin_expect(team_bit != 0, 0)) {                               // :760, into the sample's log
+                    if (emission.x != 0.0f || emission.y != 0.0f || emission.z != 0.0f) {
+                        const uint32_t n_terms = CAND[pid];
+                        team_log(wc, ctl, lane, __float_as_uint(p1.y), n_terms, emission);
+                        CAND[pid] = n_terms + 1u;
+                    }
                 } else {
                     result = result + emission;                                                 // :760
                 }
@@ -773,223 +1054,36 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                                           __uint_as_float(ix | (iy << 16)));
                     TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_NEWPIX << 8));
                     wf_push(mask, ST_END, lane, j);
-                } else {
+                } else if (TEAM) {
                     // no pixel left: serve the column's team, or park (END, MODE_JOIN)
                     P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
                     TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
                     wf_push(mask, ST_END, lane, j);
+                } else {
+                    atomicSub(ctl, 1u);                       // this slot is done for the launch
                 }
             }
         } else {
-            // ---- END: finish the segment (__miss__ms :833-847, shadow result, :760-778) and start the next ray --------
+            // ---- END: finish the segment, Russian roulette, next ray / sample / pixel (end_slot above) ------------------
             const int j = wf_pop_converged(mask + ST_END * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_END]++, st_lanes[ST_END] += __popc(__ballot_sync(kFull, j >= 0));
-            const int pid = (j >= 0 ? j : 0) * 32 + lane;
-            Path p;
-            p.o = p.d = f3(0.0f);
-            p.att = f3(1.0f);
-            p.seed = 0u;
-            p.depth = 0;
-            // left: samples this slot still owes its pixel -- or, for a slot that serves its column's team, the sample index
-            uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
-            float3 result = f3(0.0f);
-            bool alive = j >= 0, need_sample = false, team = false;
-            if (j >= 0) {
-                const float4 ts = TS[pid];
-                const int mode = __float_as_int(ts.w) >> 8;
-                const float4 p1 = P1[pid];
-                left = __float_as_uint(p1.y);
-                pixel_seed = __float_as_uint(p1.z);
-                const uint32_t pix = __float_as_uint(p1.w);
-                ix = pix & 0xffffu;
-                iy = pix >> 16;
-                team = TEAM && (__float_as_int(p1.x) & kTeamBit) != 0;
-                if (mode == MODE_NEWPIX) {
-                    need_sample = true;                      // first sample of a new pixel; result starts at 0
-                } else if (mode == MODE_JOIN) {
-                    if (use_teams) {
-                        team = need_sample = true;           // a slot without a pixel: take a sample of the column's team below
-                    } else {
-                        atomicSub(ctl, 1u);                  // parked for the rest of the launch
-                        alive = false;
-                    }
-                } else {
-                    const float4 p0 = P0[pid], rs = RS[pid];
-                    p.att = xyz(p0);
-                    p.seed = __float_as_uint(p0.w);
-                    const int dw = __float_as_int(p1.x);
-                    p.depth = dw & 0xff;
-                    bool done = ((dw >> 8) & 1) != 0;
-                    result = xyz(rs);
-                    float3 rad;
-                    if (mode == MODE_RAD) {                  // miss
-                        if (PROBE && left == lc.spp && p.depth == 0) {
-                            const uint32_t image_index = iy * lc.width + ix;
-                            if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
-                            if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = 0.0f;
-                        }
-                        rad = lc.background;
-                        done = true;
-                        result = result + f3(0.0f);                                            // emissionColor = 0, :760
-                        if (COUNT) ctr.n_miss++;
-                    } else {
-                        const float4 s0 = S0[pid], s1 = S1[pid];
-                        p.o = xyz(s0);
-                        p.d = xyz(s1);
-                        rad = f3(0.0f);
-                        if (done) rad = xyz(f.mat((int)((uint32_t)dw >> 16), 1));               // emissive hit, :992-996
-                        if (mode == MODE_SHADOW && __float_as_uint(ts.y) == kNoPrim)
-                            rad = rad + f3(s0.w, s1.w, rs.w);                                  // unoccluded, :1019-1024
-                    }
-                    uint32_t n_terms = 0u;
-                    if (TEAM && team) {                                                        // :761, into the sample's log
-                        n_terms = CAND[pid];
-                        team_log_term(tm, left, n_terms, rad * p.att);
-                    } else {
-                        result = result + rad * p.att;                                         // :761
-                    }
-                    const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                      // :763
-                    const bool rr = rnd(p.seed) > pr;                                          // :765
-                    if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                     // :767
-                        if (TEAM && team) {
-                            // the team's sample `left` has ended: publish it; whoever holds the lock commits in sample order
-                            uint32_t done_pix = 0u;
-                            if (team_finish(tm, left, n_terms, result, done_pix, mask, ctl, lane)) {
-                                // ... and this slot committed a pixel's last sample: it carries that pixel to the PIXEL stage
-                                P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                                P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(done_pix));
-                                RS[pid] = pack(result, 0.0f);
-                                wf_push(mask, ST_PIXEL, lane, j);
-                                alive = false;
-                            } else {
-                                need_sample = true;
-                            }
-                        } else if (--left == 0u) {           // pixel finished: the PIXEL stage writes it
-                            P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                            P1[pid] = make_float4(p1.x, __uint_as_float(0u), p1.z, p1.w);
-                            RS[pid] = pack(result, 0.0f);
-                            wf_push(mask, ST_PIXEL, lane, j);
-                            alive = false;
-                        } else {
-                            need_sample = true;
-                            // slots of this column are parked and the pixel has samples to spare: hand it to the column's team
-                            // (and go on as one of its members)
-                            if (use_teams && left >= (uint32_t)wc.team_min && left < 0xffffu && vol_ld(tm.idle) != 0u &&
-                                (!SHORT || CAND[pid] != kCandNone))
-                                team = team_create(tm, left, pixel_seed, pix, SHORT ? CAND[pid] : kCandOverflow, result, mask, ctl, lane);
-                        }
-                    } else {
-                        if (TEAM && team) CAND[pid] = n_terms;
-                        p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
-                        ++p.depth;
-                    }
-                }
-                if (TEAM && need_sample && team) {
-                    // next sample of the column's team: its pixel seed is the team's base seed 2k draws on
-                    int k;
-                    for (;;) {
-                        k = team_take(tm);
-                        if (k >= 0) break;
-                        TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
-                        P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
-                        if (team_park(tm, ctl, j)) break;
-                    }
-                    if (k < 0) {
-                        alive = need_sample = false;         // parked: a waker pushes the slot back to END
-                    } else {
-                        left = (uint32_t)k;
-                        const uint32_t tpix = vol_ld(tm.w + T_PIX * 32);
-                        ix = tpix & 0xffffu;
-                        iy = tpix >> 16;
-                        pixel_seed = lcg_skip(vol_ld(tm.w + T_SEED * 32), 2u * (uint32_t)k);
-                        result = f3(0.0f);
-                    }
-                }
-                if (need_sample) {
-                    generate_camera_ray(lc, ix, iy, pixel_seed, p);                            // next sample, in place
-                    if (COUNT) ctr.n_samples++;
-                    if (PROBE && left == lc.spp) {
-                        const uint32_t image_index = iy * lc.width + ix;
-                        if (lc.dbg_seed_after_jitter) lc.dbg_seed_after_jitter[image_index] = pixel_seed;
-                        if (lc.dbg_primary_dir) {
-                            lc.dbg_primary_dir[3 * image_index + 0] = p.d.x;
-                            lc.dbg_primary_dir[3 * image_index + 1] = p.d.y;
-                            lc.dbg_primary_dir[3 * image_index + 2] = p.d.z;
-                        }
-                    }
-                }
+            bool team_slot = false;
+            if (TEAM && j >= 0) {
+                const int pid = j * 32 + lane;
+                team_slot = (__float_as_int(TS[pid].w) >> 8) == MODE_JOIN || (__float_as_int(P1[pid].x) & kTeamBit) != 0;
             }
-            // "continue the path" and "next sample" took different branches above; reconverge before the part they share
-            // (set up the next ray), or it runs once per branch at half occupancy
-            __syncwarp();
-            if (alive) {
-                if (COUNT) ctr.n_radiance++;
-                P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                P1[pid] = make_float4(__int_as_float(p.depth | ((TEAM && team) ? kTeamBit : 0)), __uint_as_float(left), __uint_as_float(pixel_seed),
-                                      __uint_as_float(ix | (iy << 16)));
-                RS[pid] = pack(result, 0.0f);
-                uint32_t cand = kCandOverflow;
-                if (SHORT && need_sample) cand = (TEAM && team) ? vol_ld(tm.w + T_CAND * 32) : CAND[pid];
-                if (TEAM && team && need_sample) CAND[pid] = 0u;                               // terms logged for this sample so far
-                if (SHORT && cand == kCandNone) {
-                    // No triangle can be reached from this pixel: every camera ray is a miss.  Finish up to
-                    // wc.miss_loop samples right here, each exactly as the miss branch above does (:833-847, :760-772):
-                    // background times attenuation 1, the Russian-roulette draw, next sample.  Background tiles are
-                    // handed out together (tile order), so the lanes of a batch take this loop together.
-                    for (int rep = 0; rep < wc.miss_loop && left > 1u; ++rep) {
-                        if (PROBE && left == lc.spp) {
-                            const uint32_t image_index = iy * lc.width + ix;
-                            if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
-                            if (lc.dbg_primary_t) lc.dbg_primary_t[image_index] = 0.0f;
-                        }
-                        result = result + f3(0.0f);                                            // :760
-                        result = result + lc.background * p.att;                               // :761
-                        (void)rnd(p.seed);                                                     // :765 (done anyway)
-                        --left;
-                        generate_camera_ray(lc, ix, iy, pixel_seed, p);
-                        if (COUNT) ctr.n_miss++, ctr.n_samples++, ctr.n_radiance++;
-                    }
-                    P0[pid] = pack(p.att, __uint_as_float(p.seed));
-                    P1[pid] = make_float4(__int_as_float(p.depth), __uint_as_float(left), __uint_as_float(pixel_seed),
-                                          __uint_as_float(ix | (iy << 16)));
-                    RS[pid] = pack(result, 0.0f);
-                }
-                if (SHORT && cand != kCandOverflow) {
-                    // camera ray of a pixel with a candidate list: closest hit among <= 4 triangles, no traversal.  The
-                    // list holds every triangle any camera ray of the pixel can reach (pixel_candidates), and the
-                    // closest hit under (t, primIdx) does not depend on the order of the tests => same (t, prim).
-                    Ray r;
-                    r.o = p.o;
-                    r.d = p.d;
-                    r.inv = r.ood = f3(0.0f);
-                    float best_t = 1e16f;                                                      // tmax :755
-                    uint32_t best_prim = kNoPrim;
-                    for (uint32_t c = cand; (c & 0xffu) != 0xffu; c = (c >> 8) | 0xff000000u) {
-                        const int leaf = (int)(c & 0xffu);
-                        const float4 t0 = f.tri(leaf, 0), t1 = f.tri(leaf, 1), t2 = f.tri(leaf, 2);
-                        float th;
-                        if (COUNT) ctr.n_tri++;
-                        if (ray_tri(r, xyz(t0), xyz(t1), xyz(t2), 0.01f, 1e16f, th)) {         // tmin :754
-                            const uint32_t prim = __float_as_uint(t0.w);
-                            if (th < best_t || (th == best_t && prim < best_prim)) {
-                                best_t = th;
-                                best_prim = prim;
-                            }
-                        }
-                    }
-                    R0[pid] = pack(r.o, 0.0f);
-                    R1[pid] = pack(r.d, 0.0f);
-                    TS[pid] = make_float4(best_t, __uint_as_float(best_prim), __int_as_float(kTravDone), __int_as_float(MODE_RAD << 8));
-                    wf_push(mask, best_prim != kNoPrim ? shade_row_of(best_prim) : ST_END, lane, j);
-                } else {
-                    const Ray r = make_ray(p.o, p.d);                                          // traceRadiance :577-635
-                    R0[pid] = pack(r.o, 0.0f);
-                    R1[pid] = pack(r.d, 0.0f);
-                    R2[pid] = pack(r.inv, 0.0f);
-                    TS[pid] = make_float4(1e16f, __uint_as_float(kNoPrim), __int_as_float(have_tris ? 0 : kTravDone),
-                                          __int_as_float(MODE_RAD << 8));                      // tmax :755
-                    wf_push(mask, have_tris ? ST_NODE : ST_END, lane, j);
-                }
+            unsigned long long counted;
+            if (TEAM && __builtin_expect(team_slot, 0)) {
+                __syncwarp();                                // the other lanes' reconvergence point inside end_slot
+                counted = end_team_slot<COUNT, PROBE, SHORT, MSORT>(lc, wc, smem4, f, lane, j, have_tris);
+            } else {
+                counted = end_slot<COUNT, PROBE, SHORT, MSORT, TEAM, false>(lc, wc, smem4, f, lane, j, have_tris);
+            }
+            if (COUNT) {
+                ctr.n_miss += (uint32_t)(counted & 0xffffu);
+                ctr.n_samples += (uint32_t)((counted >> 16) & 0xffffu);
+                ctr.n_radiance += (uint32_t)((counted >> 32) & 0xffffu);
+                ctr.n_tri += (uint32_t)(counted >> 48);
             }
         }
     }
@@ -1015,27 +1109,27 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         }
     }
     // a team that is still open when every slot has parked would be a lost pixel: never expected, reported like the watchdog
-    if (use_teams && warp == 0 && vol_ld(tm.w + T_TAKE * 32) != 0u) {
-        ctl[1] = 1u;
-        if (team_debug_dump(wc)) {
-            const uint32_t tk = vol_ld(tm.w + T_TAKE * 32), cm = vol_ld(tm.w + T_COMMIT * 32);
-            atomicAdd(lc.error_flag + 12, 1ull);
-            lc.error_flag[13] = tk;
-            lc.error_flag[14] = cm;
-            unsigned long long marks = 0;
-            for (uint32_t k2 = 0; k2 < 32u && k2 < (tk >> 16); ++k2)
-                if ((ld_acquire(tm.meta + (k2 & tm.wmask)) >> 9) == k2 + 1u) marks |= 1ull << k2;
-            lc.error_flag[15] = marks | ((unsigned long long)vol_ld(tm.w + T_LOCK * 32) << 40) | ((unsigned long long)vol_ld(tm.idle) << 44 >> 44 << 48);
+    // (tune "team=2" also leaves its words in d_counters[27..30], pt_scene_get_sched_stats 11..14)
+    if (TEAM && wc.team != 0 && warp == 0) {
+        const Team t = team_view(wc, ctl, lane);
+        if (vol_ld(t.w + T_TAKE * 32) != 0u) {
+            ctl[1] = 1u;
+            if (wc.team > 1) {
+                atomicAdd(lc.error_flag + 12, 1ull);
+                lc.error_flag[13] = vol_ld(t.w + T_TAKE * 32);
+                lc.error_flag[14] = vol_ld(t.w + T_COMMIT * 32);
+                lc.error_flag[15] = vol_ld(t.w + T_DONE * 32) | ((unsigned long long)vol_ld(t.w + T_LOCK * 32) << 32) | ((unsigned long long)vol_ld(t.idle) << 33);
+            }
         }
     }
     __syncwarp();
     if (threadIdx.x == 0 && vol_ld(ctl + 1)) atomicAdd(lc.error_flag, 1ull);   // watchdog fired
 }
 
-template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV, bool MSORT = false>
+template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV, bool MSORT = false, bool TEAM = false>
 cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc, size_t smem_bytes, cudaStream_t stream)
 {
-    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE, SHORT, TRAV, MSORT>;
+    auto kernel = render_wavefront_kernel<COUNT, PROBE, SCENE, SHORT, TRAV, MSORT, TEAM>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 0;
@@ -1143,7 +1237,7 @@ static WfTune tuned(const WfTune& base)
     clamp(t.full_cols_g, 1, 32);
     clamp(t.sticky, 0, 64);
     clamp(t.tail_cols, 0, 160);
-    clamp(t.miss_loop, 0, 1 << 20);
+    clamp(t.miss_loop, 0, 4096);
     clamp(t.idle_ns, 0, 1 << 16);
     clamp(t.idle_shift, 0, 10);
     return t;
@@ -1236,34 +1330,37 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
         }
         wc.stack_over = s.d_stack_over;
     }
-    // sample teams: the term log, sized for every SM
+    const bool count = s.count_enabled;
+    const int scene = smem_scene ? (int)wc.copies_shift : -1;
+    // Sample teams (tune "team": 0 off, 1 auto, 2 on, 3 on + debug dump).  Auto = scenes read from global memory: there a
+    // launch is latency-bound, pixels differ widely in cost and the teams are worth +28 % (C3); a scene staged in shared
+    // memory runs at its instruction-fetch limit and the kernel WITHOUT the team code is the faster one on full frames
+    // (C2: the hot code exceeds the 32 KB L1.5 instruction cache either way; measurements in DESIGN.md 4.2b).
+    const bool team_on = !probe && (tune.team >= 2 || (tune.team == 1 && scene < 0));
     wc.team = 0;
     wc.team_min = tune.team_min < 1 ? 1 : tune.team_min;
-    wc.team_cap = lc.max_depth + 2u;                     // emission + one term per segment (maxDepth + 1 segments)
+    wc.team_cap = lc.max_depth + 3u;                     // emission + one term per segment (maxDepth + 1 segments) + terminator
     wc.team_wmask = (wc.team_cap <= 32u ? 128u : (wc.team_cap <= 64u ? 64u : (wc.team_cap <= 128u ? 32u : 16u))) - 1u;
-    if (tune.team != 0 && !probe) {
+    if (team_on) {
+        // the term log, sized for every SM
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const size_t per_column = (size_t)(wc.team_wmask + 1u) * (wc.team_cap * sizeof(float4) + sizeof(uint32_t));
+        const size_t per_column = (size_t)(wc.team_wmask + 1u) * wc.team_cap * sizeof(float4);
         const size_t need = (size_t)sms * 32u * per_column;
         if (s.team_log_bytes < need) {
             if (s.d_team_log) cudaFree(s.d_team_log);
             s.d_team_log = nullptr;
             s.team_log_bytes = 0;
-            if (cudaMalloc((void**)&s.d_team_log, need) == cudaSuccess) {
-                s.team_log_bytes = need;
-            }
+            if (cudaMalloc((void**)&s.d_team_log, need) == cudaSuccess) s.team_log_bytes = need;
             else cudaGetLastError();                     // no memory for the log: this launch runs without teams
         }
         if (s.team_log_bytes >= need) {
-            wc.team = tune.team;
+            wc.team = tune.team == 3 ? 2 : 1;
             wc.team_log = reinterpret_cast<float4*>(s.d_team_log);
-            wc.team_meta = reinterpret_cast<uint32_t*>(wc.team_log + (size_t)sms * 32u * (wc.team_wmask + 1u) * wc.team_cap);
         }
     }
-    const bool count = s.count_enabled;
-    const int scene = smem_scene ? (int)wc.copies_shift : -1;
+    const bool team = wc.team != 0;
     // Per-pixel candidate lists for camera rays: only where building one (a loop over all triangles per pixel) is
     // cheap, i.e. tiny scenes staged with 8 copies.  The counted kernel always traverses, so that its node / triangle
     // counters stay the ones of the specified traversal (and equal to the oracle's).
@@ -1279,23 +1376,34 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
             lq.q_step = make_float3(s.q_step[0], s.q_step[1], s.q_step[2]);
             s.last_trav = 1;
             if (probe) return launch_wavefront<false, true, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
-            if (count) return launch_wavefront<true, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
-            return launch_wavefront<false, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
+            if (count)
+                return team ? launch_wavefront<true, false, -1, false, TRAV_QUANT, false, true>(s, lq, wc, smem_bytes, stream)
+                            : launch_wavefront<true, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
+            return team ? launch_wavefront<false, false, -1, false, TRAV_QUANT, false, true>(s, lq, wc, smem_bytes, stream)
+                        : launch_wavefront<false, false, -1, false, TRAV_QUANT>(s, lq, wc, smem_bytes, stream);
         }
         trav = TRAV_DIRECT;                              // a box could not be contained (never expected): exact nodes
     }
     // material-sorted SHADE batches (pt_scene_set_tune "msort=1"; A/B in profiles/): scenes with more than one BSDF type
     if (tune.msort != 0 && s.n_bsdf_types > 1 && !probe && !count && !use_short) {
-        if (scene == 0) return launch_wavefront<false, false, 0, false, TRAV_DIRECT, true>(s, lc, wc, smem_bytes, stream);
-        if (scene < 0) return launch_wavefront<false, false, -1, false, TRAV_DIRECT, true>(s, lc, wc, smem_bytes, stream);
+        if (scene == 0)
+            return team ? launch_wavefront<false, false, 0, false, TRAV_DIRECT, true, true>(s, lc, wc, smem_bytes, stream)
+                        : launch_wavefront<false, false, 0, false, TRAV_DIRECT, true, false>(s, lc, wc, smem_bytes, stream);
+        if (scene < 0)
+            return team ? launch_wavefront<false, false, -1, false, TRAV_DIRECT, true, true>(s, lc, wc, smem_bytes, stream)
+                        : launch_wavefront<false, false, -1, false, TRAV_DIRECT, true, false>(s, lc, wc, smem_bytes, stream);
     }
-#define PTB_WF_DISPATCH(COUNT, PROBE, SHORT)                                                      \
-    (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream)   \
-     : scene == 0 ? launch_wavefront<COUNT, PROBE, 0, false, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream)   \
-                  : launch_wavefront<COUNT, PROBE, -1, false, TRAV_DIRECT>(s, lc, wc, smem_bytes, stream))
-    if (probe) return use_short ? PTB_WF_DISPATCH(false, true, true) : PTB_WF_DISPATCH(false, true, false);
-    if (count) return (use_short && s.count_executed) ? PTB_WF_DISPATCH(true, false, true) : PTB_WF_DISPATCH(true, false, false);
-    return use_short ? PTB_WF_DISPATCH(false, false, true) : PTB_WF_DISPATCH(false, false, false);
+#define PTB_WF_DISPATCH(COUNT, PROBE, SHORT, TEAM)                                                                    \
+    (scene == 3   ? launch_wavefront<COUNT, PROBE, 3, SHORT, TRAV_DIRECT, false, TEAM>(s, lc, wc, smem_bytes, stream)   \
+     : scene == 0 ? launch_wavefront<COUNT, PROBE, 0, false, TRAV_DIRECT, false, TEAM>(s, lc, wc, smem_bytes, stream)   \
+                  : launch_wavefront<COUNT, PROBE, -1, false, TRAV_DIRECT, false, TEAM>(s, lc, wc, smem_bytes, stream))
+    if (probe) return use_short ? PTB_WF_DISPATCH(false, true, true, false) : PTB_WF_DISPATCH(false, true, false, false);
+    if (count) {
+        if (use_short && s.count_executed) return team ? PTB_WF_DISPATCH(true, false, true, true) : PTB_WF_DISPATCH(true, false, true, false);
+        return team ? PTB_WF_DISPATCH(true, false, false, true) : PTB_WF_DISPATCH(true, false, false, false);
+    }
+    if (use_short) return team ? PTB_WF_DISPATCH(false, false, true, true) : PTB_WF_DISPATCH(false, false, true, false);
+    return team ? PTB_WF_DISPATCH(false, false, false, true) : PTB_WF_DISPATCH(false, false, false, false);
 #undef PTB_WF_DISPATCH
 }
 

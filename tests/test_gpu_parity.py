@@ -895,15 +895,16 @@ def test_quantised_nodes_contain_the_exact_boxes(api, port, scenes_cache, name):
 # ---- sample teams (wavefront.cu "Sample teams"): several slots work on one pixel, ordered commit ------------------------------
 TEAM_CASES = [
     # scene, w, h, spp, maxDepth, tune -- few pixels and many samples: almost every sample is rendered by a team
-    ("cornell", 40, 24, 64, 16, ""),
-    ("cornell", 9, 5, 200, 16, ""),                    # fewer pixels than columns
-    ("material", 48, 27, 48, 28, ""),                  # long refractive / conductor paths: the commit frontier lags
-    ("material", 48, 27, 48, 28, "team_min=40"),       # pixels switch late or not at all
-    ("tess40", 32, 18, 32, 8, ""),                     # scene in global memory
-    ("cornell", 24, 16, 96, 200, ""),                  # deep logs: 202 entries per sample, a window of 16 samples (parking)
-    ("cornell", 40, 24, 64, 16, "paths32=4,block=128"),
+    ("cornell", 40, 24, 64, 16, "team=2"),             # (team=2: also for scenes staged in shared memory, where auto leaves it off)
+    ("cornell", 9, 5, 200, 16, "team=2"),              # fewer pixels than columns
+    ("material", 48, 27, 48, 28, "team=2"),            # long refractive / conductor paths: the commit frontier lags
+    ("material", 48, 27, 48, 28, "team=2,team_min=40"),  # pixels switch late or not at all
+    ("tess40", 32, 18, 32, 8, ""),                     # scene in global memory: teams by default
+    ("cornell", 24, 16, 96, 200, "team=2"),            # deep logs: 203 entries per sample, a window of 16 samples (parking)
+    ("cornell", 40, 24, 64, 16, "team=2,paths32=4,block=128"),
     ("cornell", 40, 24, 64, 16, "team=0"),             # the sequential chain, for reference
-    ("material", 64, 36, 24, 28, "msort=1"),           # SHADE batches sorted by BSDF type (three queues)
+    ("material", 64, 36, 24, 28, "team=2,msort=1"),    # SHADE batches sorted by BSDF type (three queues)
+    ("material", 64, 36, 24, 28, "team=0,msort=1"),
 ]
 
 
@@ -941,6 +942,7 @@ def test_small_share_of_a_frame_uses_every_sm(api, port, scenes_cache):
     w, h = 256, 144
     acc, fb = _dev_buffers(w, h)
     p = api.make_params(w, h, 128, 16, frame=0, nee=True, importance=True, scene=gs)
+    gs.set_tune("team=2")
     _launch_dev(api, gs, p, acc, fb, rank=3, n=8)
     grid_team = gs.last_launch_info()["grid"]
     got = acc.cpu().numpy().copy()
@@ -978,7 +980,7 @@ def test_schedule_perturbation(api, port, scenes_cache):
             spec = dict(block=block, paths32=paths32, node_votes=int(rng.integers(1, 9)), node_keep8=int(rng.integers(0, 9)),
                         full_cols=int(rng.integers(1, 33)), sticky=int(rng.integers(0, 9)), tail_cols=int(rng.choice([0, 8, 24, 64, 160])),
                         idle_ns=int(rng.choice([0, 16, 64, 512])), idle_shift=int(rng.integers(0, 6)), stack_smem=int(rng.choice([0, 2, 5, 12])),
-                        team=int(rng.choice([0, 1, 1])), team_min=int(rng.choice([1, 2, 8, 20])), msort=int(rng.choice([0, 1])))
+                        team=int(rng.choice([0, 1, 2, 2])), team_min=int(rng.choice([1, 2, 8, 20])), msort=int(rng.choice([0, 1])))
             tune = ",".join(f"{k}={v}" for k, v in spec.items())
             tried.append(tune)
             gs.set_tune(tune)
@@ -1008,6 +1010,7 @@ def test_soak_200_launches_no_watchdog(api, port, scenes_cache):
     w, h = 64, 36
     acc, fb = _dev_buffers(w, h)
     p = api.make_params(w, h, 48, 16, frame=0, nee=True, importance=True, scene=gs)
+    gs.set_tune("team=2")
     _launch_dev(api, gs, p, acc, fb)
     first = acc.clone()
     o = osc.render(p, math_mode=1, use_bvh=True)
@@ -1018,6 +1021,7 @@ def test_soak_200_launches_no_watchdog(api, port, scenes_cache):
         _launch_dev(api, gs, p, acc, fb)
         assert torch.equal(acc.view(torch.int32), first.view(torch.int32)), i
     gs.check_error()
+    gs.set_tune("")
 
 
 # ---- launches the wavefront record cannot hold fall back to pipeline 1 ----------------------------------------
