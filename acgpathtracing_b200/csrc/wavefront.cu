@@ -329,6 +329,16 @@ __device__ __forceinline__ bool team_commit(const Team& t, float3& result, uint3
         // load of another location on both sides.  Without a sequentially consistent fence between them both can read the old
         // value -- the holder leaves, this slot gives up, and if it was the team's last sample nobody ever commits it.
         __threadfence_block();
+        // The log of the sample at the frontier is read BEFORE the lock is taken (it cannot change any more once its bit
+        // is set): the global-memory latency stays out of the critical section, which is what bounds a team's commit rate.
+        const uint32_t cmg = vol_ld(t.w + T_COMMIT * 32), slotg = cmg & t.wmask;
+        const bool ahead = (vol_ld(t.w + (T_DONE + (slotg >> 5)) * 32) & (1u << (slotg & 31u))) != 0u;
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+        if (ahead) {
+            __threadfence_block();                                         // acquire: the log of a sample whose bit is set
+            const float4* src = t.log + (size_t)slotg * t.cap;
+            g0 = src[0], g1 = src[1], g2 = src[2];
+        }
         if (atomicCAS(t.w + T_LOCK * 32, 0u, 1u) != 0u) return false;      // the holder re-checks the frontier after unlocking
         __threadfence_block();
         const uint32_t n = vol_ld(t.w + T_TAKE * 32) >> 16;
@@ -346,9 +356,10 @@ __device__ __forceinline__ bool team_commit(const Team& t, float3& result, uint3
             __threadfence_block();                                         // acquire: the log of a sample whose bit is set
             atomicAnd(dw, ~bit);                                           // the window slot is free again once T_COMMIT has passed it
             const float4* src = t.log + (size_t)slot * t.cap;
-            float4 e0 = __ldcg(src), e1 = __ldcg(src + 1), e2 = __ldcg(src + 2);   // most samples have at most two terms
+            const bool pre = ahead && cm == cmg;                           // the team (and its frontier) is the one looked at above
+            const float4 e0 = pre ? g0 : src[0], e1 = pre ? g1 : src[1], e2 = pre ? g2 : src[2];   // most samples have at most two terms
             for (uint32_t i = 0;; ++i) {
-                const float4 v = i == 0 ? e0 : (i == 1 ? e1 : (i == 2 ? e2 : __ldcg(src + i)));
+                const float4 v = i == 0 ? e0 : (i == 1 ? e1 : (i == 2 ? e2 : src[i]));
                 if (v.w != 0.0f) break;                                    // the terminator
                 r = r + f3(v.x, v.y, v.z);                                 // :760-761, in sample order, term by term
             }
@@ -398,8 +409,8 @@ __device__ __noinline__ int team_next(const WfConst& wc, float4* smem4, int lane
     const Team t = team_view(wc, ctl, lane);
     if (ended >= 0) {
         const uint32_t slot = (uint32_t)ended & t.wmask;
-        __stcg(t.log + (size_t)slot * t.cap + n_terms, make_float4(0.0f, 0.0f, 0.0f, kLogEnd));
-        __threadfence();                                                   // release: the log (global memory) before the bit
+        t.log[(size_t)slot * t.cap + n_terms] = make_float4(0.0f, 0.0f, 0.0f, kLogEnd);
+        __threadfence_block();                                             // release: the log before the bit (every reader is in this CTA)
         atomicOr(t.w + (T_DONE + (slot >> 5)) * 32, 1u << (slot & 31u));
         float3 result;
         uint32_t pix;
