@@ -86,6 +86,8 @@ def _load():
         "pt_obj_copy": (i32, [vp, vp, vp, vp, vp]),
         "pt_scene_create_from_obj": (i32, [vp, C.POINTER(vp)]),
         "pt_image_write_ppm": (i32, [C.c_char_p, vp, u32, u32]),
+        "pt_image_write_png": (i32, [C.c_char_p, vp, u32, u32]),
+        "pt_image_write": (i32, [C.c_char_p, vp, u32, u32]),
         "pt_accum_save": (i32, [C.c_char_p, vp, u32, u32, u32]),
         "pt_accum_load": (i32, [C.c_char_p, vp, u32, u32, C.POINTER(u32)]),
         "pt_device_info": (i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.c_char_p]),

@@ -196,7 +196,7 @@ int main(int argc, char** argv)
             printf("Throughput: %.1f Mpixel-samples/s\n", (double)px * (double)sample_sum / (total_ms * 1e-3) / 1e6);
 
         cuda_check(cudaMemcpy(h_frame.data(), d_frame, px * 4, cudaMemcpyDeviceToHost), "download frame");
-        check(pt_image_write_ppm(out_path.c_str(), h_frame.data(), width, height));
+        check(pt_image_write(out_path.c_str(), h_frame.data(), width, height));            // sutil::saveImage: .ppm or .png
         printf("Wrote %s\n", out_path.c_str());
         if (!accum_out.empty()) {
             cuda_check(cudaMemcpy(h_accum.data(), d_accum, px * 16, cudaMemcpyDeviceToHost), "download accumulation");

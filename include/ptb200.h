@@ -276,6 +276,11 @@ int pt_scene_create_from_obj(const pt_obj* obj, pt_scene** out);
 /* sutil::saveImage for a UNSIGNED_BYTE4 buffer and a ".ppm" file name (sutil/sutil.cpp:543-570): binary P6 with
  * the vertical flip (row 0 of frameBuffer is the bottom of the picture), alpha dropped.  Host pointer. */
 int pt_image_write_ppm(const char* path, const void* frame_rgba8_host, uint32_t width, uint32_t height);
+/* The ".png" branch of sutil::saveImage (sutil/sutil.cpp:622-638: stbi_write_png, 4 components, flipped vertically): 8-bit
+ * RGBA, same flip.  (Stored deflate blocks: the file is a valid PNG of the same pixels, not the same bytes as stb's.) */
+int pt_image_write_png(const char* path, const void* frame_rgba8_host, uint32_t width, uint32_t height);
+/* saveImage's own dispatch on the last three characters of the name ("ppm" / "png", either case; sutil.cpp:548-549, :622) */
+int pt_image_write(const char* path, const void* frame_rgba8_host, uint32_t width, uint32_t height);
 /* The running average + the next currentFrameIdx are the renderer's whole resumable state
  * (pathTracerPrograms.cu:803-811).  Host pointers; pt_accum_load checks the size. */
 int pt_accum_save(const char* path, const void* accum_float4_host, uint32_t width, uint32_t height, uint32_t next_frame_idx);

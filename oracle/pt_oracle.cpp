@@ -259,6 +259,11 @@ struct OrScene {
     // 1: jitter y takes the first draw (what g++ makes of pathTracerPrograms.cu:730 in the host build of
     //    the reference); used only to compare this port with oracle/_ref bit for bit.
     int jitter_order = 0;
+    // optional [w*h] output: per pixel a hash of every discrete decision of the launch's paths -- the primitive each segment
+    // hit (or the miss), the dielectric's reflect / refract / total-internal-reflection branch, whether a shadow ray was cast
+    // and what it found, and how the segment ended (done / Russian roulette / depth).  Two renders whose arithmetic differs in
+    // the last place (deterministic vs glibc transcendentals) agree to ~1e-6 on a pixel exactly when these hashes agree.
+    uint32_t* decision_probe = nullptr;
     Lbvh bvh;
 };
 
@@ -268,7 +273,11 @@ struct PathState {   // RadiancePayloadRayData, pathTracer.h:19-32
     int depth;
     V3 emissionColor, radiance, origin, direction;
     int done;
+    uint32_t decisions;   // test aid: hash of the discrete decisions the path took (see OrScene::decision_probe)
 };
+
+// FNV-1a step: the hash of a pixel's decisions only has to tell "same sequence" from "different sequence"
+static inline void decide(PathState& prd, uint32_t what) { prd.decisions = (prd.decisions ^ what) * 16777619u; }
 
 template <bool USE_BVH>
 static inline Hit trace_closest(const OrScene& sc, V3 o, V3 d, float tmin, float tmax, TraceCounters* tc)
@@ -354,10 +363,12 @@ static inline void closesthit_program(const OrScene& sc, const OrParams& params,
             float F = FrDielectric(cos_theta, 1.0f, IOR);
             if (rnd(seed) < F) {
                 prd.direction = reflect(incidentRayDir, N_0);
+                decide(prd, 0x101u);
             } else {
                 V3 refractedDir;
                 bool didRefract = refract(refractedDir, incidentRayDir, N_0, IOR);
                 prd.direction = didRefract ? refractedDir : reflect(incidentRayDir, N_0);
+                decide(prd, didRefract ? 0x102u : 0x103u);
             }
             prd.origin = P + prd.direction * 1e-3f;
             prd.attenuation *= matDiffuse;
@@ -393,6 +404,7 @@ static inline void closesthit_program(const OrScene& sc, const OrParams& params,
             ctr.n_shadow++;
             // traceOcclusion :651-684 reduces to "anything hit" 
             const bool occluded = trace_any<USE_BVH>(sc, P, L, 0.01f, Ldist - 0.01f, tc);
+            decide(prd, occluded ? 0x201u : 0x202u);
             if (!occluded) {
                 const float A = length(cross(lv1, lv2));
                 float weight = nDl * LnDl * A / (kPi * Ldist * Ldist);        // :1022
@@ -469,6 +481,7 @@ static void raygen_pixel(const OrScene& sc, const OrParams& params, uint32_t ix,
                 first = false;
             }
             first = false;
+            decide(prd, hit.hit ? hit.prim : 0xffffffffu);
             if (hit.hit) {
                 closesthit_program<M, USE_BVH>(sc, params, hit.prim, hit.t, ray_origin, ray_direction, prd, ctr, tc);
             } else {
@@ -480,6 +493,7 @@ static void raygen_pixel(const OrScene& sc, const OrParams& params, uint32_t ix,
             const float p = dot(prd.attenuation, v3(0.30f, 0.59f, 0.11f));     // :763
             bool russianRoulette = rnd(prd.randomSeed) > p;                    // :765
             const bool done = prd.done || russianRoulette || (unsigned int)prd.depth >= maxDepth;   // :767
+            decide(prd, 0x300u | (prd.done ? 1u : 0u) | (russianRoulette ? 2u : 0u) | ((unsigned int)prd.depth >= maxDepth ? 4u : 0u));
             if (done) break;
             prd.attenuation = safeDivide(prd.attenuation, p);                  // :773
             ray_origin = prd.origin;
@@ -500,6 +514,7 @@ static void raygen_pixel(const OrScene& sc, const OrParams& params, uint32_t ix,
     accum[4 * (size_t)image_index + 2] = accum_color.z;
     accum[4 * (size_t)image_index + 3] = 1.0f;
     if (fb) make_color<M>(accum_color, fb + 4 * (size_t)image_index);        // :814
+    if (sc.decision_probe) sc.decision_probe[image_index] = prd.decisions;
     if (probe) {
         if (probe->final_path_seed) probe->final_path_seed[image_index] = prd.randomSeed;
         if (probe->final_pixel_seed) probe->final_pixel_seed[image_index] = seed;
@@ -661,6 +676,7 @@ void ptor_scene_set_background(void* s, float r, float g, float b)
 }
 
 void ptor_scene_set_jitter_order(void* s, int order) { ((OrScene*)s)->jitter_order = order; }
+void ptor_scene_set_decision_probe(void* s, uint32_t* buf) { ((OrScene*)s)->decision_probe = buf; }
 
 // which tree the traversals walk: 0 auto (the library's rule), 1 LBVH, 2 SAH, 3 PLOC; returns the tree in use
 int ptor_scene_set_tree(void* s, int tree) { return select_tree(((OrScene*)s)->bvh, tree); }

@@ -67,6 +67,7 @@ def load_port():
                                 C.POINTER(Counters), _vp, _vp, _vp, _vp, _vp, _vp,
                                 C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.ptor_hardware_threads.restype = C.c_int
+    lib.ptor_scene_set_decision_probe.argtypes = [_vp, _vp]
     return lib
 
 
@@ -165,9 +166,12 @@ class OracleScene:
         return prim, t, anyh, ctr
 
     def render(self, params: PathTraceParams, accum=None, math_mode=1, use_bvh=True, nthreads=0, probes=False,
-               region=None, want_fb=True):
-        """One launch.  Returns dict(accum (h,w,4) f32, fb (h,w,4) u8, counters, probes...)."""
+               region=None, want_fb=True, decisions=False):
+        """One launch.  Returns dict(accum (h,w,4) f32, fb (h,w,4) u8, counters, probes...); decisions=True adds
+        "decisions": (h,w) u32, a hash of every discrete decision the pixel's paths took (pt_oracle.cpp decision_probe)."""
         w, h = params.width, params.height
+        dec = np.zeros((h, w), np.uint32) if decisions else None
+        self.lib.ptor_scene_set_decision_probe(self.h, _ptr(dec))
         if accum is None:
             accum = np.zeros((h, w, 4), np.float32)
         accum = np.ascontiguousarray(accum, np.float32)
@@ -185,8 +189,11 @@ class OracleScene:
                                   C.byref(ctr), _ptr(pr.get("prim")), _ptr(pr.get("t")),
                                   _ptr(pr.get("seed_after_jitter")), _ptr(pr.get("final_path_seed")),
                                   _ptr(pr.get("final_pixel_seed")), _ptr(pr.get("primary_dir")), x0, x1, y0, y1)
+        self.lib.ptor_scene_set_decision_probe(self.h, None)
         if rc != 0:
             raise RuntimeError(f"ptor_render failed: {rc}")
+        if decisions:
+            pr["decisions"] = dec
         return dict(accum=accum, fb=fb, counters=ctr.asdict(), **pr)
 
 

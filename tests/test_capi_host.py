@@ -263,6 +263,30 @@ def test_ppm_writer_flips_rows_and_drops_alpha(api, tmp_path):
         api._check(api.lib.pt_image_write_ppm(path.encode(), None, w, h))
 
 
+def test_png_writer_and_extension_dispatch(api, tmp_path):
+    """The ".png" branch of sutil::saveImage (sutil/sutil.cpp:622-638): RGBA, flipped vertically; decoded here with PIL.  Sizes
+    include one whose raw data spans several 65535-byte stored blocks."""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    for w, h in ((5, 3), (1, 1), (301, 257)):
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)             # row 0 = bottom of the picture
+        path = str(tmp_path / f"a{w}.png")
+        api._check(api.lib.pt_image_write_png(path.encode(), img.ctypes.data, w, h))
+        got = Image.open(path)
+        assert got.mode == "RGBA" and got.size == (w, h)
+        assert np.array_equal(np.asarray(got), img[::-1])
+        via = str(tmp_path / f"b{w}.PNG")
+        api._check(api.lib.pt_image_write(via.encode(), img.ctypes.data, w, h))
+        assert open(via, "rb").read() == open(path, "rb").read()
+    ppm = str(tmp_path / "c.ppm")
+    api._check(api.lib.pt_image_write(ppm.encode(), img.ctypes.data, w, h))
+    assert open(ppm, "rb").read().startswith(b"P6")
+    for bad in ("x.jpg", "a.exr", "noextension"):
+        with pytest.raises(api.PtError) as e:
+            api._check(api.lib.pt_image_write(str(tmp_path / bad).encode(), img.ctypes.data, w, h))
+        assert e.value.code == api.PT_ERR_INVALID
+
+
 def test_accumulation_checkpoint_round_trip(api, tmp_path):
     w, h = 7, 4
     acc = np.random.default_rng(3).random((h, w, 4)).astype(np.float32)

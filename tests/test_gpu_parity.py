@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 RADIANCE_RTOL = 0.0          # vs the oracle's det-math mode: bit-exact
 LIBM_RTOL = 1e-4             # vs the oracle's glibc mode (reference source semantics), per channel
-LIBM_OUTLIER_BUDGET = 2e-3   # fraction of pixels allowed outside LIBM_RTOL (a flipped discrete decision)
+LIBM_OUTLIER_BUDGET = 1e-4   # fraction of pixels allowed outside LIBM_RTOL (attributed pixel by pixel in tests/test_tolerance.py)
 
 
 @pytest.fixture(scope="module")
@@ -187,19 +187,24 @@ def test_uncounted_kernel_equals_counted(api, port, scenes_cache):
     assert np.array_equal(a["fb"], b["fb"])
 
 
-def test_radiance_vs_reference_libm_semantics(api, port, scenes_cache):
+@pytest.mark.parametrize("name,w,h,md,nee", [("cornell", 512, 512, 3, False), ("cornell", 960, 540, 16, True), ("material", 960, 540, 28, True)],
+                         ids=["c1", "c2-shape", "c3-shape"])
+def test_radiance_vs_reference_libm_semantics(api, port, scenes_cache, name, w, h, md, nee, capsys):
     """North-star tolerance: 1e-4 relative at 1 spp with identical seeds against the reference-source semantics
-    (glibc sinf/cosf/acosf/powf).  Pixels whose path took a different discrete decision (Russian roulette, Fresnel
-    branch, NEE visibility) because of a last-place difference are counted against a budget."""
-    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
-    p = api.make_params(512, 512, 1, 3, frame=0, nee=False, importance=True, scene=gs)
+    (glibc sinf/cosf/acosf/powf), on the shapes of configs 1-3.  The measured outlier fraction is printed and must stay within
+    the survey's budget of 1e-4 of the pixels; tests/test_tolerance.py attributes every outlier (a flipped Russian-roulette /
+    Fresnel / shadow decision, or an ill-conditioned grazing term) on the CPU, where both math modes are available."""
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    p = api.make_params(w, h, 1, md, frame=0, nee=nee, importance=True, scene=gs)
     g = gs.launch_host(p)
     o = osc.render(p, math_mode=0, use_bvh=True)
     ga, oa = g["accum"][..., :3], o["accum"][..., :3]
-    bad = np.abs(ga - oa) > LIBM_RTOL * np.maximum(np.abs(oa), 1e-3)
-    assert bad.any(axis=-1).mean() <= LIBM_OUTLIER_BUDGET
-    ok = ~bad.any(axis=-1)
-    assert np.abs(g["fb"].astype(int) - o["fb"].astype(int))[ok].max() <= 1      # framebuffer bytes: +-1 LSB
+    bad = (np.abs(ga - oa) > LIBM_RTOL * np.maximum(np.abs(oa), 1e-3)).any(axis=-1)
+    with capsys.disabled():
+        print(f"\n[tolerance, GPU vs reference semantics] {name} {w}x{h} depth {md}: {int(bad.sum())} of {bad.size} pixels outside "
+              f"{LIBM_RTOL:g} relative ({bad.mean():.2e}; budget {LIBM_OUTLIER_BUDGET:g})")
+    assert bad.mean() <= LIBM_OUTLIER_BUDGET
+    assert np.abs(g["fb"].astype(int) - o["fb"].astype(int))[~bad].max() <= 1      # framebuffer bytes: +-1 LSB
 
 
 # ---- edge cases ---------------------------------------------------------------------------------------------------------
@@ -532,14 +537,15 @@ def test_raw_means_plus_fold_equal_sequential_launches(api, port, scenes_cache, 
         api.fold_frames(acc3.data_ptr(), None, [means[0].data_ptr()] * 65, 0, w, h, stream)
 
 
-def test_converged_image_vs_reference_semantics(api, port, scenes_cache):
-    """North-star bound for converged images: 4096 spp (32 launches x 128 spp, running average), GPU (portable
+@pytest.mark.parametrize("name,md", [("cornell", 16), ("material", 28)], ids=["c2-shape", "c3-shape"])
+def test_converged_image_vs_reference_semantics(api, port, scenes_cache, name, md):
+    """North-star bound for converged images (config 3 is quoted at 4096 spp): 32 launches x 128 spp, running average, GPU (portable
     transcendentals) against the oracle in glibc mode = the reference source's semantics.  Individual paths may differ
     after a flipped discrete decision, the converged image may not: RMSE of linear radiance <= 1e-3 x mean luminance,
     frame buffers equal up to 1 LSB in at most 1 % of the bytes.  Against the oracle's own deterministic mode the image
     is bit-identical (checked on the first 4 launches to keep the CPU side short)."""
-    arr, gs, osc = _get(scenes_cache, api, port, "cornell")
-    w, h, spp, md, launches = 96, 54, 128, 16, 32
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    w, h, spp, launches = 96, 54, 128, 32
     acc_g = acc_l = acc_d = None
     for f in range(launches):
         p = api.make_params(w, h, spp, md, frame=f, nee=True, importance=True, scene=gs)
