@@ -469,12 +469,17 @@ __device__ __forceinline__ int shade_row_of(const FETCH& f, uint32_t prim)
 
 // ---- END stage, one slot: finish the segment (__miss__ms :833-847, shadow result, :760-778), Russian roulette, then the
 // next ray / the next sample / the finished pixel.  Two instantiations:
-//   TEAMSLOT = false  the slot works alone on its pixel (or the lane holds none: j < 0).  Inlined into the kernel -- this
-//                     is the hot path, and it contains nothing of the teams but one flag test and one shared-memory load;
-//   TEAMSLOT = true   the slot serves its column's team, or has no pixel and wants to (MODE_JOIN).  Out of line
-//                     (end_team_slot), so that its code stays out of the instruction cache while no team exists.
+//   ANY = false  every slot of the batch works alone on its pixel (or the lane holds none: j < 0).  Inlined into the kernel:
+//                the hot path, with nothing of the teams in it.  Used until the work counter runs dry -- no slot can be
+//                without a pixel before that, so no team can exist;
+//   ANY = true   from then on ("team phase", a flag of the CTA): slots that serve their column's team, slots that have no
+//                pixel and want to (MODE_JOIN) and slots still alone on a pixel, told apart per lane.  Out of line
+//                (end_any_slot) and used by WHOLE warps, so that exactly one copy of the END code is live in either phase:
+//                the first version sent only the team lanes of a batch out of line -- both copies were hot at once, the
+//                hot code no longer fitted the instruction caches, and a launch in its team phase stalled on instruction
+//                fetch 5.2 times per issued instruction (profiles/r2_icache_notes.txt).
 // Returns the work counted (COUNT): misses | samples << 16 | radiance rays << 32 | triangle tests << 48.
-template <bool COUNT, bool PROBE, bool SHORT, bool MSORT, bool TEAM, bool TEAMSLOT, class FETCH>
+template <bool COUNT, bool PROBE, bool SHORT, bool MSORT, bool TEAM, bool ANY, class FETCH>
 __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, const WfConst& wc, float4* smem4, const FETCH& f, int lane, int j,
                                                        bool have_tris)
 {
@@ -502,7 +507,7 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
     // left: samples this slot still owes its pixel -- or, for a slot that serves its column's team, the sample index
     uint32_t left = 0u, pixel_seed = 0u, ix = 0u, iy = 0u;
     float3 result = f3(0.0f);
-    bool alive = j >= 0, need_sample = false;
+    bool alive = j >= 0, need_sample = false, team = false;
     if (j >= 0) {
         const float4 ts = TS[pid];
         const int mode = __float_as_int(ts.w) >> 8;
@@ -514,15 +519,12 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
         iy = pix >> 16;
         int ended = -2;                              // team slots: -1 = take a sample, k >= 0 = sample k has just ended
         uint32_t n_terms = 0u;
-        if (!TEAMSLOT && mode == MODE_NEWPIX) {
+        team = ANY && (__float_as_int(p1.x) & kTeamBit) != 0;            // this slot runs sample `left` of its column's team
+        if (mode == MODE_NEWPIX) {
             need_sample = true;                      // first sample of a new pixel; result starts at 0
-        } else if (TEAMSLOT && mode == MODE_JOIN) {
-            if (TEAM && wc.team != 0) {
-                ended = -1;                          // a slot without a pixel: take a sample of the column's team below
-            } else {
-                atomicSub(ctl, 1u);                  // parked for the rest of the launch
-                alive = false;
-            }
+        } else if (ANY && mode == MODE_JOIN) {
+            team = true;                             // a slot without a pixel: take a sample of the column's team below
+            ended = -1;
         } else {
             const float4 p0 = P0[pid], rs = RS[pid];
             p.att = xyz(p0);
@@ -552,7 +554,7 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
                     rad = rad + f3(s0.w, s1.w, rs.w);                                  // unoccluded, :1019-1024
             }
             const float3 term = rad * p.att;
-            if (TEAMSLOT) {                                                            // :761, into the sample's log
+            if (ANY && team) {                                                         // :761, into the sample's log
                 n_terms = CAND[pid];
                 if (term.x != 0.0f || term.y != 0.0f || term.z != 0.0f) team_log(wc, ctl, lane, left, n_terms++, term);
             } else {
@@ -561,7 +563,7 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
             const float pr = dot(p.att, f3(0.30f, 0.59f, 0.11f));                      // :763
             const bool rr = rnd(p.seed) > pr;                                          // :765
             if (done || rr || (uint32_t)p.depth >= lc.max_depth) {                     // :767
-                if (TEAMSLOT) {
+                if (ANY && team) {
                     ended = (int)left;               // the team's sample `left` has ended (published below)
                 } else if (--left == 0u) {           // pixel finished: the PIXEL stage writes it
                     P0[pid] = pack(p.att, __uint_as_float(p.seed));
@@ -571,24 +573,22 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
                     alive = false;
                 } else {
                     need_sample = true;
-                    // slots of this column are parked and the pixel has samples to spare: hand it to the column's team and
-                    // come back as one of its members (MODE_JOIN)
-                    if (TEAM && wc.team != 0 && __builtin_expect(vol_ld(ctl + 4 + lane) != 0u, 0) && left >= (uint32_t)wc.team_min &&
-                        left < 0xffffu && (!SHORT || CAND[pid] != kCandNone) &&
+                    // slots of this column are parked and the pixel has samples to spare: hand it to the column's team and go
+                    // on as one of its members
+                    if (ANY && wc.team != 0 && vol_ld(ctl + 4 + lane) != 0u && left >= (uint32_t)wc.team_min && left < 0xffffu &&
+                        (!SHORT || CAND[pid] != kCandNone) &&
                         team_create(wc, mask, ctl, lane, left, pixel_seed, pix, SHORT ? CAND[pid] : kCandOverflow, result)) {
-                        P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
-                        TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
-                        wf_push(mask, ST_END, lane, j);
-                        alive = need_sample = false;
+                        team = true;
+                        ended = -1;
                     }
                 }
             } else {
-                if (TEAMSLOT) CAND[pid] = n_terms;
+                if (ANY && team) CAND[pid] = n_terms;
                 p.att = f3(safe_divide(p.att.x, pr), safe_divide(p.att.y, pr), safe_divide(p.att.z, pr));   // :773
                 ++p.depth;
             }
         }
-        if (TEAMSLOT && ended >= -1) {
+        if (ANY && team && ended >= -1) {
             // between two samples of the column's team: publish the one that ended, commit, take the next one
             if (team_next(wc, smem4, lane, j, ended, n_terms) >= 0) {
                 const float4 q1 = P1[pid];           // (team bit, sample, pixel seed before its jitter draws, pixel)
@@ -604,13 +604,12 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
         }
     }
     // "continue the path" and "next sample" took different branches above; reconverge before the part they share
-    // (set up the next ray), or it runs once per branch at half occupancy.  (Lanes with a team slot check in before they
-    // leave for end_team_slot.)
-    if (!TEAMSLOT) __syncwarp();
+    // (set up the next ray), or it runs once per branch at half occupancy
+    __syncwarp();
     if (alive) {
         uint32_t cand = kCandOverflow;
         if (need_sample) {
-            if (SHORT) cand = TEAMSLOT ? vol_ld(ctl + 4 + 32 + T_CAND * 32 + lane) : CAND[pid];
+            if (SHORT) cand = (ANY && team) ? vol_ld(ctl + 4 + 32 + T_CAND * 32 + lane) : CAND[pid];
             // The next sample's camera ray, in place.  SHORT: when no triangle can be reached from this pixel (empty
             // candidate list) every camera ray is a miss; up to wc.miss_loop samples are then finished right here, each
             // exactly as the miss branch above does (:833-847, :760-772): background times attenuation 1, the
@@ -628,7 +627,7 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
                         lc.dbg_primary_dir[3 * image_index + 2] = p.d.z;
                     }
                 }
-                if (!(SHORT && !TEAMSLOT && cand == kCandNone && rep < wc.miss_loop && left > 1u)) break;
+                if (!(SHORT && !(ANY && team) && cand == kCandNone && rep < wc.miss_loop && left > 1u)) break;
                 if (PROBE && left == lc.spp) {
                     const uint32_t image_index = iy * lc.width + ix;
                     if (lc.dbg_primary_prim) lc.dbg_primary_prim[image_index] = -1;
@@ -643,7 +642,7 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
         }
         if (COUNT) c_radiance++;
         P0[pid] = pack(p.att, __uint_as_float(p.seed));
-        P1[pid] = make_float4(__int_as_float(p.depth | (TEAMSLOT ? kTeamBit : 0)), __uint_as_float(left), __uint_as_float(pixel_seed),
+        P1[pid] = make_float4(__int_as_float(p.depth | ((ANY && team) ? kTeamBit : 0)), __uint_as_float(left), __uint_as_float(pixel_seed),
                               __uint_as_float(ix | (iy << 16)));
         RS[pid] = pack(result, 0.0f);
         if (SHORT && cand != kCandOverflow) {
@@ -689,8 +688,8 @@ __device__ __forceinline__ unsigned long long end_slot(const LaunchConst& lc, co
 }
 
 template <bool COUNT, bool PROBE, bool SHORT, bool MSORT, class FETCH>
-__device__ __noinline__ unsigned long long end_team_slot(const LaunchConst& lc, const WfConst& wc, float4* smem4, const FETCH f, int lane, int j,
-                                                         bool have_tris)
+__device__ __noinline__ unsigned long long end_any_slot(const LaunchConst& lc, const WfConst& wc, float4* smem4, const FETCH f, int lane, int j,
+                                                        bool have_tris)
 {
     return end_slot<COUNT, PROBE, SHORT, MSORT, true, true>(lc, wc, smem4, f, lane, j, have_tris);
 }
@@ -1066,7 +1065,8 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                     TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_NEWPIX << 8));
                     wf_push(mask, ST_END, lane, j);
                 } else if (TEAM) {
-                    // no pixel left: serve the column's team, or park (END, MODE_JOIN)
+                    // no pixel left: serve the column's team, or park (END, MODE_JOIN); the CTA is in its team phase from now on
+                    *reinterpret_cast<volatile uint32_t*>(ctl + 2) = 1u;
                     P1[pid] = make_float4(__int_as_float(0), __uint_as_float(0u), __uint_as_float(0u), __uint_as_float(0u));
                     TS[pid] = make_float4(0.0f, __uint_as_float(kNoPrim), __int_as_float(kTravDone), __int_as_float(MODE_JOIN << 8));
                     wf_push(mask, ST_END, lane, j);
@@ -1078,18 +1078,11 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             // ---- END: finish the segment, Russian roulette, next ray / sample / pixel (end_slot above) ------------------
             const int j = wf_pop_converged(mask + ST_END * 32 + lane, msnap, rot);
             if (COUNT) st_batches[ST_END]++, st_lanes[ST_END] += __popc(__ballot_sync(kFull, j >= 0));
-            bool team_slot = false;
-            if (TEAM && j >= 0) {
-                const int pid = j * 32 + lane;
-                team_slot = (__float_as_int(TS[pid].w) >> 8) == MODE_JOIN || (__float_as_int(P1[pid].x) & kTeamBit) != 0;
-            }
+            // once the work counter has run dry (ctl[2]) slots without a pixel and teams can exist: the whole warp takes the
+            // out-of-line END that knows about them (see end_slot)
             unsigned long long counted;
-            if (TEAM && __builtin_expect(team_slot, 0)) {
-                __syncwarp();                                // the other lanes' reconvergence point inside end_slot
-                counted = end_team_slot<COUNT, PROBE, SHORT, MSORT>(lc, wc, smem4, f, lane, j, have_tris);
-            } else {
-                counted = end_slot<COUNT, PROBE, SHORT, MSORT, TEAM, false>(lc, wc, smem4, f, lane, j, have_tris);
-            }
+            if (TEAM && __any_sync(kFull, vol_ld(ctl + 2) != 0u)) counted = end_any_slot<COUNT, PROBE, SHORT, MSORT>(lc, wc, smem4, f, lane, j, have_tris);
+            else counted = end_slot<COUNT, PROBE, SHORT, MSORT, TEAM, false>(lc, wc, smem4, f, lane, j, have_tris);
             if (COUNT) {
                 ctr.n_miss += (uint32_t)(counted & 0xffffu);
                 ctr.n_samples += (uint32_t)((counted >> 16) & 0xffffu);
