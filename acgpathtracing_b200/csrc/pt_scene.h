@@ -24,7 +24,8 @@ struct WfTune {
     int node_votes_g = 3;    // ... for scenes read from global memory: shorter batches regroup more often, which keeps more lanes
                              // (and more loads) in flight where a step is a cache miss (C4: 1396 -> 1519 with full_cols_g = 28)
     int node_keep8 = 2;      // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
-    int full_cols = 32;      // a downstream stage is taken as soon as this many columns have a waiting path
+    int full_cols = 30;      // a downstream stage is taken as soon as this many columns have a waiting path (32 before the
+                             // scheduler affinity of round 2)
     int full_cols_g = 28;    // ... for scenes read from global memory
     int sticky = 4;          // repeats of the same stage without a full vote while it fills the whole warp
     int tail_cols = 24;      // tail mode when the non-empty columns of all queues add up to at most this
@@ -43,6 +44,9 @@ struct WfTune {
     int team = 1;            // sample teams (idle path slots take samples of a pixel another slot of their column is working on):
                              // 0 off, 1 auto (scenes read from global memory), 2 on, 3 on + state dump when a team is left open
     int team_min = 2;        // ... when that pixel has at least this many samples left to hand out
+    int affinity = 2;        // schedulers (warp % 4 < affinity) whose warps look at the traversal queues first, the others at the
+                             // shading queues (instruction-cache locality per scheduler; C2 +5.7 % together with full_cols = 30)
+    int affinity_g = 3;      // ... for scenes read from global memory (C3 +7 %, C4 +2 %)
     int msort = 0;           // material-sorted SHADE: one queue per BSDF type (scenes with more than one type); measured, see DESIGN.md
 };
 
