@@ -72,6 +72,7 @@ def _load():
         "pt_bvh_export_sah": (i32, [vp, vp, C.POINTER(u32)]),
         "pt_bvh_export_ploc": (i32, [vp, vp, C.POINTER(u32), C.POINTER(C.c_float)]),
         "pt_bvh_export_quant": (i32, [vp, vp, vp, vp]),
+        "pt_bvh_export_wide": (i32, [vp, vp, u32, vp, vp, vp]),
         "pt_sah_build_host": (i32, [vp, vp, u32, vp, C.POINTER(u32)]),
         "pt_scene_last_traversal": (i32, [vp]),
         "pt_scene_last_launch_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
@@ -283,9 +284,17 @@ class Scene:
         _check(lib.pt_bvh_export_quant(self._h, _ptr(q), _ptr(lo), _ptr(step)))
         return dict(q=q, lo=lo, step=step)
 
+    def bvh_export_wide(self):
+        """4-wide quantised nodes of the tree in use: dict(w (n_wide, 16) u32, depth, build_ms)."""
+        n, depth, ms = C.c_uint32(0), C.c_uint32(0), C.c_float(0)
+        _check(lib.pt_bvh_export_wide(self._h, None, 0, C.byref(n), C.byref(depth), C.byref(ms)))
+        w = np.zeros((n.value, 16), np.uint32)
+        _check(lib.pt_bvh_export_wide(self._h, _ptr(w), n.value, C.byref(n), C.byref(depth), C.byref(ms)))
+        return dict(w=w, depth=depth.value, build_ms=ms.value)
+
     def set_traversal(self, traversal):
         """0 auto, 1 exact nodes (staged in shared memory when the scene fits), 2 exact nodes from global memory,
-        3 quantised nodes from global memory (pt_scene_set_traversal)."""
+        3 quantised nodes from global memory, 4 4-wide quantised nodes from global memory (pt_scene_set_traversal)."""
         _check(lib.pt_scene_set_traversal(self._h, traversal))
 
     def set_tune(self, spec=""):
@@ -299,7 +308,7 @@ class Scene:
         g, b, s, k = (C.c_uint32() for _ in range(4))
         _check(lib.pt_scene_last_launch_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(k)))
         return dict(grid=g.value, block=b.value, smem_bytes=s.value, kernels=k.value,
-                    traversal={0: "binary", 1: "binary-quant"}.get(lib.pt_scene_last_traversal(self._h), "?"))
+                    traversal={0: "binary", 1: "binary-quant", 2: "wide4-quant"}.get(lib.pt_scene_last_traversal(self._h), "?"))
 
     def bvh_export(self):
         info = self.info()

@@ -74,7 +74,7 @@ static void scene_free(Scene* s)
     void* ptrs[] = {s->d_verts, s->d_indices, s->d_mat_ids, s->d_mats, s->d_tri_in, s->d_tri_bb, s->d_tri_shade,
                     s->d_bounds_ordered, s->d_bounds, s->d_morton, s->d_keys[0], s->d_keys[1], s->d_vals[0], s->d_vals[1],
                     s->d_block_hist, s->d_scan_scratch, s->d_left, s->d_right, s->d_node_parent, s->d_leaf_parent, s->d_visit, s->d_node_lo,
-                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_qnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
+                    s->d_node_hi, s->d_nodes, s->d_nodes_sah, s->d_nodes_ploc, s->d_tris, s->d_qnodes, s->d_wnodes, s->d_work_counter, s->d_counters, s->d_stage_accum, s->d_stage_frame,
                     s->d_stack_over, s->d_team_log};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -487,7 +487,7 @@ int pt_scene_set_traversal(pt_scene* scene, int traversal)
 {
     Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
     if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
-    if (traversal < 0 || traversal > 3) return fail(PT_ERR_INVALID, "traversal must be 0 .. 3");
+    if (traversal < 0 || traversal > 4) return fail(PT_ERR_INVALID, "traversal must be 0 .. 4");
     s->traversal = traversal;
     return PT_OK;
 }
@@ -552,6 +552,24 @@ int pt_bvh_export_quant(pt_scene* scene, void* qnodes32, float* lo3, float* step
         if (step3) step3[a] = s->q_step[a];
     }
     if (qnodes32) PT_CUDA(cudaMemcpy(qnodes32, s->d_qnodes, 32 * (size_t)s->n_nodes, cudaMemcpyDeviceToHost));
+    return PT_OK;
+}
+
+int pt_bvh_export_wide(pt_scene* scene, void* wnodes64, uint32_t capacity, uint32_t* n_wide, uint32_t* depth, float* build_ms)
+{
+    Scene* s = scene_from_handle((uint64_t)(uintptr_t)scene);
+    if (!s) return fail(PT_ERR_INVALID, "not a live pt_scene");
+    if (s->n_tris < 2) return fail(PT_ERR_INVALID, "no wide nodes for a scene of fewer than 2 triangles");
+    DeviceGuard g(s->device);
+    PT_CUDA(build_wide_nodes(*s, 0));
+    if (!s->d_wnodes || s->wnodes_tree != scene_tree(*s)) return fail(PT_ERR_CUDA, "the wide nodes could not be built");
+    if (n_wide) *n_wide = s->n_wnodes;
+    if (depth) *depth = s->wide_depth;
+    if (build_ms) *build_ms = s->wide_ms;
+    if (wnodes64) {
+        if (capacity < s->n_wnodes) return fail(PT_ERR_INVALID, "pt_bvh_export_wide: capacity too small");
+        PT_CUDA(cudaMemcpy(wnodes64, s->d_wnodes, 64 * (size_t)s->n_wnodes, cudaMemcpyDeviceToHost));
+    }
     return PT_OK;
 }
 

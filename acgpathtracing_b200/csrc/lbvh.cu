@@ -16,6 +16,10 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <chrono>
+#include <vector>
+
 #include "pt_device.cuh"
 #include "pt_scene.h"
 
@@ -588,20 +592,31 @@ __global__ void __launch_bounds__(256) ploc_emit_kernel(const int* __restrict__ 
 // pt_device.cuh FetchGlobal::qnode4).  lo planes are rounded down, hi planes up, and the rounding is CHECKED with the very
 // expression the traversal evaluates (one fused multiply-add), so a quantised box always contains the exact one: the
 // traversal reaches a superset of the leaves and the hits -- which come from the exact triangle records -- cannot change.
-__device__ __forceinline__ uint32_t quant_down(float x, float lo, float step)
+// plane q of the grid: (2^23 + q) * step + base in one fused multiply-add -- the traversal's expression (pt_device.cuh qnode4)
+__host__ __device__ __forceinline__ float quant_plane(uint32_t q, float base, float step)
 {
-    float t = floorf((x - lo) / step);
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(__uint_as_float(0x4b000000u | q), step, base);
+#else
+    return fmaf(8388608.0f + (float)q, step, base);
+#endif
+}
+__device__ __forceinline__ uint32_t quant_down(float x, float base, float step)
+{
+    float t = floorf((x - quant_plane(0u, base, step)) / step);
     t = fminf(fmaxf(t, 0.0f), 65535.0f);
     uint32_t q = (uint32_t)t;
-    while (q > 0u && __fmaf_rn((float)q, step, lo) > x) --q;
+    while (q > 0u && quant_plane(q, base, step) > x) --q;
+    while (q < 65535u && quant_plane(q + 1u, base, step) <= x) ++q;
     return q;
 }
-__device__ __forceinline__ uint32_t quant_up(float x, float lo, float step)
+__device__ __forceinline__ uint32_t quant_up(float x, float base, float step)
 {
-    float t = ceilf((x - lo) / step);
+    float t = ceilf((x - quant_plane(0u, base, step)) / step);
     t = fminf(fmaxf(t, 0.0f), 65535.0f);
     uint32_t q = (uint32_t)t;
-    while (q < 65535u && __fmaf_rn((float)q, step, lo) < x) ++q;
+    while (q < 65535u && quant_plane(q, base, step) < x) ++q;
+    while (q > 0u && quant_plane(q - 1u, base, step) >= x) --q;
     return q;
 }
 
@@ -616,12 +631,10 @@ __global__ void __launch_bounds__(256) quantize_nodes_kernel(int n_internal, con
     const uint32_t l1x = quant_down(q2.x, lo.x, step.x), l1y = quant_down(q2.y, lo.y, step.y), l1z = quant_down(q2.z, lo.z, step.z);
     const uint32_t h1x = quant_up(q3.x, lo.x, step.x), h1y = quant_up(q3.y, lo.y, step.y), h1z = quant_up(q3.z, lo.z, step.z);
     // the guarantee, re-checked: quantised lo <= exact lo and quantised hi >= exact hi on every plane
-    const bool ok = __fmaf_rn((float)l0x, step.x, lo.x) <= q0.x && __fmaf_rn((float)l0y, step.y, lo.y) <= q0.y &&
-                    __fmaf_rn((float)l0z, step.z, lo.z) <= q0.z && __fmaf_rn((float)h0x, step.x, lo.x) >= q1.x &&
-                    __fmaf_rn((float)h0y, step.y, lo.y) >= q1.y && __fmaf_rn((float)h0z, step.z, lo.z) >= q1.z &&
-                    __fmaf_rn((float)l1x, step.x, lo.x) <= q2.x && __fmaf_rn((float)l1y, step.y, lo.y) <= q2.y &&
-                    __fmaf_rn((float)l1z, step.z, lo.z) <= q2.z && __fmaf_rn((float)h1x, step.x, lo.x) >= q3.x &&
-                    __fmaf_rn((float)h1y, step.y, lo.y) >= q3.y && __fmaf_rn((float)h1z, step.z, lo.z) >= q3.z;
+    const bool ok = quant_plane(l0x, lo.x, step.x) <= q0.x && quant_plane(l0y, lo.y, step.y) <= q0.y && quant_plane(l0z, lo.z, step.z) <= q0.z &&
+                    quant_plane(h0x, lo.x, step.x) >= q1.x && quant_plane(h0y, lo.y, step.y) >= q1.y && quant_plane(h0z, lo.z, step.z) >= q1.z &&
+                    quant_plane(l1x, lo.x, step.x) <= q2.x && quant_plane(l1y, lo.y, step.y) <= q2.y && quant_plane(l1z, lo.z, step.z) <= q2.z &&
+                    quant_plane(h1x, lo.x, step.x) >= q3.x && quant_plane(h1y, lo.y, step.y) >= q3.y && quant_plane(h1z, lo.z, step.z) >= q3.z;
     if (!ok) atomicAdd(bad, 1u);
     qnodes[2 * (size_t)i + 0] = make_uint4(l0x | (l0y << 16), l0z | (h0x << 16), h0y | (h0z << 16), l1x | (l1y << 16));
     qnodes[2 * (size_t)i + 1] = make_uint4(l1z | (h1x << 16), h1y | (h1z << 16), __float_as_uint(q0.w), __float_as_uint(q1.w));
@@ -781,11 +794,18 @@ cudaError_t quantize_nodes(Scene& s, cudaStream_t stream)
     if (!s.d_qnodes) PTB_CUDA_TRY(cudaMalloc((void**)&s.d_qnodes, sizeof(uint4) * 2 * (size_t)s.n_nodes));
     s.qnodes_tree = 0;
     for (int a = 0; a < 3; ++a) {
+        // the grid: 65536 planes, a few dozen steps of margin on either side; `base` = origin - 2^23 * step is rounded to a
+        // float (its ulp is about one step), so both ends are checked with the traversal's own expression and nudged
         const float lo = s.h_bounds[a], hi = s.h_bounds[3 + a];
-        float step = (hi - lo) / 65535.0f;
+        float step = (hi - lo) / 65500.0f;
         if (!(step > 1e-30f)) step = 1e-30f;
-        for (int it = 0; it < 64 && fmaf(65535.0f, step, lo) < hi; ++it) step = nextafterf(step, INFINITY);   // the grid must reach hi
-        s.q_lo[a] = lo;
+        float base = (float)((double)lo - 16.0 * (double)step - 8388608.0 * (double)step);
+        for (int it = 0; it < 256; ++it) {
+            if (quant_plane(0u, base, step) > lo) base = nextafterf(base, -INFINITY);
+            else if (quant_plane(65535u, base, step) < hi) step = nextafterf(step, INFINITY);
+            else break;
+        }
+        s.q_lo[a] = base;
         s.q_step[a] = step;
     }
     PTB_CUDA_TRY(cudaMemsetAsync(s.d_work_counter + 3, 0, sizeof(uint32_t), stream));
@@ -797,6 +817,161 @@ cudaError_t quantize_nodes(Scene& s, cudaStream_t stream)
     PTB_CUDA_TRY(cudaStreamSynchronize(stream));
     if (bad == 0) s.qnodes_tree = tree;
     return cudaGetLastError();
+}
+
+
+// ---- 4-wide copy of the quantised tree (pt_scene_set_traversal 4) --------------------------------------------------------
+// Every wide node takes a binary node's two children and twice replaces the internal child with the largest surface area (first
+// one on ties) by that child's own two children, so one 64-byte fetch resolves up to two binary levels along the rays' most
+// likely way down.  Child boxes are the 16-bit planes of the binary quantised nodes, copied: the containment guarantee of
+// quantize_nodes carries over.  Nodes are numbered breadth first (root = 0: the levels every ray walks share cache lines), which
+// also makes the build a loop over levels: count the internal children of the level's nodes, scan, write the records and the next
+// level's list.  Record layout: pt_device.cuh FetchGlobal::wnode16.
+struct WideChild {
+    uint32_t w[3];     // lo | hi << 16 per axis
+    int ref;
+    double area;
+};
+__device__ __forceinline__ WideChild wide_child(const uint32_t* __restrict__ q, int node, int k, double sx, double sy, double sz)
+{
+    const uint32_t* r = q + 8 * (size_t)node;
+    const uint32_t w0 = r[3 * k], w1 = r[3 * k + 1], w2 = r[3 * k + 2];   // lo.x | lo.y << 16, lo.z | hi.x << 16, hi.y | hi.z << 16
+    const uint32_t lx = w0 & 0xffffu, ly = w0 >> 16, lz = w1 & 0xffffu, hx = w1 >> 16, hy = w2 & 0xffffu, hz = w2 >> 16;
+    WideChild c;
+    c.w[0] = lx | (hx << 16), c.w[1] = ly | (hy << 16), c.w[2] = lz | (hz << 16);
+    c.ref = (int)r[6 + k];
+    const double dx = sx * ((double)hx - (double)lx), dy = sy * ((double)hy - (double)ly), dz = sz * ((double)hz - (double)lz);
+    c.area = dx * dy + dy * dz + dz * dx;
+    return c;
+}
+__device__ __forceinline__ int wide_children(const uint32_t* __restrict__ q, int node, double sx, double sy, double sz, WideChild ch[4])
+{
+    int n = 2;
+    ch[0] = wide_child(q, node, 0, sx, sy, sz), ch[1] = wide_child(q, node, 1, sx, sy, sz);
+    while (n < 4) {
+        int best = -1;
+        for (int k = 0; k < n; ++k)
+            if (ch[k].ref >= 0 && (best < 0 || ch[k].area > ch[best].area)) best = k;
+        if (best < 0) break;
+        const int b = ch[best].ref;
+        ch[best] = wide_child(q, b, 0, sx, sy, sz);
+        ch[n++] = wide_child(q, b, 1, sx, sy, sz);
+    }
+    return n;
+}
+
+// state: [0] first wide index of the level  [1] nodes in the level  [2] levels so far
+__global__ void wide_init_kernel(int* __restrict__ state, int* __restrict__ level_nodes)
+{
+    state[0] = 0, state[1] = 1, state[2] = 1;
+    level_nodes[0] = 0;
+}
+__global__ void __launch_bounds__(256) wide_count_kernel(uint32_t bound, const int* __restrict__ state, const int* __restrict__ level_nodes,
+                                                         const uint32_t* __restrict__ q, double sx, double sy, double sz,
+                                                         uint32_t* __restrict__ counts)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > bound) return;
+    uint32_t c = 0;
+    if (i < (uint32_t)state[1]) {
+        WideChild ch[4];
+        const int n = wide_children(q, level_nodes[i], sx, sy, sz, ch);
+        for (int k = 0; k < n; ++k) c += ch[k].ref >= 0 ? 1u : 0u;
+    }
+    counts[i] = c;                                       // counts[bound] = 0: after the scan, the size of the next level
+}
+__global__ void __launch_bounds__(256) wide_emit_kernel(uint32_t bound, const int* __restrict__ state, const int* __restrict__ level_nodes,
+                                                        const uint32_t* __restrict__ q, double sx, double sy, double sz,
+                                                        const uint32_t* __restrict__ offsets, int* __restrict__ next_nodes,
+                                                        uint4* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= bound || i >= (uint32_t)state[1]) return;
+    WideChild ch[4];
+    const int n = wide_children(q, level_nodes[i], sx, sy, sz, ch);
+    uint32_t rec[16];
+    uint32_t at = offsets[i];
+    const uint32_t next_first = (uint32_t)(state[0] + state[1]);
+    for (int k = 0; k < 4; ++k) {
+        if (k >= n) {                                    // empty slot: child 0 again behind an inside-out box
+            rec[3 * k] = rec[3 * k + 1] = rec[3 * k + 2] = 0x0000ffffu;
+            continue;
+        }
+        rec[3 * k] = ch[k].w[0], rec[3 * k + 1] = ch[k].w[1], rec[3 * k + 2] = ch[k].w[2];
+        if (ch[k].ref >= 0) {
+            next_nodes[at] = ch[k].ref;
+            rec[12 + k] = next_first + at++;
+        } else {
+            rec[12 + k] = (uint32_t)ch[k].ref;
+        }
+    }
+    for (int k = n; k < 4; ++k) rec[12 + k] = rec[12];
+    uint4* o = out + 4 * ((size_t)state[0] + i);
+    for (int k = 0; k < 4; ++k) o[k] = make_uint4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+}
+__global__ void wide_advance_kernel(uint32_t bound, int* __restrict__ state, const uint32_t* __restrict__ offsets)
+{
+    const int next = (int)offsets[bound];
+    state[0] += state[1];
+    state[1] = next;
+    if (next > 0) state[2] += 1;
+}
+
+// Leaves s.d_wnodes null when the quantised nodes are not available.  Synchronous (reads the node count back).
+cudaError_t build_wide_nodes(Scene& s, cudaStream_t stream)
+{
+    const int tree = scene_tree(s);
+    if (s.n_tris < 2) return cudaSuccess;
+    if (s.d_wnodes && s.wnodes_tree == tree) return cudaSuccess;
+    PTB_CUDA_TRY(quantize_nodes(s, stream));
+    if (!s.d_qnodes || s.qnodes_tree != tree) return cudaSuccess;
+    s.wnodes_tree = 0;
+    if (s.d_wnodes) cudaFree(s.d_wnodes);
+    s.d_wnodes = nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    const uint32_t nn = s.n_nodes;
+    char* arena = nullptr;                               // two level lists, the counts, the state, all nn records
+    const size_t o_list0 = 0, o_list1 = o_list0 + sizeof(int) * (size_t)nn, o_counts = o_list1 + sizeof(int) * (size_t)nn,
+                 o_state = o_counts + sizeof(uint32_t) * ((size_t)nn + 1), o_out = (o_state + 16 + 255) & ~(size_t)255;
+    PTB_CUDA_TRY(cudaMalloc((void**)&arena, o_out + 64 * (size_t)nn));
+    int* lists[2] = {(int*)(arena + o_list0), (int*)(arena + o_list1)};
+    uint32_t* counts = (uint32_t*)(arena + o_counts);
+    int* state = (int*)(arena + o_state);
+    uint4* out = (uint4*)(arena + o_out);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(s.d_qnodes);
+    const double sx = s.q_step[0], sy = s.q_step[1], sz = s.q_step[2];
+    wide_init_kernel<<<1, 1, 0, stream>>>(state, lists[0]);
+    const uint32_t levels = scene_depth(s) + 1u;         // a wide level never spans less than one binary level
+    uint64_t width = 1;
+    for (uint32_t level = 0; level < levels; ++level) {
+        const uint32_t bound = (uint32_t)std::min<uint64_t>(width, nn);
+        const int cur = (int)(level & 1u);
+        wide_count_kernel<<<div_up(bound + 1, 256), 256, 0, stream>>>(bound, state, lists[cur], q, sx, sy, sz, counts);
+        scan_exclusive(counts, bound + 1u, s.d_scan_scratch, stream);
+        wide_emit_kernel<<<div_up(bound, 256), 256, 0, stream>>>(bound, state, lists[cur], q, sx, sy, sz, counts, lists[cur ^ 1], out);
+        wide_advance_kernel<<<1, 1, 0, stream>>>(bound, state, counts);
+        width = std::min<uint64_t>(width * 4, nn);
+    }
+    int h_state[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h_state, state, sizeof(h_state), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && h_state[1] == 0 && h_state[0] >= 1 && (uint32_t)h_state[0] <= nn) {   // every level consumed
+        e = cudaMalloc((void**)&s.d_wnodes, 64 * (size_t)h_state[0]);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_wnodes, out, 64 * (size_t)h_state[0], cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) {
+            s.n_wnodes = (uint32_t)h_state[0];
+            s.wide_depth = (uint32_t)h_state[2];
+            s.wnodes_tree = tree;
+        } else if (s.d_wnodes) {
+            cudaFree(s.d_wnodes);
+            s.d_wnodes = nullptr;
+        }
+    }
+    cudaFree(arena);
+    s.wide_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return e;
 }
 
 }  // namespace ptb

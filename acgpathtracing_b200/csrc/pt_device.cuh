@@ -98,28 +98,43 @@ struct FetchGlobal {
     const float4 *nodes, *tris, *shade, *mats;
     // quantised nodes (lbvh.cu quantize_nodes_kernel), 32 bytes = one LDG.E.256 per node: twelve 16-bit plane positions on
     // the scene's bounding-box grid (w0 = lo0.x | lo0.y << 16, w1 = lo0.z | hi0.x << 16, w2 = hi0.y | hi0.z << 16, w3..w5 the
-    // same for child 1) and the two child references (w6, w7).  A plane is q * step + lo in ONE fused multiply-add, the same
+    // same for child 1) and the two child references (w6, w7).  A plane is (2^23 + q) * step + base in ONE fused multiply-add
+    // -- 2^23 + q is the float with bit pattern 0x4b000000 | q, so no integer conversion is needed -- and that is the
     // expression the build checks its rounding with: lo planes never above, hi planes never below the exact box.
     const float4* qnodes;
-    float3 q_lo, q_step;
+    float3 q_lo, q_step;                                  // base = grid origin - 2^23 * step, and the step, per axis
+    bool prefetch = true;                                 // pull deferred children towards L2 (WfTune::prefetch)
+    __device__ __forceinline__ float qf_lo(uint32_t w) const { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)); }
+    __device__ __forceinline__ float qf_hi(uint32_t w) const { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)); }
     __device__ __forceinline__ void qnode4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
     {
         float4 a, b;
         ldg256(qnodes + 2 * (size_t)i, a, b);
         const uint32_t w0 = __float_as_uint(a.x), w1 = __float_as_uint(a.y), w2 = __float_as_uint(a.z), w3 = __float_as_uint(a.w);
         const uint32_t w4 = __float_as_uint(b.x), w5 = __float_as_uint(b.y);
-        q0 = make_float4(__fmaf_rn((float)(w0 & 0xffffu), q_step.x, q_lo.x), __fmaf_rn((float)(w0 >> 16), q_step.y, q_lo.y),
-                         __fmaf_rn((float)(w1 & 0xffffu), q_step.z, q_lo.z), b.z);
-        q1 = make_float4(__fmaf_rn((float)(w1 >> 16), q_step.x, q_lo.x), __fmaf_rn((float)(w2 & 0xffffu), q_step.y, q_lo.y),
-                         __fmaf_rn((float)(w2 >> 16), q_step.z, q_lo.z), b.w);
-        q2 = make_float4(__fmaf_rn((float)(w3 & 0xffffu), q_step.x, q_lo.x), __fmaf_rn((float)(w3 >> 16), q_step.y, q_lo.y),
-                         __fmaf_rn((float)(w4 & 0xffffu), q_step.z, q_lo.z), 0.0f);
-        q3 = make_float4(__fmaf_rn((float)(w4 >> 16), q_step.x, q_lo.x), __fmaf_rn((float)(w5 & 0xffffu), q_step.y, q_lo.y),
-                         __fmaf_rn((float)(w5 >> 16), q_step.z, q_lo.z), 0.0f);
+        q0 = make_float4(__fmaf_rn(qf_lo(w0), q_step.x, q_lo.x), __fmaf_rn(qf_hi(w0), q_step.y, q_lo.y), __fmaf_rn(qf_lo(w1), q_step.z, q_lo.z), b.z);
+        q1 = make_float4(__fmaf_rn(qf_hi(w1), q_step.x, q_lo.x), __fmaf_rn(qf_lo(w2), q_step.y, q_lo.y), __fmaf_rn(qf_hi(w2), q_step.z, q_lo.z), b.w);
+        q2 = make_float4(__fmaf_rn(qf_lo(w3), q_step.x, q_lo.x), __fmaf_rn(qf_hi(w3), q_step.y, q_lo.y), __fmaf_rn(qf_lo(w4), q_step.z, q_lo.z), 0.0f);
+        q3 = make_float4(__fmaf_rn(qf_hi(w4), q_step.x, q_lo.x), __fmaf_rn(qf_lo(w5), q_step.y, q_lo.y), __fmaf_rn(qf_hi(w5), q_step.z, q_lo.z), 0.0f);
     }
     __device__ __forceinline__ void prefetch_qchild(int c) const
     {
+        if (!prefetch) return;
         const void* p = c >= 0 ? (const void*)(qnodes + 2 * (size_t)c) : (const void*)(tris + 3 * (~c));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+    // 4-wide quantised nodes (lbvh.cu build_wide_nodes), 64 bytes = two LDG.E.256 per node, read through `qnodes`: four child
+    // boxes on the same grid, one word per child and axis (lo | hi << 16; words 3k .. 3k+2 = x, y, z of child k), and four child
+    // references (words 12..15).  The planes are those of the binary quantised nodes; an empty slot repeats child 0 behind an
+    // inside-out box (lo = 65535, hi = 0 on every axis: never entered before it is left -- and harmless if it ever were).
+    __device__ __forceinline__ void wnode16(int i, float4& a, float4& b, float4& c, float4& d) const
+    {
+        ldg256(qnodes + 4 * (size_t)i, a, b);
+        ldg256(qnodes + 4 * (size_t)i + 2, c, d);
+    }
+    __device__ __forceinline__ void prefetch_wchild(int c) const
+    {
+        const void* p = c >= 0 ? (const void*)(qnodes + 4 * (size_t)c) : (const void*)(tris + 3 * (~c));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
     __device__ __forceinline__ void node4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
@@ -143,6 +158,7 @@ struct FetchGlobal {
     // a deferred child will be fetched after the subtree of its sibling: start pulling its record towards L2/L1 now
     __device__ __forceinline__ void prefetch_child(int c) const
     {
+        if (!prefetch) return;
         const void* p = c >= 0 ? (const void*)(nodes + 4 * c) : (const void*)(tris + 3 * (~c));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
@@ -184,12 +200,24 @@ struct StackLocal {      // per-thread array (local memory)
     int* a;
     __device__ __forceinline__ void put(int i, int v) const { a[i] = v; }
     __device__ __forceinline__ int get(int i) const { return a[i]; }
+    __device__ __forceinline__ void put3(int sp, int n, int c3, int c2, int c1) const
+    {
+        if (n > 3) put(sp, c3);
+        if (n > 2) put(sp + n - 3, c2);
+        if (n > 1) put(sp + n - 2, c1);
+    }
 };
 struct StackStrided {    // level-major words, `stride` paths apart (shared memory; bank = path id mod 32)
     int* base;
     int stride;
     __device__ __forceinline__ void put(int i, int v) const { base[i * stride] = v; }
     __device__ __forceinline__ int get(int i) const { return base[i * stride]; }
+    __device__ __forceinline__ void put3(int sp, int n, int c3, int c2, int c1) const
+    {
+        if (n > 3) put(sp, c3);
+        if (n > 2) put(sp + n - 3, c2);
+        if (n > 1) put(sp + n - 2, c1);
+    }
 };
 
 // The first `cap` levels in shared memory as above, deeper levels in a global-memory array (level-major, `ostride`
@@ -208,6 +236,21 @@ struct StackSpill {
         else over[(size_t)(i - cap) * ostride] = v;
     }
     __device__ __forceinline__ int get(int i) const { return i < cap ? base[i * stride] : over[(size_t)(i - cap) * ostride]; }
+    // up to three pushes of one wide-node step (n - 1 of them, farthest child first): predicated shared-memory stores while
+    // all three levels are in shared memory
+    __device__ __forceinline__ void put3(int sp, int n, int c3, int c2, int c1) const
+    {
+        if (sp + 3 <= cap) {
+            int* p = base + sp * stride;
+            if (n > 3) p[0] = c3;
+            if (n > 2) p[(n - 3) * stride] = c2;
+            if (n > 1) p[(n - 2) * stride] = c1;
+        } else {
+            if (n > 3) put(sp, c3);
+            if (n > 2) put(sp + n - 3, c2);
+            if (n > 1) put(sp + n - 2, c1);
+        }
+    }
 };
 
 struct Ray {
@@ -337,6 +380,76 @@ __device__ __forceinline__ void trav_qnode_step(Trav& t, const STK& stack, const
     float4 q0, q1, q2, q3;
     f.qnode4(t.cur, q0, q1, q2, q3);
     trav_node_apply<true>(t, stack, f, tmin, q0, q1, q2, q3);
+}
+
+// Node step on the 4-wide quantised nodes: one fetch resolves up to two levels of the binary tree.  Every axis word holds both
+// planes of a child; which half is the entry plane follows from the ray's direction sign (selectors `sel`: byte-permute codes
+// of the entry half per axis, the exit half is the other one), so the slab test needs no min/max per axis -- the distances are
+// the same numbers ray_box() computes.  The hit children are visited nearest first (entry distance with the low two mantissa
+// bits replaced by the slot number); the order only matters for the amount of work.
+struct WideSel {
+    uint32_t x, y, z;
+};
+__device__ __forceinline__ WideSel wide_selectors(float3 inv)
+{
+    return WideSel{inv.x < 0.0f ? 0x7432u : 0x7410u, inv.y < 0.0f ? 0x7432u : 0x7410u, inv.z < 0.0f ? 0x7432u : 0x7410u};
+}
+template <class FETCH>
+__device__ __forceinline__ uint32_t wide_child_key(const Trav& t, const FETCH& f, WideSel sel, float wx, float wy, float wz, float tmin)
+{
+    const uint32_t ux = __float_as_uint(wx), uy = __float_as_uint(wy), uz = __float_as_uint(wz);
+    const float nx = __fmaf_rn(__uint_as_float(__byte_perm(ux, 0x4b000000u, sel.x)), f.q_step.x, f.q_lo.x);
+    const float ny = __fmaf_rn(__uint_as_float(__byte_perm(uy, 0x4b000000u, sel.y)), f.q_step.y, f.q_lo.y);
+    const float nz = __fmaf_rn(__uint_as_float(__byte_perm(uz, 0x4b000000u, sel.z)), f.q_step.z, f.q_lo.z);
+    const float fx = __fmaf_rn(__uint_as_float(__byte_perm(ux, 0x4b000000u, sel.x ^ 0x0022u)), f.q_step.x, f.q_lo.x);
+    const float fy = __fmaf_rn(__uint_as_float(__byte_perm(uy, 0x4b000000u, sel.y ^ 0x0022u)), f.q_step.y, f.q_lo.y);
+    const float fz = __fmaf_rn(__uint_as_float(__byte_perm(uz, 0x4b000000u, sel.z ^ 0x0022u)), f.q_step.z, f.q_lo.z);
+    const float tn = fmaxf(fmaxf(__fmaf_rn(nx, t.r.inv.x, -t.r.ood.x), __fmaf_rn(ny, t.r.inv.y, -t.r.ood.y)),
+                           fmaxf(__fmaf_rn(nz, t.r.inv.z, -t.r.ood.z), tmin));
+    const float tf = fminf(fminf(__fmaf_rn(fx, t.r.inv.x, -t.r.ood.x), __fmaf_rn(fy, t.r.inv.y, -t.r.ood.y)),
+                           fminf(__fmaf_rn(fz, t.r.inv.z, -t.r.ood.z), t.tfar));
+    return tn <= tf * 1.0000004f ? __float_as_uint(tn) : 0x7f800000u;    // tn >= tmin > 0: the bit patterns order like the floats
+}
+
+__device__ __forceinline__ void wide_order(uint32_t& ka, int& ra, uint32_t& kb, int& rb)
+{
+    const bool sw = kb < ka;
+    const uint32_t k = sw ? kb : ka;
+    const int r = sw ? rb : ra;
+    kb = sw ? ka : kb, rb = sw ? ra : rb;
+    ka = k, ra = r;
+}
+
+template <class FETCH, class STK>
+__device__ __forceinline__ void trav_wnode_step(Trav& t, const STK& stack, const FETCH& f, float tmin, WideSel sel)
+{
+    float4 a, b, c, d;
+    f.wnode16(t.cur, a, b, c, d);
+    int r0 = __float_as_int(d.x), r1 = __float_as_int(d.y), r2 = __float_as_int(d.z), r3 = __float_as_int(d.w);
+    constexpr uint32_t kMiss = 0x7f800000u;
+    uint32_t k0 = wide_child_key(t, f, sel, a.x, a.y, a.z, tmin);
+    uint32_t k1 = wide_child_key(t, f, sel, a.w, b.x, b.y, tmin);
+    uint32_t k2 = wide_child_key(t, f, sel, b.z, b.w, c.x, tmin);
+    uint32_t k3 = wide_child_key(t, f, sel, c.y, c.z, c.w, tmin);
+    // sorting network on (entry distance, child): misses last
+    wide_order(k0, r0, k1, r1);
+    wide_order(k2, r2, k3, r3);
+    wide_order(k0, r0, k2, r2);
+    wide_order(k1, r1, k3, r3);
+    wide_order(k1, r1, k2, r2);
+    // selects and predicated stores instead of a branch ladder (the warp runs this once for all lanes): the stack top is read
+    // unconditionally so that "no child hit -> next deferred child" needs no divergent branch
+    const int sp = t.sp;
+    const int top = stack.get(sp > 0 ? sp - 1 : 0);
+    const int n = (k0 < kMiss) + (k1 < kMiss) + (k2 < kMiss) + (k3 < kMiss);
+    stack.put3(sp, n, r3, r2, r1);                        // farthest first
+    if (f.prefetch) {
+        if (n > 3) f.prefetch_wchild(r3);
+        if (n > 2) f.prefetch_wchild(r2);
+        if (n > 1) f.prefetch_wchild(r1);
+    }
+    t.cur = n > 0 ? r0 : (sp > 0 ? top : kTravDone);
+    t.sp = n > 0 ? sp + n - 1 : (sp > 0 ? sp - 1 : 0);
 }
 
 template <class FETCH, class STK>

@@ -47,6 +47,7 @@ struct WfTune {
     int affinity = 2;        // schedulers (warp % 4 < affinity) whose warps look at the traversal queues first, the others at the
                              // shading queues (instruction-cache locality per scheduler; C2 +5.7 % together with full_cols = 30)
     int affinity_g = 3;      // ... for scenes read from global memory (C3 +7 %, C4 +2 %)
+    int prefetch = 0;        // scenes in global memory: prefetch deferred children towards L2 (measured: C4 -6 %, C3 -1 %)
     int msort = 0;           // material-sorted SHADE: one queue per BSDF type (scenes with more than one type); measured, see DESIGN.md
 };
 
@@ -115,8 +116,13 @@ struct Scene {
     float4* d_qnodes = nullptr;
     int qnodes_tree = 0;              // which tree (1 LBVH, 2 SAH, 3 PLOC) d_qnodes was made from; 0 = none
     float q_lo[3] = {0.f, 0.f, 0.f}, q_step[3] = {1.f, 1.f, 1.f};
+    // 4-wide quantised 64-byte nodes of the tree in use (lbvh.cu build_wide_nodes), built at the first launch that wants them
+    float4* d_wnodes = nullptr;
+    int wnodes_tree = 0;              // which tree d_wnodes was made from; 0 = none
+    uint32_t n_wnodes = 0, wide_depth = 0;
+    float wide_ms = 0.f;              // host time of the collapse
     int traversal = 0;                // pt_scene_set_traversal: 0 auto, 1 exact nodes (staged when the scene fits), 2 exact nodes from
-                                      // global memory whatever the size, 3 quantised nodes (global memory)
+                                      // global memory whatever the size, 3 quantised nodes (global memory), 4 4-wide quantised nodes
 
     // launch-time scratch
     uint32_t* d_work_counter = nullptr;         // [0] pixel fetch counter  [1] LBVH depth (build)
@@ -138,7 +144,7 @@ struct Scene {
     size_t team_log_bytes = 0;
 
     // last launch
-    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_trav = 0;   // last_trav: 0 exact 64-byte nodes, 1 quantised 32-byte nodes
+    uint32_t last_grid = 0, last_block = 0, last_smem = 0, last_kernels = 0, last_trav = 0;   // last_trav: 0 exact 64-byte nodes, 1 quantised 32-byte nodes, 2 4-wide quantised nodes
 };
 
 constexpr uint32_t kSahMaxTris = 8192;    // the host build is O(n log^2 n); larger scenes keep the GPU-built LBVH
@@ -176,6 +182,7 @@ size_t lbvh_scan_scratch_entries(size_t n_tris);
 cudaError_t lbvh_build(Scene& s, cudaStream_t stream);
 cudaError_t ploc_build(Scene& s, cudaStream_t stream);
 cudaError_t quantize_nodes(Scene& s, cudaStream_t stream);
+cudaError_t build_wide_nodes(Scene& s, cudaStream_t stream);
 
 // render.cu
 constexpr uint32_t kMaxFoldFrames = 64;

@@ -62,6 +62,7 @@ struct WfConst {
     uint32_t stack_depth;    // words per path in shared memory
     uint32_t stack_total;    // words per path the tree can need; levels >= stack_depth live in `stack_over`
     int* stack_over;         // [stack_total - stack_depth][grid * np], or null
+    int prefetch;            // scenes in global memory: prefetch deferred children towards L2
     uint32_t copies_shift;   // staged scene copies = 1 << copies_shift
     int node_steps;          // K: slab-test steps per NODE batch
     int node_keep8;          // a NODE batch continues while lanes_at_node * 8 >= lanes_at_start * node_keep8
@@ -699,9 +700,19 @@ __device__ __noinline__ unsigned long long end_any_slot(const LaunchConst& lc, c
 //   TRAV_DIRECT  every lane reads its own 64-byte node (two LDG.E.256)
 //   TRAV_QUANT   quantised nodes: twelve 16-bit planes + two child references in 32 bytes, ONE LDG.E.256 per lane and node
 //                (lbvh.cu quantize_nodes_kernel): half the L1 requests and half the node bytes of TRAV_DIRECT
-// (Round 1 also measured two-level wide nodes and a warp-cooperative transposed fetch; both lost on B200 --
+//   TRAV_WIDE    4-wide quantised nodes: four child boxes + four references in 64 bytes (lbvh.cu build_wide_nodes), one step
+//                resolves up to two binary levels: half the dependent fetches and half the pops / pushes / votes per ray
+// (Round 1 also measured uncompressed two-level nodes and a warp-cooperative transposed fetch; both lost on B200 --
 // profiles/r1_c3_c4_traversal_variants.txt -- and were removed.)
-enum : int { TRAV_DIRECT = 0, TRAV_QUANT = 1 };
+enum : int { TRAV_DIRECT = 0, TRAV_QUANT = 1, TRAV_WIDE = 2 };
+
+template <int TRAV, class FETCH, class STK>
+__device__ __forceinline__ void wf_node_step(Trav& t, const STK& stack, const FETCH& f, WideSel sel)
+{
+    if constexpr (TRAV == TRAV_WIDE) trav_wnode_step(t, stack, f, 0.01f, sel);
+    else if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
+    else trav_node_step(t, stack, f, 0.01f);                                     // tmin :754
+}
 
 template <bool COUNT, bool PROBE, int SCENE, bool SHORT, int TRAV, bool MSORT, bool TEAM>
 __global__ void __launch_bounds__(kWfBlock, 1)
@@ -735,6 +746,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
         f.qnodes = lc.qnodes;
         f.q_lo = lc.q_lo;
         f.q_step = lc.q_step;
+        f.prefetch = wc.prefetch != 0;
     }
     if (SCENE >= 0) {
         const uint32_t shift = SCENE >= 0 ? (uint32_t)SCENE : 0u, copies = 1u << shift;
@@ -893,6 +905,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 mode = spm >> 8;
             }
             const typename WfStack<SCENE>::type stack = WfStack<SCENE>::make(stack_mem, pid, NP, wc);
+            const WideSel sel = wide_selectors(t.r.inv);
             for (;;) {
                 const bool at_node = t.cur >= 0;
                 const bool at_leaf = t.cur < 0 && t.cur != kTravDone;
@@ -901,8 +914,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 if (__popc(bn) >= __popc(bl)) {
                     if (at_node) {
                         if (COUNT) ctr.n_node++;
-                        if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
-                        else trav_node_step(t, stack, f, 0.01f);
+                        wf_node_step<TRAV>(t, stack, f, sel);
                     }
                 } else if (at_leaf) {
                     if (COUNT) ctr.n_tri++;
@@ -939,6 +951,7 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
             }
             const typename WfStack<SCENE>::type stack = WfStack<SCENE>::make(stack_mem, pid, NP, wc);
             const int n0 = __popc(__ballot_sync(kFull, active));
+            const WideSel sel = wide_selectors(t.r.inv);
             if (COUNT) st_batches[ST_NODE]++, st_lanes[ST_NODE] += n0;
             for (int step = 0; step < wc.node_steps; ++step) {
                 const bool at = t.cur >= 0;
@@ -947,13 +960,11 @@ render_wavefront_kernel(const __grid_constant__ LaunchConst lc, const __grid_con
                 if (COUNT) st_steps++, st_step_lanes += n;
                 if (at) {
                     if (COUNT) ctr.n_node++;
-                    if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
-                    else trav_node_step(t, stack, f, 0.01f);                     // tmin :754
+                    wf_node_step<TRAV>(t, stack, f, sel);
                 }
-                if (t.cur >= 0) {                                                // second step under the same vote
+                if (TRAV != TRAV_WIDE && t.cur >= 0) {                           // second step under the same vote
                     if (COUNT) ctr.n_node++;
-                    if constexpr (TRAV == TRAV_QUANT) trav_qnode_step(t, stack, f, 0.01f);
-                    else trav_node_step(t, stack, f, 0.01f);
+                    wf_node_step<TRAV>(t, stack, f, sel);
                 }
             }
             if (active) {
@@ -1180,7 +1191,8 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
 
 // How NODE batches read a scene that stays in global memory (pt_scene_set_traversal; PTB_TUNE quant= overrides).
 // Measured on B200: per-lane 256-bit loads of the exact 64-byte nodes are the fastest while the records fit
-// in L2 (C3); above that the 32-byte quantised nodes win (C4).  Both are bit-identical in their pixels.
+// in L2 (C3); above that the 4-wide quantised nodes win (C4: +11 % over the 32-byte binary ones).  All are bit-identical in
+// their pixels.
 static int choose_trav(const Scene& s, const WfTune& tune)
 {
     // quantised nodes: not for launches that count the SPECIFIED work (their counters are those of the exact boxes)
@@ -1191,8 +1203,9 @@ static int choose_trav(const Scene& s, const WfTune& tune)
         if (cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev) != cudaSuccess) l2_bytes = 0;
     }
     const bool larger_than_l2 = 64 * (size_t)s.n_nodes + 48 * (size_t)s.n_tris > (size_t)l2_bytes;
-    const bool quant = tune.quant >= 0 ? tune.quant != 0 : (s.traversal == 3 || (s.traversal == 0 && larger_than_l2));
-    return ((!s.count_enabled || s.count_executed) && s.n_tris >= 2 && quant) ? TRAV_QUANT : TRAV_DIRECT;
+    const bool wide = tune.quant >= 0 ? tune.quant == 2 : (s.traversal == 4 || (s.traversal == 0 && larger_than_l2));
+    const bool quant = tune.quant >= 0 ? tune.quant != 0 : s.traversal == 3;
+    return ((!s.count_enabled || s.count_executed) && s.n_tris >= 2 && (quant || wide)) ? (wide ? TRAV_WIDE : TRAV_QUANT) : TRAV_DIRECT;
 }
 
 // PTB_TUNE="node_votes=6,tail_cols=40,..." -- experiment overrides of WfTune from the environment, parsed once per
@@ -1211,7 +1224,7 @@ static const TuneKey kTuneKeys[] = {{"node_votes_g", &WfTune::node_votes_g}, {"f
                                     {"idle_shift", &WfTune::idle_shift}, {"stack_smem", &WfTune::stack_smem},
                                     {"team", &WfTune::team},             {"team_min", &WfTune::team_min},
                                     {"msort", &WfTune::msort},           {"affinity", &WfTune::affinity},
-                                    {"affinity_g", &WfTune::affinity_g}};
+                                    {"affinity_g", &WfTune::affinity_g}, {"prefetch", &WfTune::prefetch}};
 
 bool wf_tune_apply(WfTune& t, const char* spec)
 {
@@ -1268,7 +1281,7 @@ static bool wavefront_plan(const Scene& s, const WfTune& tune, WfConst& wc, size
     const uint32_t depth = scene_depth(s) + 1u;           // deferred children never exceed the tree depth
     if (depth > 255u) return false;
     trav = TRAV_DIRECT;
-    const bool force_global = s.traversal == 2 || s.traversal == 3;
+    const bool force_global = s.traversal >= 2;
     const size_t scene_f4 = 4 * (size_t)s.n_nodes + 4 * (size_t)s.n_tris + 3 * (size_t)s.n_mats;
     const size_t fixed = (size_t)kCtlF4 * 16;
     const size_t per_path = (size_t)kStateF4 * 16 + 4 + 4 * (size_t)depth;   // state, candidate word, stack
@@ -1334,7 +1347,15 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     wc.idle_ns = tune.idle_ns;
     wc.idle_shift = tune.idle_shift;
     wc.affinity = smem_scene ? tune.affinity : tune.affinity_g;
+    wc.prefetch = tune.prefetch;
     wc.stack_over = nullptr;
+    if (!smem_scene && trav == TRAV_WIDE) {
+        // a wide step defers up to three children: the stack is sized from the wide tree's own depth
+        cudaError_t we = build_wide_nodes(s, stream);
+        if (we != cudaSuccess) return we;
+        if (s.d_wnodes && s.wnodes_tree == scene_tree(s) && 3u * s.wide_depth + 1u <= 255u) wc.stack_total = 3u * s.wide_depth + 1u;
+        else trav = TRAV_QUANT;
+    }
     if (!smem_scene && wc.stack_total > wc.stack_depth) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
@@ -1385,6 +1406,19 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     // counters stay the ones of the specified traversal (and equal to the oracle's).
     const bool use_short = scene == 3 && s.n_tris <= 64 && tune.shortlist != 0;
     s.last_trav = 0;
+    if (scene < 0 && trav == TRAV_WIDE) {
+        LaunchConst lq = lc;
+        lq.qnodes = s.d_wnodes;
+        lq.q_lo = make_float3(s.q_lo[0], s.q_lo[1], s.q_lo[2]);
+        lq.q_step = make_float3(s.q_step[0], s.q_step[1], s.q_step[2]);
+        s.last_trav = 2;
+        if (probe) return launch_wavefront<false, true, -1, false, TRAV_WIDE>(s, lq, wc, smem_bytes, stream);
+        if (count)
+            return team ? launch_wavefront<true, false, -1, false, TRAV_WIDE, false, true>(s, lq, wc, smem_bytes, stream)
+                        : launch_wavefront<true, false, -1, false, TRAV_WIDE>(s, lq, wc, smem_bytes, stream);
+        return team ? launch_wavefront<false, false, -1, false, TRAV_WIDE, false, true>(s, lq, wc, smem_bytes, stream)
+                    : launch_wavefront<false, false, -1, false, TRAV_WIDE>(s, lq, wc, smem_bytes, stream);
+    }
     if (scene < 0 && trav == TRAV_QUANT) {
         cudaError_t qe = quantize_nodes(s, stream);
         if (qe != cudaSuccess) return qe;

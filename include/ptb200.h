@@ -211,15 +211,18 @@ int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
 int pt_scene_set_tree(pt_scene* scene, int tree);
 int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH, 3 PLOC */
 /* How the render kernel reads the acceleration structure:
- *   0 = auto: 1, except 3 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
+ *   0 = auto: 1, except 4 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
  *   1 = the exact 64-byte nodes of the tree in use, every lane fetches its own (from shared memory when the scene fits);
  *   2 = the same, but read from global memory whatever the scene's size (tests, A/B runs);
  *   3 = quantised nodes: 32 bytes per node (twelve 16-bit plane positions on the grid of the scene's bounding box,
- *       rounded outwards and checked, + two child references), one 256-bit load per node; scene read from global memory.
+ *       rounded outwards and checked, + two child references), one 256-bit load per node; scene read from global memory;
+ *   4 = 4-wide quantised nodes: 64 bytes per node (four child boxes on the same grid + four references), every node stands
+ *       for up to two levels of the binary tree (the internal child with the largest surface area is opened, twice);
+ *       collapsed on the host at the first launch that asks for it; scene read from global memory.
  * The pixels do not depend on it: every variant culls with boxes that contain the tree's own and every hit comes from
  * the same triangle test (OptiX's acceleration structure, PathTracerMain.cpp:311-398, is closed). */
 int pt_scene_set_traversal(pt_scene* scene, int traversal);
-int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 exact nodes, 1 quantised nodes */
+int pt_scene_last_traversal(const pt_scene* scene);   /* last launch: 0 exact nodes, 1 quantised nodes, 2 4-wide quantised nodes */
 /* Scheduling constants of the render kernel for ONE scene: "key=value,key=value" (keys: csrc/pt_scene.h WfTune).  They
  * change how paths are batched, never a pixel (tests/test_gpu_parity.py::test_schedule_perturbation).  The environment
  * variable PTB_TUNE, read once per process, overrides them for every scene.  PT_ERR_INVALID for an unknown key. */
@@ -244,6 +247,10 @@ int pt_bvh_export_ploc(const pt_scene* scene, void* nodes64, uint32_t* depth, fl
  * (lo0.x|lo0.y<<16, lo0.z|hi0.x<<16, hi0.y|hi0.z<<16, then the same for child 1) + the two child references; a plane is
  * fma(q, step[axis], lo[axis]). */
 int pt_bvh_export_quant(pt_scene* scene, void* qnodes32, float* lo3, float* step3);
+/* 4-wide quantised nodes of the tree in use (built on first use): n_wide records of 16 words -- words 3k..3k+2 the box of child
+ * k (lo | hi << 16 per axis, planes of the binary quantised nodes), words 12..15 the child references (>= 0 wide node, < 0 ~leaf
+ * slot); numbered breadth first.  wnodes64 may be NULL (sizes only); capacity in records. */
+int pt_bvh_export_wide(pt_scene* scene, void* wnodes64, uint32_t capacity, uint32_t* n_wide, uint32_t* depth, float* build_ms);
 /* The host builder on its own (no device needed): tri_boxes8 = per PRIMITIVE (lo.xyz, -, hi.xyz, -), sorted_prim =
  * leaf slot -> primitive (pt_bvh_export), n_tris >= 2; writes (n_tris - 1) x 64 B. */
 int pt_sah_build_host(const float* tri_boxes8, const uint32_t* sorted_prim, uint32_t n_tris, void* nodes64, uint32_t* depth);

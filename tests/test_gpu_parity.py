@@ -472,8 +472,8 @@ def test_full_size_c4_two_million_triangles(api, port):
         assert gs.last_launch_info()["traversal"] == "binary"                     # pipeline 1 ran last
         import torch
         acc_c, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
-        assert gs.last_launch_info()["traversal"] == "binary-quant"               # auto: the records do not fit in L2
-        for trav, expect in ((2, "binary"), (1, "binary")):
+        assert gs.last_launch_info()["traversal"] == "wide4-quant"                # auto: the records do not fit in L2
+        for trav, expect in ((2, "binary"), (3, "binary-quant"), (1, "binary")):
             gs.set_traversal(trav)
             acc_t, _ = _crop_check(api, gs, osc, 1920, 1080, 4, 8, (940, 964, 420, 432))
             assert gs.last_launch_info()["traversal"] == expect
@@ -670,7 +670,7 @@ def test_random_soups_and_cameras(api, port, seed):
 
 
 # ---- node fetch variants (pt_scene_set_traversal): same pixels ------------------------------------------------------------
-TRAVERSALS = ((2, "binary"), (3, "binary-quant"), (1, "binary"))   # exact nodes from global memory, quantised, auto placement
+TRAVERSALS = ((2, "binary"), (3, "binary-quant"), (4, "wide4-quant"), (1, "binary"))   # global exact, quantised, 4-wide, auto placement
 
 
 @pytest.mark.parametrize("name,w,h,spp,md", [("cornell", 160, 90, 6, 16), ("material", 200, 112, 6, 28), ("tess40", 160, 90, 4, 8),
@@ -705,7 +705,7 @@ def test_traversal_variants_single_triangle_and_soups(api, port):
             p = api.make_params(64, 40, 4, 6, frame=0, nee=True, scene=gs)
             o = osc.render(p, math_mode=1, use_bvh=True)
             for trav, expect in TRAVERSALS:
-                if n_tri < 2 and trav == 3:
+                if n_tri < 2 and trav in (3, 4):
                     expect = "binary"                         # a single triangle has no quantised node array: exact nodes
                 gs.set_traversal(trav)
                 g = gs.launch_host(p)
@@ -717,7 +717,7 @@ def test_traversal_variants_single_triangle_and_soups(api, port):
                 a[:, [11, 15]] = 0
                 b[:, [11, 15]] = 0
                 assert gp["depth"] == op["depth"] and np.array_equal(a, b), n_tri
-                for trav in (0, 3):                          # exact and quantised nodes of each tree
+                for trav in (0, 3, 4):                       # exact, quantised and 4-wide nodes of each tree
                     gs.set_traversal(trav)
                     for tree in (1, 2, 3):
                         gs.set_tree(tree)
@@ -861,7 +861,7 @@ def test_degenerate_scenes_all_trees(api, port, kind):
             assert exp_g["depth"] == exp_o["depth"] and np.array_equal(a, b)
         p = api.make_params(96, 54, 3, 12, frame=0, nee=True, scene=gs)
         for tree in (0, 1, 2, 3):
-            for trav in (0, 2, 3):
+            for trav in (0, 2, 3, 4):
                 used = osc.set_tree(tree)
                 try:
                     gs.set_tree(tree)
@@ -876,9 +876,78 @@ def test_degenerate_scenes_all_trees(api, port, kind):
         gs.destroy()
 
 
+def _collapse_wide(q, step):
+    """The 4-wide collapse restated (lbvh.cu build_wide_nodes): breadth first; per node the two children of a binary node,
+    then twice the internal child with the largest surface area (first one on ties) replaced by its own two children."""
+    sx, sy, sz = (float(v) for v in step)
+
+    def child(node, k):
+        w0, w1, w2 = (int(v) for v in q[node, 3 * k:3 * k + 3])
+        lx, ly, lz, hx, hy, hz = w0 & 0xFFFF, w0 >> 16, w1 & 0xFFFF, w1 >> 16, w2 & 0xFFFF, w2 >> 16
+        dx, dy, dz = sx * (float(hx) - float(lx)), sy * (float(hy) - float(ly)), sz * (float(hz) - float(lz))
+        ref = int(np.int32(q[node, 6 + k]))
+        return [lx | (hx << 16), ly | (hy << 16), lz | (hz << 16)], ref, dx * dy + dy * dz + dz * dx
+
+    binary_of, level, out = [0], [1], []
+    wi = 0
+    while wi < len(binary_of):
+        ch = [child(binary_of[wi], 0), child(binary_of[wi], 1)]
+        while len(ch) < 4:
+            best = -1
+            for k, c in enumerate(ch):
+                if c[1] >= 0 and (best < 0 or c[2] > ch[best][2]):
+                    best = k
+            if best < 0:
+                break
+            b = ch[best][1]
+            ch[best] = child(b, 0)
+            ch.append(child(b, 1))
+        rec = [0] * 16
+        for k in range(4):
+            if k >= len(ch):
+                rec[3 * k:3 * k + 3] = [0xFFFF] * 3
+                continue
+            rec[3 * k:3 * k + 3] = ch[k][0]
+            if ch[k][1] >= 0:
+                rec[12 + k] = len(binary_of)
+                binary_of.append(ch[k][1])
+                level.append(level[wi] + 1)
+            else:
+                rec[12 + k] = ch[k][1] & 0xFFFFFFFF
+        for k in range(len(ch), 4):
+            rec[12 + k] = rec[12]
+        out.append(rec)
+        wi += 1
+    return np.array(out, dtype=np.uint32), max(level)
+
+
+@pytest.mark.parametrize("name", ["cornell", "material", "tess40"])
+def test_wide_nodes_are_the_collapse_of_the_quantised_tree(api, port, scenes_cache, name):
+    """64-byte 4-wide nodes (pt_scene_set_traversal 4): the GPU build equals the restated collapse record for record, for every
+    tree; every leaf is referenced exactly once and every wide node but the root exactly once."""
+    arr, gs, osc = _get(scenes_cache, api, port, name)
+    try:
+        for tree in (1, 2, 3):
+            gs.set_tree(tree)
+            qd = gs.bvh_export_quant()
+            wd = gs.bvh_export_wide()
+            want, depth = _collapse_wide(qd["q"], qd["step"])
+            assert wd["w"].shape == want.shape and wd["depth"] == depth, (tree, wd["w"].shape, want.shape, wd["depth"], depth)
+            assert np.array_equal(wd["w"], want), tree
+            refs, boxes = wd["w"][:, 12:].astype(np.int64), wd["w"][:, :12].reshape(-1, 4, 3)
+            real = ~np.all(boxes == 0xFFFF, axis=2)                       # not an empty slot
+            signed = np.where(refs >= 2**31, refs - 2**32, refs)
+            leaves = np.sort(~signed[real & (signed < 0)])
+            assert np.array_equal(leaves, np.arange(arr.n_tri)), tree
+            inner = np.sort(signed[real & (signed >= 0)])
+            assert np.array_equal(inner, np.arange(1, len(want))), tree
+    finally:
+        gs.set_tree(0)
+
+
 @pytest.mark.parametrize("name", ["cornell", "material", "tess40", "tess300"])
 def test_quantised_nodes_contain_the_exact_boxes(api, port, scenes_cache, name):
-    """32-byte nodes (pt_scene_set_traversal 3): every dequantised plane -- fma(q, step, lo), the traversal's expression,
+    """32-byte nodes (pt_scene_set_traversal 3): every dequantised plane -- fma(2^23 + q, step, base), the traversal's expression,
     evaluated here in float64 and rounded once like a float32 fma -- is on the outside of the exact plane, the child
     references are the exact node's, and a plane is never more than one grid step away."""
     arr, gs, osc = _get(scenes_cache, api, port, name)
@@ -896,8 +965,9 @@ def test_quantised_nodes_contain_the_exact_boxes(api, port, scenes_cache, name):
             planes = np.stack([w[:, 0] & 0xFFFF, w[:, 0] >> 16, w[:, 1] & 0xFFFF, w[:, 1] >> 16, w[:, 2] & 0xFFFF, w[:, 2] >> 16,
                                w[:, 3] & 0xFFFF, w[:, 3] >> 16, w[:, 4] & 0xFFFF, w[:, 4] >> 16, w[:, 5] & 0xFFFF, w[:, 5] >> 16], axis=1)
             axis = np.array([0, 1, 2, 0, 1, 2, 0, 1, 2, 0, 1, 2])
-            # q * step is exact in float64 (16 x 24 bits), the sum is rounded once to float32: the value of the fused multiply-add
-            deq = (planes.astype(np.float64) * step[axis] + lo[axis]).astype(np.float32)
+            # (2^23 + q) * step is exact in float64 (24 x 24 bits), the sum is rounded once to float32: the value of the fused
+            # multiply-add; `lo` is the addend of that expression (grid origin - 2^23 * step)
+            deq = ((planes.astype(np.float64) + 8388608.0) * step[axis] + lo[axis]).astype(np.float32)
             ex = np.stack([f[:, 0], f[:, 1], f[:, 2], f[:, 4], f[:, 5], f[:, 6], f[:, 8], f[:, 9], f[:, 10], f[:, 12], f[:, 13], f[:, 14]], axis=1)
             is_lo = np.array([1, 1, 1, 0, 0, 0, 1, 1, 1, 0, 0, 0], bool)
             assert np.all(deq[:, is_lo] <= ex[:, is_lo]) and np.all(deq[:, ~is_lo] >= ex[:, ~is_lo]), tree
@@ -998,7 +1068,7 @@ def test_schedule_perturbation(api, port, scenes_cache):
             tune = ",".join(f"{k}={v}" for k, v in spec.items())
             tried.append(tune)
             gs.set_tune(tune)
-            gs.set_traversal(int(rng.choice([1, 2, 3])))          # staged, global exact, global quantised
+            gs.set_traversal(int(rng.choice([1, 2, 3, 4])))       # staged, global exact, global quantised, global 4-wide
             gs.set_pipeline(2)
             g = gs.launch_host(p, accum=prev.copy())
             assert np.array_equal(g["accum"].view(np.uint32), o["accum"].view(np.uint32)), tune
