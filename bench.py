@@ -58,12 +58,17 @@ def _load_profile_facts():
 PROFILE_FACTS = _load_profile_facts()
 
 
-def algorithmic_work(c, nee):
-    flops = (FLOP_NODE * c["n_node"] + FLOP_TRI * c["n_tri"] + FLOP_SAMPLE * c["n_samples"] +
+# node step of the executed traversal: (flop, bytes) -- two exact boxes in 64 B, two quantised boxes in 32 B, four in 64 B
+NODE_STEP = {"binary": (FLOP_NODE, BYTES_NODE), "binary-quant": (FLOP_NODE, 32), "wide4-quant": (2 * FLOP_NODE, 64)}
+
+
+def algorithmic_work(c, nee, traversal="binary"):
+    flop_node, bytes_node = NODE_STEP.get(traversal, NODE_STEP["binary"])
+    flops = (flop_node * c["n_node"] + FLOP_TRI * c["n_tri"] + FLOP_SAMPLE * c["n_samples"] +
              FLOP_SEGMENT * c["n_radiance"] + sum(f * n for f, n in zip(FLOP_HIT, c["n_hit"])))
     if nee:
         flops += FLOP_NEE * (c["n_hit"][0] + c["n_hit"][1])
-    return flops, BYTES_NODE * c["n_node"] + BYTES_TRI * c["n_tri"]
+    return flops, bytes_node * c["n_node"] + BYTES_TRI * c["n_tri"]
 
 
 def make_scene_arrays(name):
@@ -347,8 +352,9 @@ def run_b200(args):
 
     counters, sched = counted(1)
     counters_exec, _ = counted(2)
+    traversal_exec = scene.last_launch_info()["traversal"]      # of the mode-2 launches = of the timed ones
     flops, tbytes = algorithmic_work(counters, nee)
-    flops_exec, tbytes_exec = algorithmic_work(counters_exec, nee)
+    flops_exec, tbytes_exec = algorithmic_work(counters_exec, nee, traversal_exec)
     rays = counters["n_radiance"] + counters["n_shadow"]
 
     # ---- end to end through the host-buffer entry point (pt_launch_host): pinned host buffers, H2D + D2H in the
@@ -460,7 +466,7 @@ def run_b200(args):
                            "; MEASURED_PEAKS.json has no such figure",
             "peak_nominal_fp32": fp32_nominal,
             "kernel_ms": kernel_ms,
-            "executed": exe,
+            "executed": dict(exe, traversal=traversal_exec),
             "specified": dict(spec, note="every ray through the tree named in config.pipeline.tree, exact nodes: the oracle's counts"),
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this workload
             "traffic": facts["dram_bytes"] if facts else None,
