@@ -42,7 +42,7 @@ struct WfTune {
                              // global memory (0 = all in shared memory).  C4: 672 -> 992 paths per CTA, +21 %
     int quant = -1;          // -1: follow Scene::traversal; 0 / 1: exact 64-byte / quantised 32-byte nodes for scenes in global memory
     int team = 1;            // sample teams (idle path slots take samples of a pixel another slot of their column is working on):
-                             // 0 off, 1 auto (scenes read from global memory), 2 on, 3 on + state dump when a team is left open
+                             // 0 off, 1 auto (scenes read from global memory whose pixels differ in cost or that are small shares, wavefront_launch), 2 on, 3 on + state dump when a team is left open
     int team_min = 2;        // ... when that pixel has at least this many samples left to hand out
     int affinity = 2;        // schedulers (warp % 4 < affinity) whose warps look at the traversal queues first, the others at the
                              // shading queues (instruction-cache locality per scheduler; C2 +5.7 % together with full_cols = 30)

@@ -1376,7 +1376,15 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     // launch is latency-bound, pixels differ widely in cost and the teams are worth +28 % (C3); a scene staged in shared
     // memory runs at its instruction-fetch limit and the kernel WITHOUT the team code is the faster one on full frames
     // (C2: the hot code exceeds the 32 KB L1.5 instruction cache either way; measurements in DESIGN.md 4.2b).
-    const bool team_on = !probe && (tune.team >= 2 || (tune.team == 1 && scene < 0));
+    // ... and within those, launches whose pixels differ widely in cost (more than one BSDF type, or deep paths) or that have
+    // fewer than four pixels per path slot (small shares of a frame: the tail is most of the launch).  A full frame of uniform
+    // pixels has no tail to speak of and runs 2 % faster without the team code (C4: 1736 -> 1770).
+    int dev_t = 0, sms_t = 0;
+    cudaGetDevice(&dev_t);
+    cudaDeviceGetAttribute(&sms_t, cudaDevAttrMultiProcessorCount, dev_t);
+    const uint64_t pixels = (uint64_t)lc.n_owned_tiles * 32u, slots = (uint64_t)wc.np * (uint64_t)sms_t;
+    const bool team_auto = scene < 0 && (s.n_bsdf_types > 1 || lc.max_depth > 16u || pixels < 4u * slots);
+    const bool team_on = !probe && (tune.team >= 2 || (tune.team == 1 && team_auto));
     wc.team = 0;
     wc.team_min = tune.team_min < 1 ? 1 : tune.team_min;
     wc.team_cap = lc.max_depth + 3u;                     // emission + one term per segment (maxDepth + 1 segments) + terminator
