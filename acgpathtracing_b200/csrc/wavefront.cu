@@ -1352,6 +1352,10 @@ cudaError_t wavefront_launch(Scene& s, const LaunchConst& lc, bool probe, cudaSt
     if (!smem_scene && trav == TRAV_WIDE) {
         // a wide step defers up to three children: the stack is sized from the wide tree's own depth
         cudaError_t we = build_wide_nodes(s, stream);
+        if (we == cudaErrorMemoryAllocation) {           // no room for the build's scratch: the binary quantised nodes will do
+            cudaGetLastError();
+            we = cudaSuccess;
+        }
         if (we != cudaSuccess) return we;
         if (s.d_wnodes && s.wnodes_tree == scene_tree(s) && 3u * s.wide_depth + 1u <= 255u) wc.stack_total = 3u * s.wide_depth + 1u;
         else trav = TRAV_QUANT;
