@@ -103,7 +103,8 @@ struct FetchGlobal {
     // expression the build checks its rounding with: lo planes never above, hi planes never below the exact box.
     const float4* qnodes;
     float3 q_lo, q_step;                                  // base = grid origin - 2^23 * step, and the step, per axis
-    bool prefetch = true;                                 // pull deferred children towards L2 (WfTune::prefetch)
+    bool prefetch = true;                                 // pull deferred children towards L2; the wavefront kernel sets it from
+                                                          // WfTune::prefetch (off: measured), the fallback kernels keep it
     __device__ __forceinline__ float qf_lo(uint32_t w) const { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7410)); }
     __device__ __forceinline__ float qf_hi(uint32_t w) const { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7432)); }
     __device__ __forceinline__ void qnode4(int i, float4& q0, float4& q1, float4& q2, float4& q3) const
