@@ -1190,20 +1190,14 @@ cudaError_t launch_wavefront(Scene& s, const LaunchConst& lc, const WfConst& wc,
 }  // namespace
 
 // How NODE batches read a scene that stays in global memory (pt_scene_set_traversal; PTB_TUNE quant= overrides).
-// Measured on B200: per-lane 256-bit loads of the exact 64-byte nodes are the fastest while the records fit
-// in L2 (C3); above that the 4-wide quantised nodes win (C4: +11 % over the 32-byte binary ones).  All are bit-identical in
-// their pixels.
+// Measured on B200: the 4-wide quantised nodes win from a few thousand triangles on (+5 % at 29 K, +8 % at
+// 180 K and 500 K, +12 % at 2 M triangles: C4) and tie with per-lane 256-bit loads of the exact 64-byte nodes on the smallest
+// scenes that are not staged (C3, 2592 triangles), which keep the exact nodes.  The boundary is the one of the trees: above
+// 8192 triangles (PLOC tree) the wide nodes.  All variants are bit-identical in their pixels.
 static int choose_trav(const Scene& s, const WfTune& tune)
 {
     // quantised nodes: not for launches that count the SPECIFIED work (their counters are those of the exact boxes)
-    static int l2_bytes = -1;
-    if (l2_bytes < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev) != cudaSuccess) l2_bytes = 0;
-    }
-    const bool larger_than_l2 = 64 * (size_t)s.n_nodes + 48 * (size_t)s.n_tris > (size_t)l2_bytes;
-    const bool wide = tune.quant >= 0 ? tune.quant == 2 : (s.traversal == 4 || (s.traversal == 0 && larger_than_l2));
+    const bool wide = tune.quant >= 0 ? tune.quant == 2 : (s.traversal == 4 || (s.traversal == 0 && s.n_tris > 8192u));
     const bool quant = tune.quant >= 0 ? tune.quant != 0 : s.traversal == 3;
     return ((!s.count_enabled || s.count_executed) && s.n_tris >= 2 && (quant || wide)) ? (wide ? TRAV_WIDE : TRAV_QUANT) : TRAV_DIRECT;
 }

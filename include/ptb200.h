@@ -211,7 +211,7 @@ int pt_scene_set_pipeline(pt_scene* scene, int pipeline);
 int pt_scene_set_tree(pt_scene* scene, int tree);
 int pt_scene_tree_in_use(const pt_scene* scene);   /* 1 LBVH, 2 SAH, 3 PLOC */
 /* How the render kernel reads the acceleration structure:
- *   0 = auto: 1, except 4 for scenes whose node and triangle records do not fit in L2 (the fastest measured on B200);
+ *   0 = auto: 1, except 4 for scenes of more than 8192 triangles (the fastest measured on B200: +5 % at 29 K triangles, +12 % at 2 M);
  *   1 = the exact 64-byte nodes of the tree in use, every lane fetches its own (from shared memory when the scene fits);
  *   2 = the same, but read from global memory whatever the scene's size (tests, A/B runs);
  *   3 = quantised nodes: 32 bytes per node (twelve 16-bit plane positions on the grid of the scene's bounding box,

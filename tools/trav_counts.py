@@ -10,10 +10,19 @@ from acgpathtracing_b200 import api
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="c4")
 ap.add_argument("--travs", default="2,3,4")
+ap.add_argument("--tess", type=int, default=0, help="use scenes.tessellated_scene(N) instead of the workload's scene")
+ap.add_argument("--spp", type=int, default=0)
 a = ap.parse_args()
 scene_name, w, h, spp, md, nee, imp, desc = bench.WORKLOADS[a.workload]
 torch.cuda.set_device(0)
-scene = api.Scene(bench.make_scene_arrays(scene_name))
+spp = a.spp or spp
+if a.tess:
+    from acgpathtracing_b200 import scenes
+    arr = scenes.tessellated_scene(a.tess)
+    print("tessellated_scene", a.tess, "triangles", arr.n_tri, flush=True)
+    scene = api.Scene(arr)
+else:
+    scene = api.Scene(bench.make_scene_arrays(scene_name))
 acc = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
 fb = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
 for trav in [int(x) for x in a.travs.split(",")]:
